@@ -1,0 +1,86 @@
+# hpc-patterns-b200 — native build (sm_100a only).
+#
+#   make            everything: static lib, CLIs in bin/, torch extension (_C.so)
+#   make cli        native CLIs only            make ext   torch extension only
+#   make omp_con    host-only concurrency bench (plain g++ -fopenmp, no CUDA)
+#   make sass       cuobjdump SASS listings -> docs/sass/
+#   make test       CPU test-suite (pytest -m "not gpu")
+#
+# Capability parity with the reference's build files: concurency/run_sycl.sh:6,
+# run_omp.sh:6-7, p2p/run.sh:3-5, aurora.mpich.miniapps/src/CMakeLists.txt.
+NVCC      ?= nvcc
+CXX       ?= g++
+PYTHON    ?= python
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fopenmp,-Wall -Icsrc
+CXXFLAGS  := -O2 -std=c++17 -fPIC -fopenmp -Wall -Wextra -Icsrc -I/usr/local/cuda/include
+BUILD     := build
+
+KERNEL_SRC := $(wildcard csrc/kernels/*.cu)
+COMMON_CPP := csrc/common/driver_api.cpp csrc/common/peer_mem.cpp
+CON_CPP    := csrc/concurency/driver.cpp csrc/concurency/backend_cpu.cpp
+LIB_OBJS   := $(KERNEL_SRC:csrc/%.cu=$(BUILD)/%.o) $(COMMON_CPP:csrc/%.cpp=$(BUILD)/%.o) \
+              $(CON_CPP:csrc/%.cpp=$(BUILD)/%.o) $(BUILD)/concurency/backend_cuda.o
+LIB        := $(BUILD)/libhpcp.a
+
+CLIS := bin/concurency bin/omp_con bin/peer2pear bin/topology bin/allreduce bin/interop_torchless \
+        bin/interop_driver
+
+.PHONY: all cli ext omp_con sass test clean
+all: cli ext
+cli: $(CLIS)
+
+$(BUILD)/%.o: csrc/%.cu
+	@mkdir -p $(dir $@)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(BUILD)/%.o: csrc/%.cpp
+	@mkdir -p $(dir $@)
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
+$(LIB): $(LIB_OBJS)
+	ar rcs $@ $^
+
+bin/concurency: csrc/concurency/main.cpp $(LIB)
+	@mkdir -p bin
+	$(NVCC) $(NVFLAGS) $< $(LIB) -o $@ -lgomp
+
+omp_con: bin/omp_con
+bin/omp_con: csrc/concurency/main.cpp csrc/concurency/driver.cpp csrc/concurency/backend_cpu.cpp \
+             csrc/concurency/backend_nocuda.cpp
+	@mkdir -p bin
+	$(CXX) -O2 -std=c++17 -fopenmp -Wall -Wextra $^ -o $@
+
+bin/peer2pear: csrc/p2p/peer2pear.cu $(LIB)
+	@mkdir -p bin
+	$(NVCC) $(NVFLAGS) $< $(LIB) -o $@ -lgomp
+
+bin/topology: csrc/p2p/topology.cpp csrc/p2p/topology_core.cpp
+	@mkdir -p bin
+	$(CXX) $(CXXFLAGS) $^ -o $@ -ldl
+
+bin/allreduce: csrc/miniapps/allreduce.cu $(LIB)
+	@mkdir -p bin
+	$(NVCC) $(NVFLAGS) $< $(LIB) -o $@ -lgomp
+
+bin/interop_torchless: csrc/interop/interop_runtime_streams.cu $(LIB)
+	@mkdir -p bin
+	$(NVCC) $(NVFLAGS) $< $(LIB) -o $@ -lgomp
+
+bin/interop_driver: csrc/interop/interop_driver_runtime.cu $(LIB)
+	@mkdir -p bin
+	$(NVCC) $(NVFLAGS) $< $(LIB) -o $@ -lgomp
+
+ext: $(LIB)
+	$(PYTHON) -m hpc_patterns_b200._build
+
+sass: $(LIB)
+	@mkdir -p docs/sass
+	for o in $(KERNEL_SRC:csrc/%.cu=$(BUILD)/%.o); do \
+	  cuobjdump -sass $$o > docs/sass/$$(basename $$o .o).sass; done
+
+test:
+	$(PYTHON) -m pytest tests -x -q -m "not gpu"
+
+clean:
+	rm -rf $(BUILD) bin hpc_patterns_b200/_C*.so

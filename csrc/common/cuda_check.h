@@ -1,0 +1,46 @@
+// Error handling shared by every native component.
+//
+// The reference aborts through `error()` + MPI_Finalize + exit(1)
+// (aurora.mpich.miniapps/src/allreduce/mpi-sycl/allreduce-mpi-sycl.cpp:79-86).
+// Here every CUDA runtime / driver failure becomes a C++ exception carrying
+// file:line and the CUDA error string, so CLIs can print + exit(1) and the
+// Python bindings can surface a RuntimeError instead of killing the process.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <sstream>
+#include <stdexcept>
+#include <string>
+
+namespace hpcp {
+
+struct CudaError : std::runtime_error {
+  cudaError_t code;
+  CudaError(cudaError_t c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+
+inline void cuda_check(cudaError_t e, const char* expr, const char* file, int line) {
+  if (e == cudaSuccess) return;
+  std::ostringstream os;
+  os << "CUDA error " << static_cast<int>(e) << " (" << cudaGetErrorName(e) << ": "
+     << cudaGetErrorString(e) << ") at " << file << ":" << line << " in `" << expr << "`";
+  // Clear the sticky-less error so the next call reports its own status.
+  (void)cudaGetLastError();
+  throw CudaError(e, os.str());
+}
+
+[[noreturn]] inline void fail(const std::string& msg, const char* file, int line) {
+  std::ostringstream os;
+  os << msg << " (" << file << ":" << line << ")";
+  throw std::runtime_error(os.str());
+}
+
+}  // namespace hpcp
+
+#define HPCP_CUDA(expr) ::hpcp::cuda_check((expr), #expr, __FILE__, __LINE__)
+#define HPCP_FAIL(msg) ::hpcp::fail((msg), __FILE__, __LINE__)
+#define HPCP_REQUIRE(cond, msg) \
+  do {                          \
+    if (!(cond)) HPCP_FAIL(msg); \
+  } while (0)

@@ -1,0 +1,122 @@
+// Host-callable launchers for every sm_100a kernel in the suite.
+//
+// Plain C++ (no torch, no MPI): raw device pointers + a cudaStream_t.  Both
+// front ends use exactly these entry points:
+//   * the native CLIs (csrc/p2p, csrc/concurency, csrc/miniapps) through the
+//     thread-per-rank runtime in csrc/common/rank_runtime.h, and
+//   * the PyTorch extension (csrc/bindings.cpp) for one-process-per-GPU runs
+//     launched by torchrun, where peer pointers come from CUDA IPC handles.
+//
+// Pointers named *_peer may be NVLink peer-mapped addresses; *_mc are NVSwitch
+// multicast addresses.  Every launcher returns after enqueueing on `stream`.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace hpcp {
+
+constexpr int kApiMaxRanks = 16;
+
+// How the bytes move inside a copy kernel.
+enum class CopyEngine : int {
+  kLdSt = 0,  // 128-bit ld.global / st.global from every thread of the grid
+  kTma = 1,   // one elected thread per CTA drives cp.async.bulk (TMA) through smem stages
+};
+
+struct CopyTuning {
+  int ctas = 0;      // 0 -> heuristic (multiple of the SM count)
+  int threads = 0;   // 0 -> heuristic
+  int unroll = 0;    // LdSt: 16-byte loads in flight per thread (1,2,4,8); 0 -> 4
+  int stage_kb = 0;  // Tma: smem stage size in KiB; 0 -> 16
+  int stages = 0;    // Tma: number of smem stages; 0 -> 8
+};
+
+// Optional prologue wait + epilogue signal attached to a data-moving kernel so a
+// whole "rendezvous send" (wait for receiver, move, tell receiver) is ONE launch.
+struct SyncOps {
+  const uint32_t* wait_flag = nullptr;  // local word to wait on before moving (may be null)
+  uint32_t wait_epoch = 0;
+  uint32_t* signal_flag = nullptr;      // word (usually on the peer) to publish after moving
+  uint32_t signal_epoch = 0;
+  uint32_t* ticket = nullptr;           // rank-local CTA ticket counter (needed iff signal_flag)
+  uint32_t ticket_base = 0;             // value of *ticket before this launch
+  uint64_t timeout_ns = 0;              // 0 = wait forever
+  uint32_t* status = nullptr;           // rank-local status word (see signal.cuh)
+};
+
+int device_sm_count(int device);
+
+// ---------------------------------------------------------------- signals ----
+void launch_signal(uint32_t* flag, uint32_t epoch, cudaStream_t stream);
+void launch_wait(const uint32_t* flag, uint32_t epoch, uint64_t timeout_ns, uint32_t* status,
+                 cudaStream_t stream);
+// In-kernel barrier across `world` GPUs: writes `epoch` into slot [rank] of every
+// peer's barrier section, then waits until all slots of the local pad reach it.
+void launch_barrier_all(uint32_t* const* pads /*[world], peer-mapped*/, int rank, int world,
+                        uint32_t epoch, uint64_t timeout_ns, uint32_t* status,
+                        cudaStream_t stream);
+
+// ------------------------------------------------------------------- p2p ----
+// dst[0:bytes) = src[0:bytes).  Either side may be a peer-mapped pointer:
+// put = local src -> peer dst, get = peer src -> local dst.  Returns the number
+// of CTAs launched (the caller advances its ticket counter by it).
+int launch_copy(void* dst, const void* src, size_t bytes, bool src_is_peer, CopyEngine engine,
+                const CopyTuning& tune, const SyncOps& sync, int device, cudaStream_t stream);
+
+// Payload: word[i] = mix32(i*2654435761 ^ seed) — a seeded bijection of the index,
+// generated on the device (↔ fill_randomly, p2p/peer2pear.cpp:8-17).
+void launch_fill_pattern(uint32_t* dst, size_t n_words, uint32_t seed, cudaStream_t stream);
+// Exact receiver-side check (↔ sorted-sum check p2p/peer2pear.cpp:55-63, made exact):
+// counts mismatching words into *mismatch_count and accumulates the 64-bit word sum.
+// If wait_flag != null each CTA first waits for the arrival epoch (fused wait+verify).
+void launch_verify_pattern(const uint32_t* data, size_t n_words, uint32_t seed,
+                           unsigned long long* mismatch_count, unsigned long long* word_sum,
+                           const uint32_t* wait_flag, uint32_t wait_epoch, uint64_t timeout_ns,
+                           uint32_t* status, cudaStream_t stream);
+
+// ------------------------------------------------ fused triad + P2P put ----
+// a = b + s*c computed once and written BOTH to a_local and (over NVLink) to
+// a_peer, then the arrival epoch is published on the peer and (optionally) the
+// local arrival word is awaited — compute, put and sync in one launch.
+struct TriadPutArgs {
+  float* a_local = nullptr;
+  float* a_peer = nullptr;  // may equal nullptr -> plain triad (the unfused compute)
+  const float* b = nullptr;
+  const float* c = nullptr;
+  float s = 0.f;
+  size_t n = 0;             // elements, multiple of 4
+};
+int launch_triad_put(const TriadPutArgs& args, CopyEngine engine, const CopyTuning& tune,
+                     const SyncOps& sync, const uint32_t* arrive_flag, uint32_t arrive_epoch,
+                     int device, cudaStream_t stream);
+void launch_fill_triad_inputs(float* b, float* c, size_t n, int rank, cudaStream_t stream);
+void launch_verify_triad(const float* a, size_t n, int src_rank, float s,
+                         unsigned long long* mismatch_count, cudaStream_t stream);
+
+// ------------------------------------------- fused concurrency "megakernel" ----
+// One persistent launch that executes a whole command group of the concurrency
+// benchmark: CTAs are partitioned between the commands, so compute and copies
+// overlap by construction instead of by the runtime's stream scheduling.
+enum class FusedKind : int { kBusy = 0, kTriad = 1, kCopy = 2 };
+struct FusedCommand {
+  FusedKind kind = FusedKind::kBusy;
+  size_t n = 0;              // work-items (busy) / elements (triad, copy)
+  size_t tripcount = 0;      // busy only
+  void* dst = nullptr;       // copy: destination (device, peer, pinned-host or managed)
+  const void* src = nullptr; // copy: source
+  float* a = nullptr;        // busy: output; triad: a
+  const float* b = nullptr;
+  const float* c = nullptr;
+  float s = 3.0f;
+  int ctas = 0;              // 0 -> heuristic share of the SMs
+};
+constexpr int kFusedMaxCommands = 8;
+// Returns the total number of CTAs launched.
+int launch_fused_bench(const FusedCommand* cmds, int n_cmds, CopyEngine engine,
+                       const CopyTuning& tune, int device, cudaStream_t stream);
+// The stand-alone busy-wait command (N work-items x 64*tripcount dependent FMAs).
+void launch_busy_wait(float* out, size_t n_items, size_t tripcount, cudaStream_t stream);
+
+}  // namespace hpcp

@@ -1,0 +1,305 @@
+// K-fused-triad-put: the suite's flagship fused compute + communication kernel.
+//
+// The reference never overlaps compute with communication: its miniapp runs
+// "kernel; wait; MPI_Send/Recv; wait" (allreduce-mpi-sycl.cpp:176-181, whose
+// header calls the kernel "triad + send/recv", :1-4) and its concurrency bench
+// only asks the runtime to overlap separately submitted commands
+// (concurency/bench_sycl.cpp:84-121).  Here the stream triad
+//        a[i] = b[i] + s * c[i]
+// and the P2P put of `a` to a neighbour GPU are ONE kernel: each result vector
+// is produced once in registers (LdSt engine) or once in shared memory (TMA
+// engine) and written to BOTH the local array and the peer's receive buffer
+// over NVLink.  The put costs no extra HBM read, there is no second launch, no
+// MPI/NCCL/cudaMemcpy, and arrival is published to the peer with a
+// release-scoped epoch word in the same launch.
+//
+// TMA engine layout (warp specialised, one CTA per SM):
+//   warp 0 / lane 0 : DMA thread — cp.async.bulk b,c tiles -> smem stage
+//                     (mbarrier complete_tx), later cp.async.bulk smem -> a_local
+//                     and smem -> a_peer for the computed tile.
+//   warps 1..4      : math — wait full[stage], a = b + s*c in place in smem,
+//                     fence.proxy.async, arrive on computed[stage].
+#include "api.h"
+
+#include <algorithm>
+
+#include "../common/cuda_check.h"
+#include "../common/signal.cuh"
+
+namespace hpcp {
+
+namespace {
+
+__device__ __forceinline__ float4 triad4(const float4& b, const float4& c, float s) {
+  return make_float4(fmaf(s, c.x, b.x), fmaf(s, c.y, b.y), fmaf(s, c.z, b.z), fmaf(s, c.w, b.w));
+}
+
+__device__ __forceinline__ float4 ld_f4_stream(const float4* p) {
+  const uint4 v = ptx::ld_stream_v4(reinterpret_cast<const uint4*>(p));
+  return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z),
+                     __uint_as_float(v.w));
+}
+__device__ __forceinline__ void st_f4_stream(float4* p, const float4& f) {
+  ptx::st_stream_v4(reinterpret_cast<uint4*>(p),
+                    make_uint4(__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z),
+                               __float_as_uint(f.w)));
+}
+
+__device__ __forceinline__ bool cta_prologue_wait(const SyncOps& sync) {
+  if (sync.wait_flag == nullptr) return true;
+  __shared__ int ok_s;
+  if (threadIdx.x == 0)
+    ok_s = wait_epoch(sync.wait_flag, sync.wait_epoch, sync.timeout_ns, sync.status) ? 1 : 0;
+  __syncthreads();
+  return ok_s != 0;
+}
+
+// Publish "my put landed" on the peer (last CTA) and, on CTA 0, wait for the
+// neighbour's put into *my* buffer, so kernel completion == exchange complete.
+__device__ __forceinline__ void cta_epilogue(const SyncOps& sync, const uint32_t* arrive_flag,
+                                             uint32_t arrive_epoch) {
+  if (sync.ticket != nullptr)
+    last_cta_publish(sync.ticket, sync.ticket_base + gridDim.x, sync.signal_flag,
+                     sync.signal_epoch);
+  if (arrive_flag != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
+    wait_epoch(arrive_flag, arrive_epoch, sync.timeout_ns, sync.status);
+}
+
+// ------------------------------------------------------------ LdSt engine ----
+template <int U, bool kPut>
+__global__ void __launch_bounds__(512)
+    triad_put_ldst_kernel(float4* __restrict__ a_local, float4* __restrict__ a_peer,
+                          const float4* __restrict__ b, const float4* __restrict__ c, float s,
+                          size_t nvec, SyncOps sync, const uint32_t* arrive_flag,
+                          uint32_t arrive_epoch) {
+  if (!cta_prologue_wait(sync)) return;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + (U - 1) * stride < nvec; i += U * stride) {
+    float4 vb[U], vc[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      vb[k] = ld_f4_stream(b + i + k * stride);
+      vc[k] = ld_f4_stream(c + i + k * stride);
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const float4 va = triad4(vb[k], vc[k], s);
+      st_f4_stream(a_local + i + k * stride, va);
+      if (kPut) st_f4_stream(a_peer + i + k * stride, va);
+    }
+  }
+  for (; i < nvec; i += stride) {
+    const float4 va = triad4(ld_f4_stream(b + i), ld_f4_stream(c + i), s);
+    st_f4_stream(a_local + i, va);
+    if (kPut) st_f4_stream(a_peer + i, va);
+  }
+  cta_epilogue(sync, arrive_flag, arrive_epoch);
+}
+
+// ------------------------------------------------------------- TMA engine ----
+constexpr int kMathWarps = 4;
+constexpr int kTmaThreads = 32 * (1 + kMathWarps);
+
+// Dynamic smem: [stages][2][tile_bytes] (b tile, c tile) | full[stages] | computed[stages]
+template <bool kPut>
+__global__ void __launch_bounds__(kTmaThreads)
+    triad_put_tma_kernel(float* __restrict__ a_local, float* __restrict__ a_peer,
+                         const float* __restrict__ b, const float* __restrict__ c, float s,
+                         size_t n_bytes /*multiple of 16*/, uint32_t tile_bytes, int stages,
+                         SyncOps sync, const uint32_t* arrive_flag, uint32_t arrive_epoch) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const size_t stage_stride = 2 * static_cast<size_t>(tile_bytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * stage_stride);
+  uint64_t* computed = full + stages;
+
+  if (!cta_prologue_wait(sync)) return;
+
+  if (threadIdx.x == 0) {
+    for (int st = 0; st < stages; ++st) {
+      ptx::mbar_init(&full[st], 1);
+      ptx::mbar_init(&computed[st], kMathWarps);
+    }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+
+  const size_t tiles_total = (n_bytes + tile_bytes - 1) / tile_bytes;
+  const size_t n = tiles_total > blockIdx.x
+                       ? (tiles_total - blockIdx.x + gridDim.x - 1) / gridDim.x
+                       : 0;
+  auto tile_off = [&](size_t j) {
+    return (static_cast<size_t>(blockIdx.x) + j * gridDim.x) * tile_bytes;
+  };
+  auto tile_len = [&](size_t j) {
+    const size_t off = tile_off(j);
+    return static_cast<uint32_t>(n_bytes - off < tile_bytes ? n_bytes - off : tile_bytes);
+  };
+  const unsigned char* bb = reinterpret_cast<const unsigned char*>(b);
+  const unsigned char* cb = reinterpret_cast<const unsigned char*>(c);
+  unsigned char* alb = reinterpret_cast<unsigned char*>(a_local);
+  unsigned char* apb = reinterpret_cast<unsigned char*>(a_peer);
+
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    if (threadIdx.x == 0) {
+      auto issue_load = [&](size_t j) {
+        const int st = static_cast<int>(j % stages);
+        const uint32_t len = tile_len(j);
+        unsigned char* sb = smem + st * stage_stride;
+        ptx::mbar_arrive_expect_tx(&full[st], 2 * len);
+        ptx::bulk_g2s(sb, bb + tile_off(j), len, &full[st]);
+        ptx::bulk_g2s(sb + tile_bytes, cb + tile_off(j), len, &full[st]);
+      };
+      const size_t lookahead = static_cast<size_t>(stages - 1);
+      for (size_t j = 0; j < lookahead && j < n; ++j) issue_load(j);
+      for (size_t j = 0; j < n; ++j) {
+        const int st = static_cast<int>(j % stages);
+        ptx::mbar_wait(&computed[st], static_cast<uint32_t>((j / stages) & 1));
+        const unsigned char* sa = smem + st * stage_stride;  // `a` overwrote the b tile
+        ptx::bulk_s2g(alb + tile_off(j), sa, tile_len(j));
+        if (kPut) ptx::bulk_s2g(apb + tile_off(j), sa, tile_len(j));
+        ptx::bulk_commit();
+        const size_t nxt = j + lookahead;
+        if (nxt < n) {
+          ptx::bulk_wait_read<1>();
+          issue_load(nxt);
+        }
+      }
+      ptx::bulk_wait<0>();
+      asm volatile("fence.proxy.async;" ::: "memory");
+    }
+  } else {
+    const int mt = threadIdx.x - 32;  // 0 .. 32*kMathWarps-1
+    for (size_t j = 0; j < n; ++j) {
+      const int st = static_cast<int>(j % stages);
+      ptx::mbar_wait(&full[st], static_cast<uint32_t>((j / stages) & 1));
+      float4* sb = reinterpret_cast<float4*>(smem + st * stage_stride);
+      const float4* sc = reinterpret_cast<const float4*>(smem + st * stage_stride + tile_bytes);
+      const uint32_t nv = tile_len(j) / 16;
+      for (uint32_t v = mt; v < nv; v += 32 * kMathWarps) sb[v] = triad4(sb[v], sc[v], s);
+      ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to TMA store
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) ptx::mbar_arrive(&computed[st]);
+    }
+  }
+  cta_epilogue(sync, arrive_flag, arrive_epoch);
+}
+
+// ---------------------------------------------------- inputs and checking ----
+__device__ __forceinline__ float triad_b(size_t i, int rank) {
+  return static_cast<float>((i + 17u * static_cast<unsigned>(rank)) & 1023u);
+}
+__device__ __forceinline__ float triad_c(size_t i, int rank) {
+  return static_cast<float>((i * 3u + static_cast<unsigned>(rank)) & 7u);
+}
+
+__global__ void fill_triad_kernel(float* __restrict__ b, float* __restrict__ c, size_t n,
+                                  int rank) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    b[i] = triad_b(i, rank);
+    c[i] = triad_c(i, rank);
+  }
+}
+
+__global__ void verify_triad_kernel(const float* __restrict__ a, size_t n, int src_rank, float s,
+                                    unsigned long long* mismatch_count) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  unsigned long long bad = 0;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float want = fmaf(s, triad_c(i, src_rank), triad_b(i, src_rank));
+    bad += (__ldcg(a + i) != want);
+  }
+  for (int off = 16; off > 0; off >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, off);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatch_count, bad);
+}
+
+}  // namespace
+
+int launch_triad_put(const TriadPutArgs& args, CopyEngine engine, const CopyTuning& tune,
+                     const SyncOps& sync, const uint32_t* arrive_flag, uint32_t arrive_epoch,
+                     int device, cudaStream_t stream) {
+  HPCP_REQUIRE(args.n % 4 == 0, "triad_put: n must be a multiple of 4 elements");
+  HPCP_REQUIRE(sync.signal_flag == nullptr || sync.ticket != nullptr,
+               "triad_put: a signal needs a ticket counter");
+  const int sms = device_sm_count(device);
+  const size_t nvec = args.n / 4;
+  const bool put = args.a_peer != nullptr;
+  int ctas = 0;
+  if (engine == CopyEngine::kLdSt) {
+    const int threads = tune.threads > 0 ? tune.threads : 512;
+    const int unroll = tune.unroll > 0 ? tune.unroll : 2;
+    const size_t per_cta = static_cast<size_t>(threads) * unroll;
+    const size_t want = std::max<size_t>(1, (nvec + per_cta - 1) / per_cta);
+    const int cap = tune.ctas > 0 ? tune.ctas : sms * 2;
+    ctas = static_cast<int>(std::min<size_t>(want, static_cast<size_t>(cap)));
+    float4* al = reinterpret_cast<float4*>(args.a_local);
+    float4* ap = reinterpret_cast<float4*>(args.a_peer);
+    const float4* b = reinterpret_cast<const float4*>(args.b);
+    const float4* c = reinterpret_cast<const float4*>(args.c);
+#define HPCP_TRIAD_LAUNCH(U)                                                                     \
+  do {                                                                                           \
+    if (put)                                                                                     \
+      triad_put_ldst_kernel<U, true><<<ctas, threads, 0, stream>>>(al, ap, b, c, args.s, nvec,   \
+                                                                   sync, arrive_flag,            \
+                                                                   arrive_epoch);                \
+    else                                                                                         \
+      triad_put_ldst_kernel<U, false><<<ctas, threads, 0, stream>>>(al, ap, b, c, args.s, nvec,  \
+                                                                    sync, arrive_flag,           \
+                                                                    arrive_epoch);               \
+  } while (0)
+    switch (unroll) {
+      case 1: HPCP_TRIAD_LAUNCH(1); break;
+      case 4: HPCP_TRIAD_LAUNCH(4); break;
+      default: HPCP_TRIAD_LAUNCH(2); break;
+    }
+#undef HPCP_TRIAD_LAUNCH
+  } else {
+    const uint32_t tile_bytes = static_cast<uint32_t>((tune.stage_kb > 0 ? tune.stage_kb : 16) * 1024);
+    const int stages = tune.stages > 0 ? tune.stages : 6;
+    HPCP_REQUIRE(stages >= 2, "triad_put: TMA engine needs >= 2 stages");
+    const size_t smem = static_cast<size_t>(stages) * 2 * tile_bytes + static_cast<size_t>(stages) * 16;
+    HPCP_REQUIRE(smem <= 227 * 1024, "triad_put: TMA stages exceed 227 KiB of shared memory");
+    const size_t n_bytes = args.n * sizeof(float);
+    const size_t tiles = std::max<size_t>(1, (n_bytes + tile_bytes - 1) / tile_bytes);
+    const int per_sm = std::max(1, static_cast<int>((227 * 1024) / smem));
+    const int cap = tune.ctas > 0 ? tune.ctas : sms * per_sm;
+    ctas = static_cast<int>(std::min<size_t>(tiles, static_cast<size_t>(cap)));
+    if (put) {
+      HPCP_CUDA(cudaFuncSetAttribute(triad_put_tma_kernel<true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+      triad_put_tma_kernel<true><<<ctas, kTmaThreads, smem, stream>>>(
+          args.a_local, args.a_peer, args.b, args.c, args.s, n_bytes, tile_bytes, stages, sync,
+          arrive_flag, arrive_epoch);
+    } else {
+      HPCP_CUDA(cudaFuncSetAttribute(triad_put_tma_kernel<false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(smem)));
+      triad_put_tma_kernel<false><<<ctas, kTmaThreads, smem, stream>>>(
+          args.a_local, args.a_peer, args.b, args.c, args.s, n_bytes, tile_bytes, stages, sync,
+          arrive_flag, arrive_epoch);
+    }
+  }
+  HPCP_CUDA(cudaGetLastError());
+  return ctas;
+}
+
+void launch_fill_triad_inputs(float* b, float* c, size_t n, int rank, cudaStream_t stream) {
+  const int threads = 256;
+  const int ctas = static_cast<int>(std::min<size_t>((n + threads - 1) / threads, 148 * 8));
+  fill_triad_kernel<<<std::max(ctas, 1), threads, 0, stream>>>(b, c, n, rank);
+  HPCP_CUDA(cudaGetLastError());
+}
+
+void launch_verify_triad(const float* a, size_t n, int src_rank, float s,
+                         unsigned long long* mismatch_count, cudaStream_t stream) {
+  const int threads = 256;
+  const int ctas = static_cast<int>(std::min<size_t>((n + threads - 1) / threads, 148 * 8));
+  verify_triad_kernel<<<std::max(ctas, 1), threads, 0, stream>>>(a, n, src_rank, s,
+                                                                mismatch_count);
+  HPCP_CUDA(cudaGetLastError());
+}
+
+}  // namespace hpcp
