@@ -9,15 +9,18 @@
 # Capability parity with the reference's build files: concurency/run_sycl.sh:6,
 # run_omp.sh:6-7, p2p/run.sh:3-5, aurora.mpich.miniapps/src/CMakeLists.txt.
 NVCC      ?= nvcc
-CXX       ?= g++
+# The image exports CXX=/opt/gcc/bin/g++, a wrapper that cannot link -fopenmp;
+# always use the system compiler (override with HOSTCXX=...).
+HOSTCXX   ?= $(shell command -v /usr/bin/g++ || echo g++)
+override CXX := $(HOSTCXX)
 PYTHON    ?= python
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fopenmp,-Wall -Icsrc
+NVFLAGS   := -ccbin $(HOSTCXX) $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fopenmp,-Wall -Icsrc
 CXXFLAGS  := -O2 -std=c++17 -fPIC -fopenmp -Wall -Wextra -Icsrc -I/usr/local/cuda/include
 BUILD     := build
 
 KERNEL_SRC := $(wildcard csrc/kernels/*.cu)
-COMMON_CPP := csrc/common/driver_api.cpp csrc/common/peer_mem.cpp
+COMMON_CPP := csrc/common/driver_api.cpp csrc/common/peer_mem.cpp csrc/p2p/topology_core.cpp
 CON_CPP    := csrc/concurency/driver.cpp csrc/concurency/backend_cpu.cpp
 LIB_OBJS   := $(KERNEL_SRC:csrc/%.cu=$(BUILD)/%.o) $(COMMON_CPP:csrc/%.cpp=$(BUILD)/%.o) \
               $(CON_CPP:csrc/%.cpp=$(BUILD)/%.o) $(BUILD)/concurency/backend_cuda.o
@@ -57,11 +60,13 @@ bin/peer2pear: csrc/p2p/peer2pear.cu $(LIB)
 
 bin/topology: csrc/p2p/topology.cpp csrc/p2p/topology_core.cpp
 	@mkdir -p bin
-	$(CXX) $(CXXFLAGS) $^ -o $@ -ldl
+	$(CXX) $(CXXFLAGS) -DHPCP_TOPOLOGY_WITH_CUDA $^ -o $@ -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
 
 bin/allreduce: csrc/miniapps/allreduce.cu $(LIB)
 	@mkdir -p bin
 	$(NVCC) $(NVFLAGS) $< $(LIB) -o $@ -lgomp
+	ln -sf allreduce bin/allreduce.float
+	ln -sf allreduce bin/allreduce.int
 
 bin/interop_torchless: csrc/interop/interop_runtime_streams.cu $(LIB)
 	@mkdir -p bin

@@ -70,11 +70,8 @@ void* alloc_bytes(size_t bytes, AllocKind kind, int device, bool zero) {
       HPCP_CUDA(cudaMallocManaged(&p, n, cudaMemAttachGlobal));
       if (zero) HPCP_CUDA(cudaMemset(p, 0, n));
       // Keep the pages resident on the owning GPU so peers reach them over NVLink.
-      cudaMemLocation loc{};
-      loc.type = cudaMemLocationTypeDevice;
-      loc.id = device;
-      (void)cudaMemAdvise(p, n, cudaMemAdviseSetPreferredLocation, loc);
-      (void)cudaMemPrefetchAsync(p, n, loc, 0, 0);
+      (void)cudaMemAdvise(p, n, cudaMemAdviseSetPreferredLocation, device);
+      (void)cudaMemPrefetchAsync(p, n, device, 0);
       (void)cudaGetLastError();
       break;
     }

@@ -119,4 +119,75 @@ int launch_fused_bench(const FusedCommand* cmds, int n_cmds, CopyEngine engine,
 // The stand-alone busy-wait command (N work-items x 64*tripcount dependent FMAs).
 void launch_busy_wait(float* out, size_t n_items, size_t tripcount, cudaStream_t stream);
 
+// ------------------------------------------------------ allreduce miniapp ----
+enum class ElemType : int { kFloat = 0, kInt = 1 };
+
+// VA = a, VB = b, VC = c (↔ Initialize, allreduce-mpi-sycl.cpp:33-41). Any pointer may be null.
+void launch_init3(void* va, void* vb, void* vc, size_t n, double a, double b, double c,
+                  ElemType type, cudaStream_t stream);
+// VC += VA, the unfused kernel of the reference pattern (↔ Accumulate, :26-31).
+void launch_accumulate(const void* va, void* vc, size_t n, ElemType type, cudaStream_t stream);
+// Counts elements with |v - expected| >= 1e-6 (↔ the assert loop, :192-204).
+void launch_count_mismatch(const void* v, size_t n, double expected, ElemType type,
+                           unsigned long long* count, cudaStream_t stream);
+
+// Fused ring "rotate + accumulate" allreduce: all P-1 exchange steps and all P
+// accumulations in ONE launch per rank.  Hop t of chunk c is read once, added
+// into VC and forwarded to the right neighbour's slot over NVLink; arrival is
+// signalled per chunk, so communication, accumulation and forwarding pipeline
+// across the ring without any host involvement.
+struct RingArgs {
+  const void* va = nullptr;       // local input block (hop 0)
+  void* vc = nullptr;             // local accumulator (VC += every hop)
+  void* slots_local = nullptr;    // (world-1) * n elements, written by the left neighbour
+  void* slots_right = nullptr;    // peer-mapped: the right neighbour's slots
+  uint32_t* arrived_local = nullptr;  // n_chunks words, written by the left neighbour
+  uint32_t* arrived_right = nullptr;  // peer-mapped: right neighbour's arrival words
+  int world = 0;
+  size_t n = 0;                   // elements per rank, multiple of 4
+  size_t chunk_elems = 0;         // 0 -> 8192 (32 KiB); multiple of 4
+  uint32_t epoch_base = 0;        // arrival words count up: base + hop
+  uint64_t timeout_ns = 0;
+  uint32_t* status = nullptr;
+};
+size_t ring_num_chunks(size_t n, size_t chunk_elems);
+void launch_ring_allreduce(const RingArgs& args, ElemType type, int ctas, int device,
+                           cudaStream_t stream);
+
+// One-kernel "collective" allreduce (the miniapp's -a path, ↔ MPI_Allreduce :61-67).
+// two-shot over peer mappings: rank r reduces slice r by loading it from every
+// rank's VA and stores the sum into every rank's VC, then a cross-GPU barrier.
+struct TwoShotArgs {
+  const void* va[kApiMaxRanks] = {nullptr};  // peer-mapped inputs of every rank
+  void* vc[kApiMaxRanks] = {nullptr};        // peer-mapped outputs of every rank
+  uint32_t* pads[kApiMaxRanks] = {nullptr};  // signal pads of every rank
+  uint32_t* ticket = nullptr;
+  uint32_t ticket_base = 0;
+  int rank = 0;
+  int world = 0;
+  size_t n = 0;                              // elements, multiple of 4 * world
+  uint32_t barrier_epoch = 0;
+  uint64_t timeout_ns = 0;
+  uint32_t* status = nullptr;
+};
+int launch_allreduce_two_shot(const TwoShotArgs& args, ElemType type, int ctas, int device,
+                              cudaStream_t stream);
+// NVLS: multimem.ld_reduce over the multicast mapping of VA for slice `rank`,
+// multimem.st of the sum into the multicast mapping of VC (in-switch reduce + broadcast).
+struct NvlsArgs {
+  const void* va_mc = nullptr;
+  void* vc_mc = nullptr;
+  uint32_t* pads[kApiMaxRanks] = {nullptr};
+  uint32_t* ticket = nullptr;
+  uint32_t ticket_base = 0;
+  int rank = 0;
+  int world = 0;
+  size_t n = 0;
+  uint32_t barrier_epoch = 0;
+  uint64_t timeout_ns = 0;
+  uint32_t* status = nullptr;
+};
+int launch_allreduce_nvls(const NvlsArgs& args, ElemType type, int ctas, int device,
+                          cudaStream_t stream);
+
 }  // namespace hpcp

@@ -1,0 +1,378 @@
+// Allreduce miniapp kernels (float and int).
+//
+// Reference pattern (aurora.mpich.miniapps/src/allreduce/mpi-sycl/allreduce-mpi-sycl.cpp:173-182):
+//     Accumulate(VA,VC).wait();
+//     for s in 1..P-1: { SendRecvRing(VA -> right, VB <- left); swap(VA,VB); Accumulate(VA,VC).wait(); }
+// i.e. kernel -> host wait -> blocking MPI -> host wait, P-1 times: zero overlap.
+//
+// K-ring (this file) keeps the same data movement — every rank forwards a full
+// N-element block to its right neighbour P-1 times and accumulates P blocks —
+// but as ONE persistent kernel per rank: for hop t and chunk c a CTA
+//   waits (acquire) on arrival word c   -> the left neighbour wrote hop t of chunk c
+//   reads the chunk ONCE                -> adds it into VC and, if t < P-1,
+//   stores it into the right neighbour's slot t over NVLink (peer-mapped pointer)
+//   publishes (release) arrival word c  on the right neighbour.
+// Accumulate, send, receive and the step barrier are fused; steps pipeline
+// across the ring chunk by chunk.  Slots are (P-1) full blocks so no ack channel
+// is needed (896 MiB at P=8, N=2^25 floats — small against 180 GB of HBM3e).
+//
+// The `-a` path (↔ MPI_Allreduce, :61-67) is a one-launch collective: two-shot
+// over peer mappings, or NVLS (multimem.ld_reduce / multimem.st) when a
+// multicast mapping exists.
+#include "api.h"
+
+#include <algorithm>
+#include <type_traits>
+
+#include "../common/cuda_check.h"
+#include "../common/signal.cuh"
+
+namespace hpcp {
+
+namespace {
+
+template <typename T>
+struct Vec4;
+template <>
+struct Vec4<float> {
+  static __device__ __forceinline__ uint4 add(const uint4& a, const uint4& b) {
+    return make_uint4(__float_as_uint(__uint_as_float(a.x) + __uint_as_float(b.x)),
+                      __float_as_uint(__uint_as_float(a.y) + __uint_as_float(b.y)),
+                      __float_as_uint(__uint_as_float(a.z) + __uint_as_float(b.z)),
+                      __float_as_uint(__uint_as_float(a.w) + __uint_as_float(b.w)));
+  }
+};
+template <>
+struct Vec4<int> {
+  static __device__ __forceinline__ uint4 add(const uint4& a, const uint4& b) {
+    return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+};
+
+// ------------------------------------------------------------ small kernels ----
+template <typename T>
+__global__ void init3_kernel(T* va, T* vb, T* vc, size_t n, T a, T b, T c) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (va) va[i] = a;
+    if (vb) vb[i] = b;
+    if (vc) vc[i] = c;
+  }
+}
+
+template <typename T>
+__global__ void accumulate_kernel(const uint4* __restrict__ va, uint4* __restrict__ vc, size_t nvec,
+                                  const T* va_tail, T* vc_tail, size_t tail) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride)
+    vc[i] = Vec4<T>::add(vc[i], ptx::ld_weak_v4(va + i));
+  if (blockIdx.x == 0 && threadIdx.x < tail) vc_tail[threadIdx.x] += va_tail[threadIdx.x];
+}
+
+template <typename T>
+__global__ void count_mismatch_kernel(const T* __restrict__ v, size_t n, double expected,
+                                      unsigned long long* count) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  unsigned long long bad = 0;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double d = static_cast<double>(__ldcg(v + i)) - expected;
+    bad += !(d < 1e-6 && d > -1e-6);
+  }
+  for (int off = 16; off > 0; off >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, off);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(count, bad);
+}
+
+// ------------------------------------------------------------------ K-ring ----
+struct RingDev {
+  const uint4* va;
+  uint4* vc;
+  const uint4* slots_local;
+  uint4* slots_right;
+  uint32_t* arrived_local;
+  uint32_t* arrived_right;
+  int world;
+  size_t nvec;        // vectors per block
+  size_t chunk_vec;   // vectors per chunk
+  size_t n_chunks;
+  uint32_t epoch_base;
+  uint64_t timeout_ns;
+  uint32_t* status;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(512) ring_allreduce_kernel(const __grid_constant__ RingDev a) {
+  __shared__ int ok_s;
+  for (int t = 0; t < a.world; ++t) {
+    const uint4* src = t == 0 ? a.va : a.slots_local + static_cast<size_t>(t - 1) * a.nvec;
+    uint4* fwd = t < a.world - 1 ? a.slots_right + static_cast<size_t>(t) * a.nvec : nullptr;
+    for (size_t c = blockIdx.x; c < a.n_chunks; c += gridDim.x) {
+      if (t > 0) {
+        if (threadIdx.x == 0)
+          ok_s = wait_epoch(a.arrived_local + c, a.epoch_base + t, a.timeout_ns, a.status) ? 1 : 0;
+        __syncthreads();
+        if (!ok_s) return;  // peer hung: status word set, drain
+      }
+      const size_t begin = c * a.chunk_vec;
+      const size_t end = begin + a.chunk_vec < a.nvec ? begin + a.chunk_vec : a.nvec;
+      size_t i = begin + threadIdx.x;
+      for (; i + 3 * blockDim.x < end; i += 4 * blockDim.x) {
+        uint4 x[4], acc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x[k] = ptx::ld_weak_v4(src + i + k * blockDim.x);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] = a.vc[i + k * blockDim.x];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (fwd) ptx::st_stream_v4(fwd + i + k * blockDim.x, x[k]);
+          a.vc[i + k * blockDim.x] = Vec4<T>::add(acc[k], x[k]);
+        }
+      }
+      for (; i < end; i += blockDim.x) {
+        const uint4 x = ptx::ld_weak_v4(src + i);
+        if (fwd) ptx::st_stream_v4(fwd + i, x);
+        a.vc[i] = Vec4<T>::add(a.vc[i], x);
+      }
+      __syncthreads();  // whole chunk stored by this CTA (and ok_s consumed by everyone)
+      if (fwd && threadIdx.x == 0) publish_epoch(a.arrived_right + c, a.epoch_base + t + 1);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- two-shot ----
+struct TwoShotDev {
+  const uint4* va[kApiMaxRanks];
+  uint4* vc[kApiMaxRanks];
+  uint32_t* pads[kApiMaxRanks];
+  uint32_t* ticket;
+  uint32_t ticket_target;
+  int rank;
+  int world;
+  size_t slice_vec;  // vectors per rank slice
+  uint32_t barrier_epoch;
+  uint64_t timeout_ns;
+  uint32_t* status;
+};
+
+// After the whole grid finished its stores, the last CTA runs the cross-GPU
+// barrier: kernel completion then implies every peer's slice landed in my VC.
+__device__ __forceinline__ void grid_then_node_barrier(uint32_t* ticket, uint32_t ticket_target,
+                                                       uint32_t* const* pads, int rank, int world,
+                                                       uint32_t epoch, uint64_t timeout_ns,
+                                                       uint32_t* status) {
+  __shared__ int last_s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ptx::fence_acq_rel_sys();
+    const uint32_t t = ptx::atom_acq_rel_gpu_add(ticket, 1u);
+    last_s = (t + 1u == ticket_target) ? 1 : 0;
+    if (last_s) ptx::fence_acq_rel_sys();
+  }
+  __syncthreads();
+  if (!last_s) return;
+  if (static_cast<int>(threadIdx.x) < world) {
+    ptx::st_release_sys(pads[threadIdx.x] + kPadBarrier + rank, epoch);
+    wait_epoch(pads[rank] + kPadBarrier + threadIdx.x, epoch, timeout_ns, status);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512) two_shot_kernel(const __grid_constant__ TwoShotDev a) {
+  const size_t base = static_cast<size_t>(a.rank) * a.slice_vec;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.slice_vec;
+       i += stride) {
+    uint4 x[kApiMaxRanks];
+#pragma unroll
+    for (int p = 0; p < kApiMaxRanks; ++p)
+      if (p < a.world) x[p] = ptx::ld_peer_v4(a.va[p] + base + i);
+    uint4 acc = x[0];
+#pragma unroll
+    for (int p = 1; p < kApiMaxRanks; ++p)
+      if (p < a.world) acc = Vec4<T>::add(acc, x[p]);
+#pragma unroll
+    for (int p = 0; p < kApiMaxRanks; ++p)
+      if (p < a.world) ptx::st_stream_v4(a.vc[p] + base + i, acc);
+  }
+  grid_then_node_barrier(a.ticket, a.ticket_target, a.pads, a.rank, a.world, a.barrier_epoch,
+                         a.timeout_ns, a.status);
+}
+
+// -------------------------------------------------------------------- NVLS ----
+struct NvlsDev {
+  const unsigned char* va_mc;
+  unsigned char* vc_mc;
+  uint32_t* pads[kApiMaxRanks];
+  uint32_t* ticket;
+  uint32_t ticket_target;
+  int rank;
+  int world;
+  size_t slice_vec;
+  uint32_t barrier_epoch;
+  uint64_t timeout_ns;
+  uint32_t* status;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(512) nvls_kernel(const __grid_constant__ NvlsDev a) {
+  const size_t base = static_cast<size_t>(a.rank) * a.slice_vec;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.slice_vec;
+       i += stride) {
+    const size_t off = (base + i) * 16;
+    float4 r;
+    if (std::is_floating_point<T>::value) {
+      r = ptx::multimem_ld_reduce_add_f32x4(a.va_mc + off);
+    } else {  // int: scalar in-switch adds, vector broadcast of the raw bits
+      r.x = __int_as_float(ptx::multimem_ld_reduce_add_s32(a.va_mc + off));
+      r.y = __int_as_float(ptx::multimem_ld_reduce_add_s32(a.va_mc + off + 4));
+      r.z = __int_as_float(ptx::multimem_ld_reduce_add_s32(a.va_mc + off + 8));
+      r.w = __int_as_float(ptx::multimem_ld_reduce_add_s32(a.va_mc + off + 12));
+    }
+    ptx::multimem_st_f32x4(a.vc_mc + off, r);
+  }
+  grid_then_node_barrier(a.ticket, a.ticket_target, a.pads, a.rank, a.world, a.barrier_epoch,
+                         a.timeout_ns, a.status);
+}
+
+int grid_for(size_t items, int threads, int cap) {
+  const size_t want = (items + threads - 1) / threads;
+  return static_cast<int>(std::max<size_t>(1, std::min<size_t>(want, static_cast<size_t>(cap))));
+}
+
+}  // namespace
+
+void launch_init3(void* va, void* vb, void* vc, size_t n, double a, double b, double c,
+                  ElemType type, cudaStream_t stream) {
+  const int ctas = grid_for(n, 256, 148 * 8);
+  if (type == ElemType::kFloat)
+    init3_kernel<float><<<ctas, 256, 0, stream>>>(static_cast<float*>(va), static_cast<float*>(vb),
+                                                  static_cast<float*>(vc), n, static_cast<float>(a),
+                                                  static_cast<float>(b), static_cast<float>(c));
+  else
+    init3_kernel<int><<<ctas, 256, 0, stream>>>(static_cast<int*>(va), static_cast<int*>(vb),
+                                                static_cast<int*>(vc), n, static_cast<int>(a),
+                                                static_cast<int>(b), static_cast<int>(c));
+  HPCP_CUDA(cudaGetLastError());
+}
+
+void launch_accumulate(const void* va, void* vc, size_t n, ElemType type, cudaStream_t stream) {
+  const size_t nvec = n / 4, tail = n % 4;
+  const int ctas = grid_for(std::max<size_t>(nvec, 1), 512, 148 * 4);
+  if (type == ElemType::kFloat)
+    accumulate_kernel<float><<<ctas, 512, 0, stream>>>(
+        static_cast<const uint4*>(va), static_cast<uint4*>(vc), nvec,
+        static_cast<const float*>(va) + nvec * 4, static_cast<float*>(vc) + nvec * 4, tail);
+  else
+    accumulate_kernel<int><<<ctas, 512, 0, stream>>>(
+        static_cast<const uint4*>(va), static_cast<uint4*>(vc), nvec,
+        static_cast<const int*>(va) + nvec * 4, static_cast<int*>(vc) + nvec * 4, tail);
+  HPCP_CUDA(cudaGetLastError());
+}
+
+void launch_count_mismatch(const void* v, size_t n, double expected, ElemType type,
+                           unsigned long long* count, cudaStream_t stream) {
+  const int ctas = grid_for(n, 256, 148 * 8);
+  if (type == ElemType::kFloat)
+    count_mismatch_kernel<float><<<ctas, 256, 0, stream>>>(static_cast<const float*>(v), n, expected,
+                                                           count);
+  else
+    count_mismatch_kernel<int><<<ctas, 256, 0, stream>>>(static_cast<const int*>(v), n, expected,
+                                                         count);
+  HPCP_CUDA(cudaGetLastError());
+}
+
+size_t ring_num_chunks(size_t n, size_t chunk_elems) {
+  const size_t ce = chunk_elems == 0 ? 8192 : chunk_elems;
+  return (n + ce - 1) / ce;
+}
+
+void launch_ring_allreduce(const RingArgs& args, ElemType type, int ctas, int device,
+                           cudaStream_t stream) {
+  HPCP_REQUIRE(args.world >= 1 && args.world <= kApiMaxRanks, "ring: world out of range");
+  HPCP_REQUIRE(args.n % 4 == 0, "ring: n must be a multiple of 4 elements");
+  const size_t ce = args.chunk_elems == 0 ? 8192 : args.chunk_elems;
+  HPCP_REQUIRE(ce % 4 == 0, "ring: chunk_elems must be a multiple of 4");
+  RingDev d{};
+  d.va = static_cast<const uint4*>(args.va);
+  d.vc = static_cast<uint4*>(args.vc);
+  d.slots_local = static_cast<const uint4*>(args.slots_local);
+  d.slots_right = static_cast<uint4*>(args.slots_right);
+  d.arrived_local = args.arrived_local;
+  d.arrived_right = args.arrived_right;
+  d.world = args.world;
+  d.nvec = args.n / 4;
+  d.chunk_vec = ce / 4;
+  d.n_chunks = ring_num_chunks(args.n, ce);
+  d.epoch_base = args.epoch_base;
+  d.timeout_ns = args.timeout_ns;
+  d.status = args.status;
+  // All CTAs may spin on arrival words: the grid must be co-resident (<= 4 CTAs of
+  // 512 threads per SM).
+  const int sms = device_sm_count(device);
+  int grid = ctas > 0 ? ctas : sms * 2;
+  grid = std::min(grid, sms * 4);
+  grid = static_cast<int>(std::min<size_t>(static_cast<size_t>(grid), std::max<size_t>(d.n_chunks, 1)));
+  if (type == ElemType::kFloat)
+    ring_allreduce_kernel<float><<<grid, 512, 0, stream>>>(d);
+  else
+    ring_allreduce_kernel<int><<<grid, 512, 0, stream>>>(d);
+  HPCP_CUDA(cudaGetLastError());
+}
+
+int launch_allreduce_two_shot(const TwoShotArgs& args, ElemType type, int ctas, int device,
+                              cudaStream_t stream) {
+  HPCP_REQUIRE(args.world >= 1 && args.world <= kApiMaxRanks, "two-shot: world out of range");
+  HPCP_REQUIRE(args.n % (4 * static_cast<size_t>(args.world)) == 0,
+               "two-shot: n must be a multiple of 4*world elements");
+  TwoShotDev d{};
+  for (int p = 0; p < args.world; ++p) {
+    d.va[p] = static_cast<const uint4*>(args.va[p]);
+    d.vc[p] = static_cast<uint4*>(args.vc[p]);
+    d.pads[p] = args.pads[p];
+  }
+  d.ticket = args.ticket;
+  d.rank = args.rank;
+  d.world = args.world;
+  d.slice_vec = args.n / 4 / args.world;
+  d.barrier_epoch = args.barrier_epoch;
+  d.timeout_ns = args.timeout_ns;
+  d.status = args.status;
+  const int sms = device_sm_count(device);
+  const int grid = grid_for(std::max<size_t>(d.slice_vec, 1), 512, ctas > 0 ? ctas : sms * 2);
+  d.ticket_target = args.ticket_base + static_cast<uint32_t>(grid);
+  if (type == ElemType::kFloat)
+    two_shot_kernel<float><<<grid, 512, 0, stream>>>(d);
+  else
+    two_shot_kernel<int><<<grid, 512, 0, stream>>>(d);
+  HPCP_CUDA(cudaGetLastError());
+  return grid;
+}
+
+int launch_allreduce_nvls(const NvlsArgs& args, ElemType type, int ctas, int device,
+                          cudaStream_t stream) {
+  HPCP_REQUIRE(args.world >= 1 && args.world <= kApiMaxRanks, "nvls: world out of range");
+  HPCP_REQUIRE(args.n % (4 * static_cast<size_t>(args.world)) == 0,
+               "nvls: n must be a multiple of 4*world elements");
+  NvlsDev d{};
+  d.va_mc = static_cast<const unsigned char*>(args.va_mc);
+  d.vc_mc = static_cast<unsigned char*>(args.vc_mc);
+  for (int p = 0; p < args.world; ++p) d.pads[p] = args.pads[p];
+  d.ticket = args.ticket;
+  d.rank = args.rank;
+  d.world = args.world;
+  d.slice_vec = args.n / 4 / args.world;
+  d.barrier_epoch = args.barrier_epoch;
+  d.timeout_ns = args.timeout_ns;
+  d.status = args.status;
+  const int sms = device_sm_count(device);
+  const int grid = grid_for(std::max<size_t>(d.slice_vec, 1), 512, ctas > 0 ? ctas : sms);
+  d.ticket_target = args.ticket_base + static_cast<uint32_t>(grid);
+  if (type == ElemType::kFloat)
+    nvls_kernel<float><<<grid, 512, 0, stream>>>(d);
+  else
+    nvls_kernel<int><<<grid, 512, 0, stream>>>(d);
+  HPCP_CUDA(cudaGetLastError());
+  return grid;
+}
+
+}  // namespace hpcp

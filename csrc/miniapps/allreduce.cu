@@ -1,0 +1,383 @@
+// allreduce — the miniapp: ring "rotate + accumulate" allreduce of a replicated
+// array, or a one-launch collective with -a.
+//
+// Capability parity with the three reference variants
+//   mpi-sycl/allreduce-mpi-sycl.cpp:88-215
+//   mpi-omp-offload/allreduce-usm-mpi-omp-offload.cpp:78-225
+//   mpi-omp-offload/allreduce-map-mpi-omp-offload.cpp:67-179
+// Options kept: -h, -a (use the collective), -p k (2^k elements, default 25),
+// -H / -D / -S allocation kind (pinned host / device / managed), element type
+// float or int (upstream: compile-time APP_DATA_TYPE -> here --type or the
+// binary-name suffix `allreduce.float` / `allreduce.int`, like the upstream
+// target names `<app>.<type>`).  Output kept: `Passed <rank>` per rank, exit 0.
+// Additions: the elapsed time the reference computes but never prints
+// (allreduce-mpi-sycl.cpp:185-190) is printed as max over ranks, with bus GB/s.
+//
+// Algorithms (--algo):
+//   ring          fused K-ring: all P-1 exchanges + P accumulations in one launch/rank
+//   ring-unfused  same data movement as the reference with separate kernels:
+//                 rendezvous put kernel, then Accumulate kernel, per step (VA/VB swap)
+//   (with -a)     nvls when NVSwitch multicast is available, else two-shot P2P;
+//                 force with --coll nvls|twoshot
+#include <getopt.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../common/cuda_check.h"
+#include "../common/dtype_traits.h"
+#include "../common/peer_mem.h"
+#include "../common/rank_runtime.h"
+#include "../kernels/api.h"
+#include "devices.hpp"
+
+namespace {
+
+using namespace hpcp;
+
+constexpr int kPadReady = 16, kPadDone = 32, kPadLocal = 64, kPadWords = 128;  // see signal.cuh
+
+struct Config {
+  int ranks = 0;
+  int log2_elems = 25;
+  bool use_collective = false;
+  AllocKind kind = AllocKind::kDevice;
+  ElemType type = ElemType::kFloat;
+  std::string algo = "ring";
+  std::string coll = "auto";
+  int iters = 5;
+  int warmup = 1;
+  int ctas = 0;
+  size_t chunk_elems = 0;
+  uint64_t timeout_ns = 30ull * 1000 * 1000 * 1000;
+  std::string json_path;
+};
+
+void print_help() {
+  std::cout << "Usage: allreduce [options]\n"
+               "options:\n"
+               " -p k        2^k elements per rank            default: 25\n"
+               " -a          one-launch collective (NVLS multimem / two-shot P2P) instead of the ring\n"
+               " -H          pinned host memory   (cudaHostAlloc)\n"
+               " -D          device memory        (cudaMalloc, default)\n"
+               " -S          managed memory       (cudaMallocManaged)\n"
+               " -n N        ranks (one host thread + one GPU each; default: all GPUs;\n"
+               "             more ranks than GPUs are placed round-robin)\n"
+               " --type float|int      element type (default float, or binary-name suffix)\n"
+               " --algo ring|ring-unfused   fused persistent ring kernel (default) or\n"
+               "                            separate put + accumulate kernels per step\n"
+               " --coll auto|nvls|twoshot   collective used with -a\n"
+               " --iters N --warmup N  timed / untimed repetitions (min is reported)\n"
+               " --ctas N --chunk N    kernel tuning (CTAs per rank, elements per ring chunk)\n"
+               " --json FILE           append one JSON row\n";
+}
+
+struct Shared {
+  Config cfg;
+  NodeMemory* mem = nullptr;
+  size_t n = 0;
+  size_t n_chunks = 0;
+  SymmetricBuffer va, vb, vc, slots, pads;
+  MulticastBuffer mc_va, mc_vc;
+  bool nvls = false;
+  double best_ms = 0;
+  unsigned long long total_bad = 0;
+};
+
+uint32_t* pad_of(const Shared& sh, int r) { return static_cast<uint32_t*>(sh.pads.ptr[r]); }
+
+void rank_main(RankCtx& ctx, Shared& sh) {
+  const Config& cfg = sh.cfg;
+  const int me = ctx.rank, P = ctx.world;
+  const int dev = sh.mem->device(me);
+  HPCP_CUDA(cudaSetDevice(dev));
+  cudaStream_t stream;
+  HPCP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  const int right = (me + 1) % P, left = (me - 1 + P) % P;
+  const size_t esz = 4;
+  uint32_t* my_pad = pad_of(sh, me);
+  uint32_t* status = my_pad + kPadWords + sh.n_chunks;
+  std::vector<uint32_t*> pad_list;
+  for (int r = 0; r < P; ++r) pad_list.push_back(pad_of(sh, r));
+
+  void* va = sh.nvls ? sh.mc_va.uc[me] : sh.va.ptr[me];
+  void* vc = sh.nvls ? sh.mc_vc.uc[me] : sh.vc.ptr[me];
+
+  uint32_t barrier_epoch = 0, ticket_issued = 0, ring_epoch = 0, step_epoch = 0;
+  cudaEvent_t e0, e1;
+  HPCP_CUDA(cudaEventCreate(&e0));
+  HPCP_CUDA(cudaEventCreate(&e1));
+  double best_ms = std::numeric_limits<double>::max();
+
+  for (int it = 0; it < cfg.warmup + cfg.iters; ++it) {
+    // (Re-)initialise outside the timed region: VA = VB = rank, VC = 0.
+    launch_init3(va, cfg.algo == "ring-unfused" && !cfg.use_collective ? sh.vb.ptr[me] : nullptr, vc,
+                 sh.n, me, me, 0, cfg.type, stream);
+    HPCP_CUDA(cudaStreamSynchronize(stream));
+    ctx.barrier();
+    launch_barrier_all(pad_list.data(), me, P, ++barrier_epoch, cfg.timeout_ns, status, stream);
+    HPCP_CUDA(cudaEventRecord(e0, stream));
+
+    if (cfg.use_collective) {
+      ++barrier_epoch;
+      if (sh.nvls) {
+        NvlsArgs a;
+        a.va_mc = sh.mc_va.mc;
+        a.vc_mc = sh.mc_vc.mc;
+        for (int r = 0; r < P; ++r) a.pads[r] = pad_list[r];
+        a.ticket = my_pad + kPadLocal;
+        a.ticket_base = ticket_issued;
+        a.rank = me;
+        a.world = P;
+        a.n = sh.n;
+        a.barrier_epoch = barrier_epoch;
+        a.timeout_ns = cfg.timeout_ns;
+        a.status = status;
+        ticket_issued += launch_allreduce_nvls(a, cfg.type, cfg.ctas, dev, stream);
+      } else {
+        TwoShotArgs a;
+        for (int r = 0; r < P; ++r) {
+          a.va[r] = sh.va.ptr[r];
+          a.vc[r] = sh.vc.ptr[r];
+          a.pads[r] = pad_list[r];
+        }
+        a.ticket = my_pad + kPadLocal;
+        a.ticket_base = ticket_issued;
+        a.rank = me;
+        a.world = P;
+        a.n = sh.n;
+        a.barrier_epoch = barrier_epoch;
+        a.timeout_ns = cfg.timeout_ns;
+        a.status = status;
+        ticket_issued += launch_allreduce_two_shot(a, cfg.type, cfg.ctas, dev, stream);
+      }
+    } else if (cfg.algo == "ring") {
+      RingArgs a;
+      a.va = va;
+      a.vc = vc;
+      a.slots_local = sh.slots.ptr[me];
+      a.slots_right = sh.slots.ptr[right];
+      a.arrived_local = my_pad + kPadWords;
+      a.arrived_right = pad_of(sh, right) + kPadWords;
+      a.world = P;
+      a.n = sh.n;
+      a.chunk_elems = cfg.chunk_elems;
+      a.epoch_base = ring_epoch;
+      a.timeout_ns = cfg.timeout_ns;
+      a.status = status;
+      ring_epoch += static_cast<uint32_t>(P);
+      launch_ring_allreduce(a, cfg.type, cfg.ctas, dev, stream);
+    } else {  // ring-unfused: the reference's step structure with separate kernels
+      void* cur = va;
+      void* other = sh.vb.ptr[me];
+      void* right_cur = sh.va.ptr[right];     // what the right neighbour currently calls VA
+      void* right_other = sh.vb.ptr[right];   // ... and VB (where my block must land)
+      launch_accumulate(cur, vc, sh.n, cfg.type, stream);
+      for (int s = 1; s < P; ++s) {
+        ++step_epoch;
+        // Post the receive: my VB is free (my previous put from it has completed in-stream).
+        launch_signal(pad_of(sh, left) + kPadReady + me, step_epoch, stream);
+        SyncOps sync;
+        sync.wait_flag = my_pad + kPadReady + right;
+        sync.wait_epoch = step_epoch;
+        sync.signal_flag = pad_of(sh, right) + kPadDone + me;
+        sync.signal_epoch = step_epoch;
+        sync.ticket = my_pad + kPadLocal;
+        sync.ticket_base = ticket_issued;
+        sync.timeout_ns = cfg.timeout_ns;
+        sync.status = status;
+        CopyTuning tune;
+        tune.ctas = cfg.ctas;
+        ticket_issued += launch_copy(right_other, cur, sh.n * esz, false, CopyEngine::kLdSt, tune, sync,
+                                     dev, stream);
+        launch_wait(my_pad + kPadDone + left, step_epoch, cfg.timeout_ns, status, stream);
+        std::swap(cur, other);
+        std::swap(right_cur, right_other);
+        launch_accumulate(cur, vc, sh.n, cfg.type, stream);
+      }
+    }
+
+    HPCP_CUDA(cudaEventRecord(e1, stream));
+    HPCP_CUDA(cudaStreamSynchronize(stream));
+    uint32_t st = 0;
+    HPCP_CUDA(cudaMemcpy(&st, status, sizeof st, cudaMemcpyDeviceToHost));
+    HPCP_REQUIRE(st == 0, "rank " + std::to_string(me) + ": device-side wait timed out");
+    float ms = 0;
+    HPCP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double t = ctx.max(ms);
+    if (it >= cfg.warmup) best_ms = std::min(best_ms, t);
+  }
+
+  // Verify: every element of VC equals P(P-1)/2.
+  unsigned long long* count = nullptr;
+  HPCP_CUDA(cudaMalloc(&count, sizeof *count));
+  HPCP_CUDA(cudaMemsetAsync(count, 0, sizeof *count, stream));
+  launch_count_mismatch(vc, sh.n, 0.5 * P * (P - 1), cfg.type, count, stream);
+  unsigned long long bad = 0;
+  HPCP_CUDA(cudaMemcpyAsync(&bad, count, sizeof bad, cudaMemcpyDeviceToHost, stream));
+  HPCP_CUDA(cudaStreamSynchronize(stream));
+  (void)cudaFree(count);
+  const double total_bad = ctx.sum(static_cast<double>(bad));
+  if (bad == 0)
+    std::cout << "Passed " << me << std::endl;
+  else
+    std::cout << "FAILED " << me << ": " << bad << " wrong elements" << std::endl;
+  if (me == 0) {
+    sh.best_ms = best_ms;
+    sh.total_bad = static_cast<unsigned long long>(total_bad);
+  }
+  (void)cudaEventDestroy(e0);
+  (void)cudaEventDestroy(e1);
+  (void)cudaStreamDestroy(stream);
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  try {
+    Shared sh;
+    Config& cfg = sh.cfg;
+    // Type from the binary name suffix (`allreduce.int`), like upstream's `<app>.<type>` targets.
+    {
+      const std::string self = argv[0];
+      const auto dot = self.rfind('.');
+      if (dot != std::string::npos) (void)elem_type_from_name(self.substr(dot + 1), &cfg.type);
+    }
+    static const option long_opts[] = {{"type", required_argument, nullptr, 1},
+                                       {"algo", required_argument, nullptr, 2},
+                                       {"coll", required_argument, nullptr, 3},
+                                       {"iters", required_argument, nullptr, 4},
+                                       {"warmup", required_argument, nullptr, 5},
+                                       {"ctas", required_argument, nullptr, 6},
+                                       {"chunk", required_argument, nullptr, 7},
+                                       {"json", required_argument, nullptr, 8},
+                                       {"help", no_argument, nullptr, 'h'},
+                                       {nullptr, 0, nullptr, 0}};
+    int opt;
+    while ((opt = getopt_long(argc, argv, "haHDSp:n:", long_opts, nullptr)) != -1) {
+      switch (opt) {
+        case 'h': print_help(); return 1;
+        case 'a': cfg.use_collective = true; break;
+        case 'H': cfg.kind = AllocKind::kPinned; break;
+        case 'D': cfg.kind = AllocKind::kDevice; break;
+        case 'S': cfg.kind = AllocKind::kManaged; break;
+        case 'p': cfg.log2_elems = std::atoi(optarg); break;
+        case 'n': cfg.ranks = std::atoi(optarg); break;
+        case 1:
+          if (!elem_type_from_name(optarg, &cfg.type)) HPCP_FAIL(std::string("unsupported --type ") + optarg);
+          break;
+        case 2: cfg.algo = optarg; break;
+        case 3: cfg.coll = optarg; break;
+        case 4: cfg.iters = std::max(1, std::atoi(optarg)); break;
+        case 5: cfg.warmup = std::max(0, std::atoi(optarg)); break;
+        case 6: cfg.ctas = std::atoi(optarg); break;
+        case 7: cfg.chunk_elems = static_cast<size_t>(std::atoll(optarg)); break;
+        case 8: cfg.json_path = optarg; break;
+        default: print_help(); return 1;
+      }
+    }
+    HPCP_REQUIRE(cfg.algo == "ring" || cfg.algo == "ring-unfused", "unknown --algo " + cfg.algo);
+    HPCP_REQUIRE(cfg.log2_elems >= 4 && cfg.log2_elems <= 32, "-p must be in [4,32]");
+
+    const int ndev = visible_device_count();
+    if (ndev == 0) {
+      std::cerr << "Error: No devices" << std::endl;
+      return 1;
+    }
+    if (cfg.ranks <= 0) cfg.ranks = ndev;
+    if (cfg.ranks < 2) {
+      std::cerr << "Error: Set ranks to an integer >= 2 (the reference requires an even integer >= 4)"
+                << std::endl;
+      return 1;
+    }
+    const int P = cfg.ranks;
+    std::vector<int> devices;
+    for (int r = 0; r < P; ++r) devices.push_back(primary_device(r, P, ndev));
+    const int ranks_per_dev = (P + ndev - 1) / ndev;
+    if (ranks_per_dev > 1 && cfg.ctas == 0)  // co-residency of spinning kernels sharing a GPU
+      cfg.ctas = std::max(1, device_sm_count(devices[0]) * 2 / ranks_per_dev);
+
+    NodeMemory mem(devices);
+    sh.mem = &mem;
+    sh.n = size_t{1} << cfg.log2_elems;
+    if (cfg.use_collective && sh.n % (4 * static_cast<size_t>(P)) != 0)
+      sh.n = (sh.n / (4 * P) + 1) * (4 * P);  // pad so that every rank owns an aligned slice
+    const size_t bytes = sh.n * 4;
+    sh.n_chunks = ring_num_chunks(sh.n, cfg.chunk_elems);
+    sh.pads = mem.alloc_pads(sh.n_chunks);
+
+    if (cfg.use_collective) {
+      bool want_nvls = cfg.coll == "nvls";
+      if (cfg.coll == "auto") {
+        want_nvls = ranks_per_dev == 1 && cfg.kind == AllocKind::kDevice;
+        for (int d : devices) want_nvls = want_nvls && NodeMemory::multicast_supported(d);
+      }
+      if (want_nvls) {
+        try {
+          sh.mc_va = mem.alloc_multicast(bytes);
+          sh.mc_vc = mem.alloc_multicast(bytes);
+          sh.nvls = true;
+        } catch (const std::exception& e) {
+          if (cfg.coll == "nvls") throw;
+          std::cerr << "# NVLS unavailable (" << e.what() << "); using two-shot P2P" << std::endl;
+        }
+      }
+    }
+    if (!sh.nvls) {
+      sh.va = mem.alloc(bytes, cfg.kind);
+      sh.vc = mem.alloc(bytes, cfg.kind);
+    }
+    if (!cfg.use_collective) {
+      if (cfg.algo == "ring")
+        sh.slots = mem.alloc(bytes * static_cast<size_t>(P - 1), cfg.kind, /*zero=*/false);
+      else
+        sh.vb = mem.alloc(bytes, cfg.kind);
+    }
+
+    run_ranks(P, [&](RankCtx& ctx) { rank_main(ctx, sh); });
+
+    // Reporting: the number the reference computes and drops.
+    const std::string algo_name =
+        cfg.use_collective ? (sh.nvls ? "nvls" : "twoshot") : cfg.algo;
+    // Per-rank bytes sent over NVLink: faithful ring (P-1)*N; bandwidth-optimal collectives (P-1)/P*N.
+    const double sent = cfg.use_collective ? static_cast<double>(bytes) * (P - 1) / P
+                                           : static_cast<double>(bytes) * (P - 1);
+    const double gbps = sent / (sh.best_ms * 1e-3) * 1e-9;
+    std::cout << "Elapsed (max over ranks, min of " << cfg.iters << "): " << sh.best_ms << " ms | "
+              << algo_name << " " << elem_type_name(cfg.type) << " " << alloc_kind_name(cfg.kind)
+              << " P=" << P << " N=2^" << cfg.log2_elems << " | " << gbps
+              << " GB/s sent per rank (" << gbps / 900.0 * 100.0 << "% of 900 GB/s)" << std::endl;
+    if (!cfg.json_path.empty()) {
+      FILE* f = std::fopen(cfg.json_path.c_str(), "a");
+      if (f) {
+        std::fprintf(f,
+                     "{\"pattern\":\"allreduce\",\"algo\":\"%s\",\"type\":\"%s\",\"alloc\":\"%s\","
+                     "\"ranks\":%d,\"elements\":%zu,\"ms\":%.6f,\"GBps_sent_per_rank\":%.3f,"
+                     "\"mismatches\":%llu}\n",
+                     algo_name.c_str(), elem_type_name(cfg.type), alloc_kind_name(cfg.kind), P, sh.n,
+                     sh.best_ms, gbps, sh.total_bad);
+        std::fclose(f);
+      }
+    }
+
+    if (sh.nvls) {
+      mem.free_multicast(sh.mc_va);
+      mem.free_multicast(sh.mc_vc);
+    } else {
+      mem.free(sh.va);
+      mem.free(sh.vc);
+    }
+    mem.free(sh.slots);
+    mem.free(sh.vb);
+    mem.free(sh.pads);
+    return sh.total_bad == 0 ? 0 : 1;
+  } catch (const std::exception& e) {
+    std::cerr << "Error: " << e.what() << std::endl;
+    return 1;
+  }
+}

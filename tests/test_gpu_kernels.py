@@ -1,0 +1,262 @@
+"""Single-GPU numerics tests: every sm_100a kernel against a plain PyTorch reference."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    torch.cuda.set_device(0)
+    return torch.device("cuda", 0)
+
+
+def _stream():
+    return torch.cuda.current_stream(0).cuda_stream
+
+
+@pytest.mark.parametrize("engine", ["ldst", "tma"])
+@pytest.mark.parametrize("nbytes", [1024, 65536 + 16, (1 << 20) + 48, 1000003, 64 << 20])
+def test_copy_matches_torch(native, dev, engine, nbytes):
+    src = torch.randint(0, 256, (nbytes,), dtype=torch.uint8, device=dev)
+    dst = torch.zeros(nbytes + 64, dtype=torch.uint8, device=dev)
+    ctas = native.copy(dst.data_ptr(), src.data_ptr(), nbytes, False, engine, {}, {}, 0, _stream())
+    torch.cuda.synchronize()
+    assert ctas >= 1
+    assert torch.equal(dst[:nbytes], src)
+    assert int(dst[nbytes:].sum()) == 0  # no overrun
+
+
+@pytest.mark.parametrize("unroll", [1, 2, 4, 8])
+def test_copy_ldst_unroll_variants(native, dev, unroll):
+    n = (8 << 20) + 32
+    src = torch.randint(0, 256, (n,), dtype=torch.uint8, device=dev)
+    dst = torch.zeros(n, dtype=torch.uint8, device=dev)
+    native.copy(dst.data_ptr(), src.data_ptr(), n, True, "ldst", {"unroll": unroll, "ctas": 37}, {}, 0, _stream())
+    torch.cuda.synchronize()
+    assert torch.equal(dst, src)
+
+
+@pytest.mark.parametrize("stages,stage_kb", [(2, 8), (4, 16), (8, 16), (6, 32)])
+def test_copy_tma_stage_variants(native, dev, stages, stage_kb):
+    n = (24 << 20) + 4096 + 16
+    src = torch.randint(0, 256, (n,), dtype=torch.uint8, device=dev)
+    dst = torch.zeros(n, dtype=torch.uint8, device=dev)
+    native.copy(dst.data_ptr(), src.data_ptr(), n, False, "tma", {"stages": stages, "stage_kb": stage_kb}, {}, 0,
+                _stream())
+    torch.cuda.synchronize()
+    assert torch.equal(dst, src)
+
+
+def test_copy_signal_and_wait_roundtrip(native, dev):
+    """Epilogue signal (last CTA publishes) + a waiting kernel + prologue wait, on one GPU."""
+    pad = torch.zeros(256, dtype=torch.int32, device=dev)
+    n = 4 << 20
+    src = torch.randint(0, 256, (n,), dtype=torch.uint8, device=dev)
+    dst = torch.zeros(n, dtype=torch.uint8, device=dev)
+    flag = pad.data_ptr() + 4 * native.PAD_DONE
+    ticket = pad.data_ptr() + 4 * native.PAD_LOCAL
+    status = pad.data_ptr() + 4 * 200
+    issued = 0
+    for epoch in (1, 2, 3):
+        sync = {"signal_flag": flag, "signal_epoch": epoch, "ticket": ticket, "ticket_base": issued,
+                "timeout_ns": int(5e9), "status": status}
+        issued += native.copy(dst.data_ptr(), src.data_ptr(), n, False, "ldst", {}, sync, 0, _stream())
+        native.wait(flag, epoch, int(5e9), status, _stream())
+        torch.cuda.synchronize()
+        assert int(pad[native.PAD_DONE].item()) == epoch
+        assert int(pad[native.PAD_LOCAL].item()) == issued
+        assert int(pad[200].item()) == native.STATUS_OK
+    assert torch.equal(dst, src)
+
+
+def test_wait_timeout_sets_status_instead_of_hanging(native, dev):
+    pad = torch.zeros(64, dtype=torch.int32, device=dev)
+    native.wait(pad.data_ptr(), 5, int(2e7), pad.data_ptr() + 4 * 8, _stream())  # 20 ms deadline
+    torch.cuda.synchronize()
+    assert int(pad[8].item()) & 0xFFFFFFFF == native.STATUS_TIMEOUT
+
+
+def test_fill_and_verify_pattern(native, dev):
+    from hpc_patterns_b200.ops.p2p import pattern_reference
+
+    n = 1 << 20
+    buf = torch.zeros(n, dtype=torch.int32, device=dev)
+    native.fill_pattern(buf.data_ptr(), n, 0xDEADBEEF, _stream())
+    torch.cuda.synchronize()
+    ref = pattern_reference(n, 0xDEADBEEF)
+    got = buf.cpu().to(torch.int64) & 0xFFFFFFFF
+    assert torch.equal(got, ref)
+    counters = torch.zeros(2, dtype=torch.int64, device=dev)
+    native.verify_pattern(buf.data_ptr(), n, 0xDEADBEEF, counters.data_ptr(), counters.data_ptr() + 8)
+    torch.cuda.synchronize()
+    assert int(counters[0]) == 0 and int(counters[1]) == int(ref.sum())
+    buf[12345] ^= 1
+    counters.zero_()
+    native.verify_pattern(buf.data_ptr(), n, 0xDEADBEEF, counters.data_ptr(), counters.data_ptr() + 8)
+    torch.cuda.synchronize()
+    assert int(counters[0]) == 1
+
+
+@pytest.mark.parametrize("engine,tune", [("ldst", {}), ("ldst", {"unroll": 4}), ("ldst", {"unroll": 1}),
+                                         ("tma", {}), ("tma", {"stages": 3, "stage_kb": 8})])
+@pytest.mark.parametrize("n", [4096, (1 << 22) + 8, 12345 * 4])
+def test_triad_put_matches_fp32_reference(native, dev, engine, tune, n):
+    from hpc_patterns_b200.ops.fused import triad_reference
+
+    b = torch.randn(n, device=dev)
+    c = torch.randn(n, device=dev)
+    a_local = torch.zeros(n, device=dev)
+    a_peer = torch.zeros(n, device=dev)  # loop-back "peer"
+    native.triad_put(a_local.data_ptr(), a_peer.data_ptr(), b.data_ptr(), c.data_ptr(), 2.5, n, engine, tune, {},
+                     0, 0, 0, _stream())
+    torch.cuda.synchronize()
+    ref = torch.addcmul(b, c, torch.tensor(2.5, device=dev))  # fused multiply-add order differs by <= 1 ulp
+    assert torch.allclose(a_local, triad_reference(b, c, 2.5), rtol=1e-6, atol=1e-6)
+    assert torch.equal(a_local, a_peer)
+    assert torch.allclose(a_local, ref, rtol=1e-6, atol=1e-6)
+    # plain triad (no put)
+    a2 = torch.zeros(n, device=dev)
+    native.triad_put(a2.data_ptr(), 0, b.data_ptr(), c.data_ptr(), 2.5, n, engine, tune, {}, 0, 0, 0, _stream())
+    torch.cuda.synchronize()
+    assert torch.equal(a2, a_local)
+
+
+def test_fill_triad_inputs_and_verify(native, dev):
+    from hpc_patterns_b200.ops.fused import triad_inputs_reference
+
+    n = 1 << 18
+    b = torch.zeros(n, device=dev)
+    c = torch.zeros(n, device=dev)
+    native.fill_triad_inputs(b.data_ptr(), c.data_ptr(), n, 3, _stream())
+    torch.cuda.synchronize()
+    rb, rc = triad_inputs_reference(n, 3)
+    assert torch.equal(b.cpu(), rb) and torch.equal(c.cpu(), rc)
+    a = (rb + 3.0 * rc).to(dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    native.verify_triad(a.data_ptr(), n, 3, 3.0, cnt.data_ptr(), _stream())
+    torch.cuda.synchronize()
+    assert int(cnt) == 0
+    a[77] += 1
+    native.verify_triad(a.data_ptr(), n, 3, 3.0, cnt.data_ptr(), _stream())
+    torch.cuda.synchronize()
+    assert int(cnt) == 1
+
+
+def test_fused_exchange_loopback(native):
+    from hpc_patterns_b200.models.peer2pear import FusedTriadExchange
+    from hpc_patterns_b200.parallel.comm import Comm
+
+    for engine in ("ldst", "tma"):
+        ex = FusedTriadExchange(Comm(), 0, nbytes=8 << 20, engine=engine)
+        for _ in range(3):
+            ex.step()
+        torch.cuda.synchronize()
+        ex.check()
+        assert ex.verify() == 0
+        assert torch.equal(ex.a, ex.b + 3.0 * ex.c)
+        host = ex.make_host_input()
+        assert ex.step_from_host(host, chunks=4) == 0
+        ex.close()
+
+
+def test_busy_wait_semantics(native, dev):
+    out = torch.full((300,), -1.0, device=dev)
+    native.busy_wait(out.data_ptr(), 300, 3, _stream())
+    torch.cuda.synchronize()
+    assert float(out[0]) == 0.0          # y=0 stays 0 through the FMA chain
+    assert bool(torch.isinf(out[1:]).all())  # everything else overflows to +inf
+
+
+def test_fused_bench_commands(native, dev):
+    n = (2 << 20) + 4
+    src = torch.randn(n, device=dev)
+    dst = torch.zeros(n, device=dev)
+    b = torch.randn(n, device=dev)
+    c = torch.randn(n, device=dev)
+    a = torch.zeros(n, device=dev)
+    out = torch.full((64,), -1.0, device=dev)
+    for engine in ("tma", "ldst"):
+        dst.zero_(); a.zero_(); out.fill_(-1)
+        cmds = [{"kind": "busy", "n": 64, "tripcount": 50, "a": out.data_ptr()},
+                {"kind": "copy", "n": n, "dst": dst.data_ptr(), "src": src.data_ptr()},
+                {"kind": "triad", "n": n, "a": a.data_ptr(), "b": b.data_ptr(), "c": c.data_ptr(), "s": 3.0}]
+        ctas = native.fused_bench(cmds, engine, {}, 0, _stream())
+        torch.cuda.synchronize()
+        assert ctas >= 3
+        assert torch.equal(dst, src)
+        assert torch.allclose(a, b + 3.0 * c, rtol=1e-6, atol=1e-6)
+        assert float(out[0]) == 0.0 and bool(torch.isinf(out[1:]).all())
+
+
+def test_fused_bench_pinned_host_copy(native, dev):
+    n = 1 << 20
+    h = torch.randn(n).pin_memory()
+    d = torch.zeros(n, device=dev)
+    back = torch.zeros(n).pin_memory()
+    native.fused_bench([{"kind": "copy", "n": n, "dst": d.data_ptr(), "src": h.data_ptr()}], "tma", {}, 0, _stream())
+    native.fused_bench([{"kind": "copy", "n": n, "dst": back.data_ptr(), "src": d.data_ptr()}], "tma", {}, 0, _stream())
+    torch.cuda.synchronize()
+    assert torch.equal(d.cpu(), h) and torch.equal(back, h)
+
+
+@pytest.mark.parametrize("dtype,td", [("float", torch.float32), ("int", torch.int32)])
+def test_allreduce_building_blocks(native, dev, dtype, td):
+    n = (1 << 18) + 4
+    va = torch.zeros(n, dtype=td, device=dev)
+    vb = torch.zeros(n, dtype=td, device=dev)
+    vc = torch.zeros(n, dtype=td, device=dev)
+    native.init3(va.data_ptr(), vb.data_ptr(), vc.data_ptr(), n, 5, 7, 1, dtype, _stream())
+    native.accumulate(va.data_ptr(), vc.data_ptr(), n, dtype, _stream())
+    native.accumulate(vb.data_ptr(), vc.data_ptr(), n, dtype, _stream())
+    torch.cuda.synchronize()
+    assert torch.equal(vc, torch.full((n,), 13, dtype=td, device=dev))
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    native.count_mismatch(vc.data_ptr(), n, 13.0, dtype, cnt.data_ptr(), _stream())
+    torch.cuda.synchronize()
+    assert int(cnt) == 0
+    vc[5] = 12
+    native.count_mismatch(vc.data_ptr(), n, 13.0, dtype, cnt.data_ptr(), _stream())
+    torch.cuda.synchronize()
+    assert int(cnt) == 1
+
+
+@pytest.mark.parametrize("algo", ["ring", "ring-unfused", "twoshot", "nccl"])
+@pytest.mark.parametrize("dtype", ["float", "int"])
+def test_allreduce_miniapp_single_rank(native, algo, dtype):
+    from hpc_patterns_b200.models.allreduce import AllreduceMiniapp
+    from hpc_patterns_b200.parallel.comm import Comm
+
+    app = AllreduceMiniapp(Comm(), 0, log2_elems=16, dtype=dtype, algo=algo)
+    res = app.run(iters=2, warmup=1)
+    app.close()
+    assert res.mismatches == 0 and res.ms > 0
+
+
+@pytest.mark.parametrize("mode", ["serial", "in_order", "out_of_order", "host_threads", "nowait", "fused"])
+def test_concurency_cuda_backend_all_modes(native, mode):
+    rc, out, err = native.concurency_main(
+        [mode, "--repetitions", "3", "--globalsize_default_memory", "4000000",
+         "--commands", "C", "D2D", "--commands", "H2D", "D2H", "--commands", "C", "A", "--commands", "M2D", "C"],
+        "cuda")
+    assert out.count("## " + mode) == 4, out + err
+    assert "Parameters used:" in out and "tripcount_C" in out
+    assert rc in (0, 1)
+
+
+def test_concurency_bench_api_profiling(native):
+    r = native.concurency_bench("cuda", "serial", ["C", "DH"], {"globalsize_C": 1, "tripcount_C": 2000,
+                                                                "globalsize_DH": 1 << 20}, True, -1, 3, False)
+    assert len(r["per_command_us"]) == 2 and len(r["device_us"]) == 2
+    assert all(t > 0 for t in r["device_us"])
+    r2 = native.concurency_bench("cuda", "in_order", ["C", "DH"], {"globalsize_C": 1, "tripcount_C": 2000,
+                                                                   "globalsize_DH": 1 << 20}, True, -1, 3, False)
+    assert r2["device_total_us"] > 0
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+
+    g.smoke()

@@ -1,0 +1,103 @@
+"""Multi-GPU tests (>= 2 B200): native CLIs (thread-per-rank) and torchrun workers (process-per-rank)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+needs2 = pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+
+
+def _run(cmd, timeout=600, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout, env=e)
+    return p.returncode, p.stdout, p.stderr
+
+
+def _torchrun(n, script_args, timeout=900, port=29601):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port)] + script_args
+    return _run(cmd, timeout)
+
+
+@needs2
+@pytest.mark.parametrize("transport", ["put", "get", "sendrecv", "memcpy"])
+@pytest.mark.parametrize("engine", ["ldst", "tma"])
+def test_cli_peer2pear(bin_dir, transport, engine):
+    if transport == "memcpy" and engine == "tma":
+        pytest.skip("engine is irrelevant for the copy-engine baseline")
+    rc, out, err = _run([os.path.join(bin_dir, "peer2pear"), "t", "-n", "2", "--transport", transport,
+                         "--engine", engine, "--bytes", str(8 << 20), "--bytes", "1024", "--iters", "3"])
+    assert rc == 0, out + err
+    assert out.count("Unidirectional Bandwidth:") == 2 and out.count("Bidirectional Bandwidth:") == 2
+    assert "VERIFICATION FAILED" not in out
+
+
+@needs2
+@pytest.mark.parametrize("engine", ["ldst", "tma"])
+def test_cli_peer2pear_fused_triad(bin_dir, engine):
+    rc, out, err = _run([os.path.join(bin_dir, "peer2pear"), "fused", "-n", "2", "--fused-triad", "--engine", engine,
+                         "--bytes", str(16 << 20), "--iters", "3"])
+    assert rc == 0, out + err
+    assert "VERIFICATION FAILED" not in out
+
+
+@needs2
+@pytest.mark.parametrize("args", [[], ["-a"], ["-a", "--coll", "twoshot"], ["--algo", "ring-unfused"],
+                                  ["--type", "int"], ["-a", "--type", "int"], ["-H", "-p", "16"], ["-S", "-p", "16"]])
+def test_cli_allreduce(bin_dir, args):
+    n = min(_ngpu(), 4)
+    rc, out, err = _run([os.path.join(bin_dir, "allreduce"), "-n", str(n), "-p", "20", "--iters", "2"] + args)
+    assert rc == 0, out + err
+    assert out.count("Passed") == n
+
+
+@needs2
+def test_cli_allreduce_oversubscribed(bin_dir):
+    rc, out, err = _run([os.path.join(bin_dir, "allreduce.int"), "-n", "4", "-p", "16", "--iters", "1"],
+                        env={"CUDA_VISIBLE_DEVICES": "0,1"})
+    assert rc == 0, out + err
+    assert out.count("Passed") == 4
+
+
+@needs2
+def test_cli_concurency_peer_letter(bin_dir):
+    rc, out, err = _run([os.path.join(bin_dir, "concurency"), "fused", "--repetitions", "3",
+                         "--globalsize_default_memory", "8000000", "--commands", "C", "D2P", "--commands", "D2P", "P2D"])
+    assert out.count("## fused") == 2, out + err
+
+
+@needs2
+def test_torchrun_workers():
+    rc, out, err = _torchrun(2, [os.path.join(ROOT, "tests", "mp_gpu_worker.py")])
+    assert rc == 0, out[-4000:] + err[-4000:]
+    assert "WORKER OK" in out
+
+
+@needs2
+def test_bench_two_gpus():
+    rc, out, err = _torchrun(2, [os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "5", "--warmup", "3",
+                                 "--e2e-steps", "2"], port=29611)
+    assert rc == 0, out[-3000:] + err[-3000:]
+    line = [l for l in out.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["n_gpus"] == 2 and d["value"] > 0 and d["wrong_words"] == 0 and d["gpu_launches"] == 5
+
+
+def test_bench_one_gpu():
+    rc, out, err = _run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "5", "--warmup", "3",
+                         "--e2e-steps", "2"])
+    assert rc == 0, out[-3000:] + err[-3000:]
+    d = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+    assert d["n_gpus"] == 1 and d["value"] > 0 and d["e2e"]["value"] > 0
