@@ -165,6 +165,48 @@ PYBIND11_MODULE(_C, m) {
     HPCP_CUDA(cudaMemcpy(as_ptr<void>(p), &v, sizeof v, cudaMemcpyDefault));
   });
 
+  // -------------------------------------------------------------- streams ----
+  m.def("stream_create", [](int device, bool non_blocking) {
+    int prev = 0;
+    HPCP_CUDA(cudaGetDevice(&prev));
+    HPCP_CUDA(cudaSetDevice(device));
+    cudaStream_t s;
+    HPCP_CUDA(cudaStreamCreateWithFlags(&s, non_blocking ? cudaStreamNonBlocking : cudaStreamDefault));
+    HPCP_CUDA(cudaSetDevice(prev));
+    return reinterpret_cast<uintptr_t>(s);
+  }, py::arg("device") = 0, py::arg("non_blocking") = true,
+  "Create a raw CUDA stream owned by this extension (wrap it with torch.cuda.ExternalStream).");
+  m.def("stream_destroy", [](uintptr_t s) { HPCP_CUDA(cudaStreamDestroy(as_stream(s))); });
+  m.def("stream_synchronize", [](uintptr_t s) {
+    py::gil_scoped_release release;
+    HPCP_CUDA(cudaStreamSynchronize(as_stream(s)));
+  });
+  m.def("device_native_info", [](int device) {
+    // Native (driver-level) handles underneath the runtime ordinal — see csrc/interop/device_table.h.
+    const DriverApi& d = DriverApi::get();
+    int prev = 0;
+    HPCP_CUDA(cudaGetDevice(&prev));
+    HPCP_CUDA(cudaSetDevice(device));
+    HPCP_CUDA(cudaFree(nullptr));
+    CUdevice cu_dev;
+    HPCP_CU(d.cuDeviceGet(&cu_dev, device));
+    CUcontext current = nullptr;
+    HPCP_CU(d.cuCtxGetCurrent(&current));
+    HPCP_CUDA(cudaSetDevice(prev));
+    py::dict out;
+    out["ordinal"] = device;
+    out["cu_device"] = static_cast<int>(cu_dev);
+    out["cu_context"] = reinterpret_cast<uintptr_t>(current);
+    return out;
+  });
+  m.def("stream_context", [](uintptr_t stream) {
+    const DriverApi& d = DriverApi::get();
+    CUcontext ctx = nullptr;
+    CUgreenCtx green = nullptr;
+    HPCP_CU(d.cuStreamGetCtx(reinterpret_cast<CUstream>(stream), &ctx, &green));
+    return reinterpret_cast<uintptr_t>(ctx);
+  });
+
   // -------------------------------------------------------------- signals ----
   m.def("signal", [](uintptr_t flag, uint32_t epoch, uintptr_t stream) {
     launch_signal(as_ptr<uint32_t>(flag), epoch, as_stream(stream));

@@ -250,7 +250,9 @@ def main(argv: Optional[List[str]] = None) -> int:
     ap.add_argument("--json", default=None)
     args = ap.parse_args(argv)
     comm = Comm()
-    device = comm.local_rank % max(torch.cuda.device_count(), 1)
+    from ..parallel.tile_mapping import selected_device
+
+    device = selected_device(default=comm.local_rank) % max(torch.cuda.device_count(), 1)
     algo = args.algo
     app = None
     if args.a:

@@ -1,0 +1,40 @@
+from hpc_patterns_b200.utils.parse import main, parse_log, render
+
+LOG = """+ export HPCP_DEVICE=0
+# out_of_order | C C | Starting Benchmarking...
+## out_of_order | C C | SUCCESS: Close from Theoretical Speedup
+## out_of_order | C MD | FAILURE: Far from Theoretical Speedup
+## in_order | C C | SUCCESS: Close from Theoretical Speedup
+## in_order | C MD | FAILURE: Minimun Bandwish not reached
++ export HPCP_DEVICE=0 CUDA_DEVICE_MAX_CONNECTIONS=1
+## fused | C  MD | SUCCESS: Close from Theoretical Speedup
+"""
+
+
+def test_parse_groups_by_env_commands_mode():
+    t = parse_log(LOG)
+    assert list(t) == ["HPCP_DEVICE=0", "HPCP_DEVICE=0 CUDA_DEVICE_MAX_CONNECTIONS=1"]
+    assert t["HPCP_DEVICE=0"]["C C"] == {"out_of_order": "SUCCESS", "in_order": "SUCCESS"}
+    assert t["HPCP_DEVICE=0"]["C MD"] == {"out_of_order": "FAILURE", "in_order": "FAILURE"}
+    assert t["HPCP_DEVICE=0 CUDA_DEVICE_MAX_CONNECTIONS=1"]["C MD"] == {"fused": "SUCCESS"}
+
+
+def test_render_has_one_table_per_env():
+    text = render(parse_log(LOG))
+    assert text.count("commands") == 2
+    assert "out_of_order" in text and "in_order" in text and "fused" in text
+
+
+def test_cli(tmp_path, capsys):
+    p = tmp_path / "x.log"
+    p.write_text(LOG)
+    assert main([str(p), "github"]) == 0
+    assert "| C C" in capsys.readouterr().out
+    assert main([]) == 2
+
+
+def test_roundtrip_with_real_driver_output(native):
+    rc, out, _ = native.concurency_main(["nowait", "--commands", "C", "M2D", "--commands", "H2D", "D2H"],
+                                        "fake:C=0.01,MD=0.0005,HD=0.0002,DH=0.0002,overlap=0.9")
+    t = parse_log("export X=1\n" + out)
+    assert t["X=1"]["C MD"]["nowait"] == "SUCCESS" and "HD DH" in t["X=1"]

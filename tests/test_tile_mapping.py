@@ -1,0 +1,70 @@
+import os
+import subprocess
+import sys
+
+import pytest
+
+from hpc_patterns_b200.parallel import tile_mapping as tm
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_environment_for_both_mechanisms():
+    e = tm.environment_for("compact", "CVD", 3, 8)
+    assert e == {"CUDA_DEVICE_ORDER": "PCI_BUS_ID", "CUDA_VISIBLE_DEVICES": "3", "HPCP_DEVICE": "0"}
+    e = tm.environment_for("spread", "SET", 3, 8)
+    assert e == {"CUDA_DEVICE_ORDER": "PCI_BUS_ID", "HPCP_DEVICE": "5"}
+    with pytest.raises(ValueError):
+        tm.environment_for("compact", "ZAM", 0, 8)
+
+
+def test_local_rank_sources():
+    assert tm.local_rank({"LOCAL_RANK": "5"}) == 5
+    assert tm.local_rank({"PALS_LOCAL_RANKID": "2"}) == 2
+    assert tm.local_rank({"OMPI_COMM_WORLD_LOCAL_RANK": "7"}) == 7
+    with pytest.raises(RuntimeError):
+        tm.local_rank({})
+
+
+@pytest.mark.parametrize("policy,mech,rank,var,val", [
+    ("compact", "CVD", 2, "CUDA_VISIBLE_DEVICES", "2"),
+    ("spread", "CVD", 1, "CUDA_VISIBLE_DEVICES", "4"),
+    ("spread", "SET", 3, "HPCP_DEVICE", "5"),
+    ("compact", "SET", 9, "HPCP_DEVICE", "1"),
+])
+def test_bash_wrapper(policy, mech, rank, var, val):
+    env = dict(os.environ, LOCAL_RANK=str(rank), HPCP_NUM_DEVICES="8")
+    p = subprocess.run([os.path.join(ROOT, "scripts", "tile_mapping.sh"), policy, mech, "bash", "-c",
+                        f"echo ${var} $CUDA_DEVICE_ORDER"], env=env, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert p.stdout.split() == [val, "PCI_BUS_ID"]
+
+
+def test_bash_wrapper_compact_plan_uses_topology_binary(bin_dir):
+    env = dict(os.environ, LOCAL_RANK="1", HPCP_NUM_DEVICES="6", HPCP_FAKE_TOPOLOGY="6:0-2,2-4,0-4,1-3,3-5,1-5")
+    p = subprocess.run([os.path.join(ROOT, "scripts", "tile_mapping.sh"), "compact_plan", "SET", "bash", "-c",
+                        "echo $HPCP_DEVICE"], env=env, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert p.stdout.strip() == "2"
+
+
+def test_bash_wrapper_rejects_bad_mechanism():
+    env = dict(os.environ, LOCAL_RANK="0", HPCP_NUM_DEVICES="8")
+    p = subprocess.run([os.path.join(ROOT, "scripts", "tile_mapping.sh"), "compact", "ZAM", "true"], env=env,
+                       capture_output=True, text=True)
+    assert p.returncode != 0 and "WRONG AFFINITY MECHANISM" in p.stderr
+
+
+def test_python_launcher(native):
+    env = dict(os.environ, LOCAL_RANK="3", HPCP_NUM_DEVICES="8", HPCP_FAKE_TOPOLOGY="8:switch", PYTHONPATH=ROOT)
+    p = subprocess.run([sys.executable, "-m", "hpc_patterns_b200.parallel.tile_mapping", "compact_plan", "CVD",
+                        "bash", "-c", "echo $CUDA_VISIBLE_DEVICES"], env=env, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert p.stdout.strip() == "3"
+
+
+def test_selected_device(monkeypatch):
+    monkeypatch.setenv("HPCP_DEVICE", "6")
+    assert tm.selected_device() == 6
+    monkeypatch.delenv("HPCP_DEVICE")
+    assert tm.selected_device(default=2) == 2
