@@ -32,13 +32,15 @@ REFERENCE_UNAVAILABLE = ("argonne-lcf/HPC-Patterns is C++17 SYCL/OpenMP-offload/
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--bytes", type=int, default=1179648 * 40 * 4)
     ap.add_argument("--engine", default=os.environ.get("HPCP_BENCH_ENGINE", "ldst"), choices=("ldst", "tma"))
     ap.add_argument("--ctas", type=int, default=int(os.environ.get("HPCP_BENCH_CTAS", "0")))
     ap.add_argument("--unroll", type=int, default=int(os.environ.get("HPCP_BENCH_UNROLL", "0")))
+    ap.add_argument("--vec", type=int, default=int(os.environ.get("HPCP_BENCH_VEC", "0")))
+    ap.add_argument("--blocked", type=int, default=int(os.environ.get("HPCP_BENCH_BLOCKED", "0")))
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-extras", action="store_true", help="skip the unfused / stock comparison runs")
     return ap.parse_args()
@@ -73,6 +75,10 @@ def main() -> int:
         tune["ctas"] = args.ctas
     if args.unroll:
         tune["unroll"] = args.unroll
+    if args.vec:
+        tune["vec_bytes"] = args.vec
+    if args.blocked:
+        tune["blocked"] = args.blocked
     ex = FusedTriadExchange(comm, device, args.bytes, s=3.0, engine=args.engine, tune=tune)
     stream = torch.cuda.current_stream(device)
 
@@ -99,8 +105,14 @@ def main() -> int:
         ex.step()
     torch.cuda.synchronize(device)
     launches_before = ex.launches
-    ms, clocks = timed(ex.step, args.steps,
-                       ClockSampler(gpu_index=device, period_ms=50) if comm.rank == 0 else None)
+    sampler = None
+    if comm.rank == 0:
+        try:
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(device).uuid)
+        except Exception:
+            uuid = None
+        sampler = ClockSampler(gpu_index=device, period_ms=1.0, uuid=uuid)
+    ms, clocks = timed(ex.step, args.steps, sampler)
     gpu_launches = ex.launches - launches_before
     bad = int(comm.sum(ex.verify()))
     ms_per_step = ms / args.steps

@@ -52,6 +52,8 @@ CopyTuning tuning_from(const py::dict& d) {
   if (d.contains("unroll")) t.unroll = d["unroll"].cast<int>();
   if (d.contains("stage_kb")) t.stage_kb = d["stage_kb"].cast<int>();
   if (d.contains("stages")) t.stages = d["stages"].cast<int>();
+  if (d.contains("vec_bytes")) t.vec_bytes = d["vec_bytes"].cast<int>();
+  if (d.contains("blocked")) t.blocked = d["blocked"].cast<int>();
   return t;
 }
 

@@ -88,6 +88,35 @@ __device__ __forceinline__ void st_stream_v4(uint4* p, const uint4& v) {
                : "memory");
 }
 
+// --------------------------------------------- 256-bit ld / st (sm_100+) ----
+// One LDG.256 / STG.256 per thread: a warp covers 1 KiB contiguous per access.
+struct alignas(32) U32x8 {
+  uint32_t v[8];
+};
+__device__ __forceinline__ U32x8 ld_stream_v8(const U32x8* p) {
+  U32x8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]),
+                 "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ U32x8 ld_weak_v8(const U32x8* p) {
+  U32x8 r;
+  asm volatile("ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]),
+                 "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_stream_v8(U32x8* p, const U32x8& r) {
+  asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p),
+               "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]),
+               "r"(r.v[6]), "r"(r.v[7])
+               : "memory");
+}
+
 // ------------------------------------------------------------- mbarrier ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

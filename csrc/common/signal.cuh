@@ -68,6 +68,13 @@ __device__ __forceinline__ void publish_epoch(uint32_t* flag_on_peer, uint32_t e
   ptx::st_release_sys(flag_on_peer, epoch);
 }
 
+// Same, without the stand-alone fence: st.release.sys is itself cumulative over
+// everything that happens-before it (the CTA's stores, ordered by the preceding
+// bar.sync), so hot per-chunk publishes pay one system-scope drain instead of two.
+__device__ __forceinline__ void publish_epoch_light(uint32_t* flag_on_peer, uint32_t epoch) {
+  ptx::st_release_sys(flag_on_peer, epoch);
+}
+
 // Grid-wide "last CTA publishes" helper: every CTA calls it (all threads); the
 // CTA that takes the final ticket publishes `epoch` to `flag_on_peer`.
 // `ticket` is a rank-local counter that counts up forever (no reset):

@@ -31,6 +31,8 @@ struct CopyTuning {
   int unroll = 0;    // LdSt: 16-byte loads in flight per thread (1,2,4,8); 0 -> 4
   int stage_kb = 0;  // Tma: smem stage size in KiB; 0 -> 16
   int stages = 0;    // Tma: number of smem stages; 0 -> 8
+  int vec_bytes = 0; // LdSt: 16 (LDG/STG.128) or 32 (sm_100 LDG/STG.256); 0 -> 16
+  int blocked = 0;   // LdSt: 1 = each CTA owns one contiguous region instead of a grid-stride
 };
 
 // Optional prologue wait + epilogue signal attached to a data-moving kernel so a

@@ -94,7 +94,7 @@ __device__ __forceinline__ void cta_copy_ldst(uint4* dst, const uint4* src, size
   for (; i < nvec; i += stride) ptx::st_stream_v4(dst + i, ptx::ld_weak_v4(src + i));
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
     fused_bench_kernel(const __grid_constant__ FusedTable table, int use_tma, uint32_t stage_bytes,
                        int stages) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -117,7 +117,20 @@ __global__ void __launch_bounds__(256)
     const float4* c = reinterpret_cast<const float4*>(me.c);
     float4* a = reinterpret_cast<float4*>(me.a);
     const size_t stride = static_cast<size_t>(ncta) * blockDim.x;
-    for (size_t i = static_cast<size_t>(lcta) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    size_t i = static_cast<size_t>(lcta) * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {  // 8 independent 128-bit loads in flight
+      float4 vb[4], vc[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        vb[k] = __ldcs(b + i + k * stride);
+        vc[k] = __ldcs(c + i + k * stride);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        __stcs(a + i + k * stride, make_float4(fmaf(me.s, vc[k].x, vb[k].x), fmaf(me.s, vc[k].y, vb[k].y),
+                                               fmaf(me.s, vc[k].z, vb[k].z), fmaf(me.s, vc[k].w, vb[k].w)));
+    }
+    for (; i < nvec; i += stride) {
       const float4 vb = __ldcs(b + i), vc = __ldcs(c + i);
       __stcs(a + i, make_float4(fmaf(me.s, vc.x, vb.x), fmaf(me.s, vc.y, vb.y),
                                 fmaf(me.s, vc.z, vb.z), fmaf(me.s, vc.w, vb.w)));
@@ -160,7 +173,7 @@ int launch_fused_bench(const FusedCommand* cmds, int n_cmds, CopyEngine engine,
                        const CopyTuning& tune, int device, cudaStream_t stream) {
   HPCP_REQUIRE(n_cmds >= 1 && n_cmds <= kFusedMaxCommands, "fused bench: 1..8 commands per group");
   const int sms = device_sm_count(device);
-  const int threads = 256;
+  const int threads = 512;
 
   // CTA budget: busy commands take what their work-item count needs (capped);
   // the rest of one resident wave (one CTA per SM) is shared by triad (weight 4)
@@ -174,12 +187,14 @@ int launch_fused_bench(const FusedCommand* cmds, int n_cmds, CopyEngine engine,
     } else if (cmds[k].kind == FusedKind::kBusy) {
       const size_t want = (std::max<size_t>(cmds[k].n, 1) + threads - 1) / threads;
       ctas[k] = static_cast<int>(std::min<size_t>(want, static_cast<size_t>(std::max(1, sms / 2))));
+      // a busy CTA only needs as many threads as work-items, but the block size is shared
       fixed += ctas[k];
     } else {
       weight_sum += cmds[k].kind == FusedKind::kTriad ? 4 : 1;
     }
   }
-  const int pool = std::max(sms - fixed, n_cmds);
+  // Two resident CTAs per SM (4 x 16 KiB smem stages each): one wave of 2*SMs CTAs.
+  const int pool = std::max(2 * sms - fixed, n_cmds);
   for (int k = 0; k < n_cmds; ++k) {
     if (ctas[k] != 0) continue;
     const int w = cmds[k].kind == FusedKind::kTriad ? 4 : 1;
@@ -210,7 +225,7 @@ int launch_fused_bench(const FusedCommand* cmds, int n_cmds, CopyEngine engine,
   }
 
   const uint32_t stage_bytes = static_cast<uint32_t>((tune.stage_kb > 0 ? tune.stage_kb : 16) * 1024);
-  const int stages = tune.stages > 0 ? tune.stages : 6;
+  const int stages = tune.stages > 0 ? tune.stages : 4;
   const size_t smem = engine == CopyEngine::kTma
                           ? static_cast<size_t>(stages) * stage_bytes + static_cast<size_t>(stages) * 8
                           : 0;

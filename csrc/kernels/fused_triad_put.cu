@@ -34,17 +34,6 @@ __device__ __forceinline__ float4 triad4(const float4& b, const float4& c, float
   return make_float4(fmaf(s, c.x, b.x), fmaf(s, c.y, b.y), fmaf(s, c.z, b.z), fmaf(s, c.w, b.w));
 }
 
-__device__ __forceinline__ float4 ld_f4_stream(const float4* p) {
-  const uint4 v = ptx::ld_stream_v4(reinterpret_cast<const uint4*>(p));
-  return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z),
-                     __uint_as_float(v.w));
-}
-__device__ __forceinline__ void st_f4_stream(float4* p, const float4& f) {
-  ptx::st_stream_v4(reinterpret_cast<uint4*>(p),
-                    make_uint4(__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z),
-                               __float_as_uint(f.w)));
-}
-
 __device__ __forceinline__ bool cta_prologue_wait(const SyncOps& sync) {
   if (sync.wait_flag == nullptr) return true;
   __shared__ int ok_s;
@@ -66,33 +55,61 @@ __device__ __forceinline__ void cta_epilogue(const SyncOps& sync, const uint32_t
 }
 
 // ------------------------------------------------------------ LdSt engine ----
-template <int U, bool kPut>
+// V = uint4 (4 floats, LDG/STG.128) or ptx::U32x8 (8 floats, LDG/STG.256).
+__device__ __forceinline__ uint4 ld_in(const uint4* p) { return ptx::ld_stream_v4(p); }
+__device__ __forceinline__ ptx::U32x8 ld_in(const ptx::U32x8* p) { return ptx::ld_stream_v8(p); }
+__device__ __forceinline__ void st_out(uint4* p, const uint4& v) { ptx::st_stream_v4(p, v); }
+__device__ __forceinline__ void st_out(ptx::U32x8* p, const ptx::U32x8& v) { ptx::st_stream_v8(p, v); }
+__device__ __forceinline__ uint32_t triad1(uint32_t b, uint32_t c, float s) {
+  return __float_as_uint(fmaf(s, __uint_as_float(c), __uint_as_float(b)));
+}
+__device__ __forceinline__ uint4 triad_vec(const uint4& b, const uint4& c, float s) {
+  return make_uint4(triad1(b.x, c.x, s), triad1(b.y, c.y, s), triad1(b.z, c.z, s), triad1(b.w, c.w, s));
+}
+__device__ __forceinline__ ptx::U32x8 triad_vec(const ptx::U32x8& b, const ptx::U32x8& c, float s) {
+  ptx::U32x8 r;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r.v[k] = triad1(b.v[k], c.v[k], s);
+  return r;
+}
+
+template <typename V, int U, bool kPut>
 __global__ void __launch_bounds__(512)
-    triad_put_ldst_kernel(float4* __restrict__ a_local, float4* __restrict__ a_peer,
-                          const float4* __restrict__ b, const float4* __restrict__ c, float s,
-                          size_t nvec, SyncOps sync, const uint32_t* arrive_flag,
-                          uint32_t arrive_epoch) {
+    triad_put_ldst_kernel(V* __restrict__ a_local, V* __restrict__ a_peer, const V* __restrict__ b,
+                          const V* __restrict__ c, float s, size_t nvec, int blocked, SyncOps sync,
+                          const uint32_t* arrive_flag, uint32_t arrive_epoch) {
   if (!cta_prologue_wait(sync)) return;
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  for (; i + (U - 1) * stride < nvec; i += U * stride) {
-    float4 vb[U], vc[U];
+  size_t begin, end, stride;
+  if (blocked) {
+    const size_t per = (nvec + gridDim.x - 1) / gridDim.x;
+    begin = static_cast<size_t>(blockIdx.x) * per;
+    end = begin + per < nvec ? begin + per : nvec;
+    stride = blockDim.x;
+    begin += threadIdx.x;
+  } else {
+    stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    begin = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    end = nvec;
+  }
+  size_t i = begin;
+  for (; i + (U - 1) * stride < end; i += U * stride) {
+    V vb[U], vc[U];
 #pragma unroll
     for (int k = 0; k < U; ++k) {
-      vb[k] = ld_f4_stream(b + i + k * stride);
-      vc[k] = ld_f4_stream(c + i + k * stride);
+      vb[k] = ld_in(b + i + k * stride);
+      vc[k] = ld_in(c + i + k * stride);
     }
 #pragma unroll
     for (int k = 0; k < U; ++k) {
-      const float4 va = triad4(vb[k], vc[k], s);
-      st_f4_stream(a_local + i + k * stride, va);
-      if (kPut) st_f4_stream(a_peer + i + k * stride, va);
+      const V va = triad_vec(vb[k], vc[k], s);
+      if (kPut) st_out(a_peer + i + k * stride, va);
+      st_out(a_local + i + k * stride, va);
     }
   }
-  for (; i < nvec; i += stride) {
-    const float4 va = triad4(ld_f4_stream(b + i), ld_f4_stream(c + i), s);
-    st_f4_stream(a_local + i, va);
-    if (kPut) st_f4_stream(a_peer + i, va);
+  for (; i < end; i += stride) {
+    const V va = triad_vec(ld_in(b + i), ld_in(c + i), s);
+    if (kPut) st_out(a_peer + i, va);
+    st_out(a_local + i, va);
   }
   cta_epilogue(sync, arrive_flag, arrive_epoch);
 }
@@ -228,31 +245,40 @@ int launch_triad_put(const TriadPutArgs& args, CopyEngine engine, const CopyTuni
   const bool put = args.a_peer != nullptr;
   int ctas = 0;
   if (engine == CopyEngine::kLdSt) {
-    const int threads = tune.threads > 0 ? tune.threads : 512;
+    const int threads = tune.threads > 0 ? std::min(tune.threads, 512) : 512;
     const int unroll = tune.unroll > 0 ? tune.unroll : 2;
-    const size_t per_cta = static_cast<size_t>(threads) * unroll;
+    const size_t per_cta = static_cast<size_t>(threads) * unroll * (tune.vec_bytes == 32 ? 2 : 1);
     const size_t want = std::max<size_t>(1, (nvec + per_cta - 1) / per_cta);
     const int cap = tune.ctas > 0 ? tune.ctas : sms * 2;
     ctas = static_cast<int>(std::min<size_t>(want, static_cast<size_t>(cap)));
-    float4* al = reinterpret_cast<float4*>(args.a_local);
-    float4* ap = reinterpret_cast<float4*>(args.a_peer);
-    const float4* b = reinterpret_cast<const float4*>(args.b);
-    const float4* c = reinterpret_cast<const float4*>(args.c);
-#define HPCP_TRIAD_LAUNCH(U)                                                                     \
-  do {                                                                                           \
-    if (put)                                                                                     \
-      triad_put_ldst_kernel<U, true><<<ctas, threads, 0, stream>>>(al, ap, b, c, args.s, nvec,   \
-                                                                   sync, arrive_flag,            \
-                                                                   arrive_epoch);                \
-    else                                                                                         \
-      triad_put_ldst_kernel<U, false><<<ctas, threads, 0, stream>>>(al, ap, b, c, args.s, nvec,  \
-                                                                    sync, arrive_flag,           \
-                                                                    arrive_epoch);               \
+    const bool wide = tune.vec_bytes == 32 && args.n % 8 == 0 &&
+                      ((reinterpret_cast<uintptr_t>(args.a_local) | reinterpret_cast<uintptr_t>(args.a_peer) |
+                        reinterpret_cast<uintptr_t>(args.b) | reinterpret_cast<uintptr_t>(args.c)) & 31) == 0;
+#define HPCP_TRIAD_LAUNCH(V, U)                                                                      \
+  do {                                                                                               \
+    V* al = reinterpret_cast<V*>(args.a_local);                                                      \
+    V* ap = reinterpret_cast<V*>(args.a_peer);                                                       \
+    const V* b = reinterpret_cast<const V*>(args.b);                                                 \
+    const V* c = reinterpret_cast<const V*>(args.c);                                                 \
+    const size_t nv = args.n * sizeof(float) / sizeof(V);                                            \
+    if (put)                                                                                         \
+      triad_put_ldst_kernel<V, U, true><<<ctas, threads, 0, stream>>>(                               \
+          al, ap, b, c, args.s, nv, tune.blocked, sync, arrive_flag, arrive_epoch);                  \
+    else                                                                                             \
+      triad_put_ldst_kernel<V, U, false><<<ctas, threads, 0, stream>>>(                              \
+          al, ap, b, c, args.s, nv, tune.blocked, sync, arrive_flag, arrive_epoch);                  \
   } while (0)
-    switch (unroll) {
-      case 1: HPCP_TRIAD_LAUNCH(1); break;
-      case 4: HPCP_TRIAD_LAUNCH(4); break;
-      default: HPCP_TRIAD_LAUNCH(2); break;
+    if (wide) {
+      switch (unroll) {
+        case 1: HPCP_TRIAD_LAUNCH(ptx::U32x8, 1); break;
+        default: HPCP_TRIAD_LAUNCH(ptx::U32x8, 2); break;
+      }
+    } else {
+      switch (unroll) {
+        case 1: HPCP_TRIAD_LAUNCH(uint4, 1); break;
+        case 4: HPCP_TRIAD_LAUNCH(uint4, 4); break;
+        default: HPCP_TRIAD_LAUNCH(uint4, 2); break;
+      }
     }
 #undef HPCP_TRIAD_LAUNCH
   } else {

@@ -55,27 +55,49 @@ __device__ __forceinline__ void epilogue_signal(const SyncOps& sync) {
 }
 
 // ------------------------------------------------------------ LdSt engine ----
-template <int U, bool kPeerSrc>
-__global__ void __launch_bounds__(512)
-    copy_ldst_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t nvec,
-                     size_t tail_bytes, SyncOps sync) {
+// V = uint4 (LDG/STG.128) or ptx::U32x8 (LDG/STG.256, sm_100+).
+template <typename V, bool kPeerSrc>
+__device__ __forceinline__ V ld_vec(const V* p);
+template <>
+__device__ __forceinline__ uint4 ld_vec<uint4, false>(const uint4* p) { return ptx::ld_stream_v4(p); }
+template <>
+__device__ __forceinline__ uint4 ld_vec<uint4, true>(const uint4* p) { return ptx::ld_peer_v4(p); }
+template <>
+__device__ __forceinline__ ptx::U32x8 ld_vec<ptx::U32x8, false>(const ptx::U32x8* p) { return ptx::ld_stream_v8(p); }
+template <>
+__device__ __forceinline__ ptx::U32x8 ld_vec<ptx::U32x8, true>(const ptx::U32x8* p) { return ptx::ld_weak_v8(p); }
+__device__ __forceinline__ void st_vec(uint4* p, const uint4& v) { ptx::st_stream_v4(p, v); }
+__device__ __forceinline__ void st_vec(ptx::U32x8* p, const ptx::U32x8& v) { ptx::st_stream_v8(p, v); }
+
+template <typename V, int U, bool kPeerSrc>
+__global__ void __launch_bounds__(1024)
+    copy_ldst_kernel(V* __restrict__ dst, const V* __restrict__ src, size_t nvec, size_t tail_bytes,
+                     int blocked, SyncOps sync) {
   if (!prologue_wait(sync)) return;
 
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-
-  for (; i + (U - 1) * stride < nvec; i += U * stride) {
-    uint4 v[U];
-#pragma unroll
-    for (int k = 0; k < U; ++k)
-      v[k] = kPeerSrc ? ptx::ld_peer_v4(src + i + k * stride) : ptx::ld_stream_v4(src + i + k * stride);
-#pragma unroll
-    for (int k = 0; k < U; ++k) ptx::st_stream_v4(dst + i + k * stride, v[k]);
+  // interleaved: vector i of batch k is handled by thread (i mod stride); blocked: every CTA
+  // owns one contiguous range (sequential NVLink / HBM pages per CTA).
+  size_t begin, end, stride;
+  if (blocked) {
+    const size_t per = (nvec + gridDim.x - 1) / gridDim.x;
+    begin = static_cast<size_t>(blockIdx.x) * per;
+    end = begin + per < nvec ? begin + per : nvec;
+    stride = blockDim.x;
+    begin += threadIdx.x;
+  } else {
+    stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    begin = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    end = nvec;
   }
-  for (; i < nvec; i += stride) {
-    const uint4 v = kPeerSrc ? ptx::ld_peer_v4(src + i) : ptx::ld_stream_v4(src + i);
-    ptx::st_stream_v4(dst + i, v);
+  size_t i = begin;
+  for (; i + (U - 1) * stride < end; i += U * stride) {
+    V v[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) v[k] = ld_vec<V, kPeerSrc>(src + i + k * stride);
+#pragma unroll
+    for (int k = 0; k < U; ++k) st_vec(dst + i + k * stride, v[k]);
   }
+  for (; i < end; i += stride) st_vec(dst + i, ld_vec<V, kPeerSrc>(src + i));
   if (tail_bytes != 0 && blockIdx.x == 0 && threadIdx.x < tail_bytes) {
     const unsigned char* s = reinterpret_cast<const unsigned char*>(src + nvec);
     unsigned char* d = reinterpret_cast<unsigned char*>(dst + nvec);
@@ -229,14 +251,21 @@ void launch_barrier_all(uint32_t* const* pads, int rank, int world, uint32_t epo
 
 namespace {
 
-template <bool kPeerSrc>
-void launch_ldst(uint4* dst, const uint4* src, size_t nvec, size_t tail, int unroll, int ctas,
-                 int threads, const SyncOps& sync, cudaStream_t stream) {
+template <typename V, bool kPeerSrc>
+void launch_ldst(void* dst, const void* src, size_t nvec, size_t tail, int unroll, int ctas,
+                 int threads, int blocked, const SyncOps& sync, cudaStream_t stream) {
+  V* d = static_cast<V*>(dst);
+  const V* s = static_cast<const V*>(src);
   switch (unroll) {
-    case 1: copy_ldst_kernel<1, kPeerSrc><<<ctas, threads, 0, stream>>>(dst, src, nvec, tail, sync); break;
-    case 2: copy_ldst_kernel<2, kPeerSrc><<<ctas, threads, 0, stream>>>(dst, src, nvec, tail, sync); break;
-    case 8: copy_ldst_kernel<8, kPeerSrc><<<ctas, threads, 0, stream>>>(dst, src, nvec, tail, sync); break;
-    default: copy_ldst_kernel<4, kPeerSrc><<<ctas, threads, 0, stream>>>(dst, src, nvec, tail, sync); break;
+    case 1: copy_ldst_kernel<V, 1, kPeerSrc><<<ctas, threads, 0, stream>>>(d, s, nvec, tail, blocked, sync); break;
+    case 2: copy_ldst_kernel<V, 2, kPeerSrc><<<ctas, threads, 0, stream>>>(d, s, nvec, tail, blocked, sync); break;
+    case 8:
+      if constexpr (sizeof(V) == 16) {  // 8 x 256-bit would not fit 64 registers/thread
+        copy_ldst_kernel<V, 8, kPeerSrc><<<ctas, threads, 0, stream>>>(d, s, nvec, tail, blocked, sync);
+        break;
+      }
+      [[fallthrough]];
+    default: copy_ldst_kernel<V, 4, kPeerSrc><<<ctas, threads, 0, stream>>>(d, s, nvec, tail, blocked, sync); break;
   }
 }
 
@@ -255,18 +284,30 @@ int launch_copy(void* dst, const void* src, size_t bytes, bool src_is_peer, Copy
   int ctas = 0;
 
   if (engine == CopyEngine::kLdSt) {
-    const int threads = tune.threads > 0 ? tune.threads : 512;
+    const int threads = tune.threads > 0 ? std::min(tune.threads, 1024) : 512;
     const int unroll = tune.unroll > 0 ? tune.unroll : 4;
+    const bool wide = tune.vec_bytes == 32 &&
+                      (reinterpret_cast<uintptr_t>(dst) & 31) == 0 &&
+                      (reinterpret_cast<uintptr_t>(src) & 31) == 0;
+    const size_t vb = wide ? 32 : 16;
+    const size_t nv = bytes / vb;
+    const size_t tl = bytes % vb;
     const size_t per_cta = static_cast<size_t>(threads) * unroll;
-    const size_t want = std::max<size_t>(1, (nvec + per_cta - 1) / per_cta);
+    const size_t want = std::max<size_t>(1, (nv + per_cta - 1) / per_cta);
     const int cap = tune.ctas > 0 ? tune.ctas : sms * 2;
     ctas = static_cast<int>(std::min<size_t>(want, static_cast<size_t>(cap)));
-    if (src_is_peer)
-      launch_ldst<true>(static_cast<uint4*>(dst), static_cast<const uint4*>(src), nvec, tail, unroll,
-                        ctas, threads, sync, stream);
-    else
-      launch_ldst<false>(static_cast<uint4*>(dst), static_cast<const uint4*>(src), nvec, tail,
-                         unroll, ctas, threads, sync, stream);
+    HPCP_REQUIRE(tl < static_cast<size_t>(threads), "launch_copy: tail larger than the CTA");
+    if (wide) {
+      if (src_is_peer)
+        launch_ldst<ptx::U32x8, true>(dst, src, nv, tl, unroll, ctas, threads, tune.blocked, sync, stream);
+      else
+        launch_ldst<ptx::U32x8, false>(dst, src, nv, tl, unroll, ctas, threads, tune.blocked, sync, stream);
+    } else {
+      if (src_is_peer)
+        launch_ldst<uint4, true>(dst, src, nv, tl, unroll, ctas, threads, tune.blocked, sync, stream);
+      else
+        launch_ldst<uint4, false>(dst, src, nv, tl, unroll, ctas, threads, tune.blocked, sync, stream);
+    }
   } else {
     const uint32_t stage_bytes = static_cast<uint32_t>((tune.stage_kb > 0 ? tune.stage_kb : 16) * 1024);
     const int stages = tune.stages > 0 ? tune.stages : 8;

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(512) ring_allreduce_kernel(const __grid_consta
         a.vc[i] = Vec4<T>::add(a.vc[i], x);
       }
       __syncthreads();  // whole chunk stored by this CTA (and ok_s consumed by everyone)
-      if (fwd && threadIdx.x == 0) publish_epoch(a.arrived_right + c, a.epoch_base + t + 1);
+      if (fwd && threadIdx.x == 0) publish_epoch_light(a.arrived_right + c, a.epoch_base + t + 1);
     }
   }
 }
@@ -175,23 +175,40 @@ __device__ __forceinline__ void grid_then_node_barrier(uint32_t* ticket, uint32_
   }
 }
 
-template <typename T>
+// W = compile-time bound on the world size (register arrays), U = vectors per thread per trip:
+// up to U*W independent NVLink loads in flight per thread.
+template <typename T, int W, int U>
 __global__ void __launch_bounds__(512) two_shot_kernel(const __grid_constant__ TwoShotDev a) {
   const size_t base = static_cast<size_t>(a.rank) * a.slice_vec;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.slice_vec;
-       i += stride) {
-    uint4 x[kApiMaxRanks];
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + (U - 1) * stride < a.slice_vec; i += U * stride) {
+    uint4 x[W][U];
 #pragma unroll
-    for (int p = 0; p < kApiMaxRanks; ++p)
-      if (p < a.world) x[p] = ptx::ld_peer_v4(a.va[p] + base + i);
-    uint4 acc = x[0];
+    for (int q = 0; q < W; ++q)
+      if (q < a.world) {
+        const int p = (a.rank + q) % a.world;  // start at self, then the neighbours: spreads load
 #pragma unroll
-    for (int p = 1; p < kApiMaxRanks; ++p)
-      if (p < a.world) acc = Vec4<T>::add(acc, x[p]);
+        for (int u = 0; u < U; ++u) x[q][u] = ptx::ld_peer_v4(a.va[p] + base + i + u * stride);
+      }
 #pragma unroll
-    for (int p = 0; p < kApiMaxRanks; ++p)
-      if (p < a.world) ptx::st_stream_v4(a.vc[p] + base + i, acc);
+    for (int q = 1; q < W; ++q)
+      if (q < a.world) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) x[0][u] = Vec4<T>::add(x[0][u], x[q][u]);
+      }
+#pragma unroll
+    for (int q = 0; q < W; ++q)
+      if (q < a.world) {
+        const int p = (a.rank + q) % a.world;
+#pragma unroll
+        for (int u = 0; u < U; ++u) ptx::st_stream_v4(a.vc[p] + base + i + u * stride, x[0][u]);
+      }
+  }
+  for (; i < a.slice_vec; i += stride) {
+    uint4 acc = ptx::ld_peer_v4(a.va[0] + base + i);
+    for (int p = 1; p < a.world; ++p) acc = Vec4<T>::add(acc, ptx::ld_peer_v4(a.va[p] + base + i));
+    for (int p = 0; p < a.world; ++p) ptx::st_stream_v4(a.vc[p] + base + i, acc);
   }
   grid_then_node_barrier(a.ticket, a.ticket_target, a.pads, a.rank, a.world, a.barrier_epoch,
                          a.timeout_ns, a.status);
@@ -216,20 +233,28 @@ template <typename T>
 __global__ void __launch_bounds__(512) nvls_kernel(const __grid_constant__ NvlsDev a) {
   const size_t base = static_cast<size_t>(a.rank) * a.slice_vec;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.slice_vec;
-       i += stride) {
-    const size_t off = (base + i) * 16;
+  auto reduce_at = [&](size_t off) {
     float4 r;
     if (std::is_floating_point<T>::value) {
       r = ptx::multimem_ld_reduce_add_f32x4(a.va_mc + off);
-    } else {  // int: scalar in-switch adds, vector broadcast of the raw bits
+    } else {  // int: scalar in-switch adds (no vector integer multimem.add), vector broadcast of the bits
       r.x = __int_as_float(ptx::multimem_ld_reduce_add_s32(a.va_mc + off));
       r.y = __int_as_float(ptx::multimem_ld_reduce_add_s32(a.va_mc + off + 4));
       r.z = __int_as_float(ptx::multimem_ld_reduce_add_s32(a.va_mc + off + 8));
       r.w = __int_as_float(ptx::multimem_ld_reduce_add_s32(a.va_mc + off + 12));
     }
-    ptx::multimem_st_f32x4(a.vc_mc + off, r);
+    return r;
+  };
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < a.slice_vec; i += 4 * stride) {  // 4 in-switch reductions in flight
+    float4 r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[k] = reduce_at((base + i + k * stride) * 16);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ptx::multimem_st_f32x4(a.vc_mc + (base + i + k * stride) * 16, r[k]);
   }
+  for (; i < a.slice_vec; i += stride)
+    ptx::multimem_st_f32x4(a.vc_mc + (base + i) * 16, reduce_at((base + i) * 16));
   grid_then_node_barrier(a.ticket, a.ticket_target, a.pads, a.rank, a.world, a.barrier_epoch,
                          a.timeout_ns, a.status);
 }
@@ -281,8 +306,10 @@ void launch_count_mismatch(const void* v, size_t n, double expected, ElemType ty
   HPCP_CUDA(cudaGetLastError());
 }
 
+constexpr size_t kRingDefaultChunk = 32768;  // 128 KiB of 4-byte elements per arrival word
+
 size_t ring_num_chunks(size_t n, size_t chunk_elems) {
-  const size_t ce = chunk_elems == 0 ? 8192 : chunk_elems;
+  const size_t ce = chunk_elems == 0 ? kRingDefaultChunk : chunk_elems;
   return (n + ce - 1) / ce;
 }
 
@@ -290,7 +317,7 @@ void launch_ring_allreduce(const RingArgs& args, ElemType type, int ctas, int de
                            cudaStream_t stream) {
   HPCP_REQUIRE(args.world >= 1 && args.world <= kApiMaxRanks, "ring: world out of range");
   HPCP_REQUIRE(args.n % 4 == 0, "ring: n must be a multiple of 4 elements");
-  const size_t ce = args.chunk_elems == 0 ? 8192 : args.chunk_elems;
+  const size_t ce = args.chunk_elems == 0 ? kRingDefaultChunk : args.chunk_elems;
   HPCP_REQUIRE(ce % 4 == 0, "ring: chunk_elems must be a multiple of 4");
   RingDev d{};
   d.va = static_cast<const uint4*>(args.va);
@@ -312,6 +339,23 @@ void launch_ring_allreduce(const RingArgs& args, ElemType type, int ctas, int de
   int grid = ctas > 0 ? ctas : sms * 2;
   grid = std::min(grid, sms * 4);
   grid = static_cast<int>(std::min<size_t>(static_cast<size_t>(grid), std::max<size_t>(d.n_chunks, 1)));
+  if (ctas <= 0 && d.n_chunks > static_cast<size_t>(grid)) {
+    // Chunks are dealt round-robin: pick the grid in [3/4 cap, cap] that wastes the least
+    // (every CTA should own the same number of chunks, or the slowest CTA paces the ring).
+    int best = grid;
+    size_t best_waste = ~size_t{0};
+    for (int g = grid; g >= grid * 3 / 4 && g >= 1; --g) {
+      const size_t rounds = (d.n_chunks + g - 1) / g;
+      const size_t waste = rounds * g - d.n_chunks;
+      // compare wasted chunk-slots relative to useful parallelism
+      if (waste * best < best_waste * g || best_waste == ~size_t{0}) {
+        best_waste = waste;
+        best = g;
+      }
+      if (waste == 0) break;
+    }
+    grid = best;
+  }
   if (type == ElemType::kFloat)
     ring_allreduce_kernel<float><<<grid, 512, 0, stream>>>(d);
   else
@@ -340,10 +384,22 @@ int launch_allreduce_two_shot(const TwoShotArgs& args, ElemType type, int ctas, 
   const int sms = device_sm_count(device);
   const int grid = grid_for(std::max<size_t>(d.slice_vec, 1), 512, ctas > 0 ? ctas : sms * 2);
   d.ticket_target = args.ticket_base + static_cast<uint32_t>(grid);
-  if (type == ElemType::kFloat)
-    two_shot_kernel<float><<<grid, 512, 0, stream>>>(d);
+#define HPCP_TWO_SHOT(W, U)                                          \
+  do {                                                               \
+    if (type == ElemType::kFloat)                                    \
+      two_shot_kernel<float, W, U><<<grid, 512, 0, stream>>>(d);     \
+    else                                                             \
+      two_shot_kernel<int, W, U><<<grid, 512, 0, stream>>>(d);       \
+  } while (0)
+  if (args.world <= 2)
+    HPCP_TWO_SHOT(2, 4);
+  else if (args.world <= 4)
+    HPCP_TWO_SHOT(4, 4);
+  else if (args.world <= 8)
+    HPCP_TWO_SHOT(8, 2);
   else
-    two_shot_kernel<int><<<grid, 512, 0, stream>>>(d);
+    HPCP_TWO_SHOT(16, 1);
+#undef HPCP_TWO_SHOT
   HPCP_CUDA(cudaGetLastError());
   return grid;
 }

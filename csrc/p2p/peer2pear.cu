@@ -79,7 +79,7 @@ void usage() {
          "  --mapping compact|spread|compact_plan   rank -> GPU policy (default compact)\n"
          "  --fused-triad            fused a=b+s*c + put of a (one kernel) instead of a plain copy\n"
          "  --no-verify              skip the exact receiver-side check\n"
-         "  --ctas N --threads N --unroll N --stages N --stage-kb N    kernel tuning\n"
+         "  --ctas N --threads N --unroll N --vec 16|32 --blocked --stages N --stage-kb N   kernel tuning\n"
          "  --json FILE              append one JSON row per size/direction\n";
 }
 
@@ -125,6 +125,10 @@ Config parse(int argc, char** argv) {
       c.tune.stages = std::atoi(val().c_str());
     } else if (a == "--stage-kb") {
       c.tune.stage_kb = std::atoi(val().c_str());
+    } else if (a == "--vec") {
+      c.tune.vec_bytes = std::atoi(val().c_str());
+    } else if (a == "--blocked") {
+      c.tune.blocked = 1;
     } else if (a == "--timeout-s") {
       c.timeout_ns = static_cast<uint64_t>(std::atof(val().c_str()) * 1e9);
     } else if (!a.empty() && a[0] == '-') {

@@ -39,6 +39,17 @@ def test_copy_ldst_unroll_variants(native, dev, unroll):
     assert torch.equal(dst, src)
 
 
+@pytest.mark.parametrize("tune", [{"vec_bytes": 32}, {"vec_bytes": 32, "blocked": 1, "ctas": 53},
+                                  {"blocked": 1, "threads": 1024, "unroll": 8}, {"vec_bytes": 32, "unroll": 8}])
+@pytest.mark.parametrize("n", [(8 << 20) + 32, 1000003, 4096])
+def test_copy_ldst_wide_and_blocked(native, dev, tune, n):
+    src = torch.randint(0, 256, (n,), dtype=torch.uint8, device=dev)
+    dst = torch.zeros(n + 64, dtype=torch.uint8, device=dev)
+    native.copy(dst.data_ptr(), src.data_ptr(), n, False, "ldst", tune, {}, 0, _stream())
+    torch.cuda.synchronize()
+    assert torch.equal(dst[:n], src) and int(dst[n:].sum()) == 0
+
+
 @pytest.mark.parametrize("stages,stage_kb", [(2, 8), (4, 16), (8, 16), (6, 32)])
 def test_copy_tma_stage_variants(native, dev, stages, stage_kb):
     n = (24 << 20) + 4096 + 16
@@ -101,6 +112,8 @@ def test_fill_and_verify_pattern(native, dev):
 
 
 @pytest.mark.parametrize("engine,tune", [("ldst", {}), ("ldst", {"unroll": 4}), ("ldst", {"unroll": 1}),
+                                         ("ldst", {"vec_bytes": 32}), ("ldst", {"vec_bytes": 32, "blocked": 1}),
+                                         ("ldst", {"blocked": 1, "ctas": 37}),
                                          ("tma", {}), ("tma", {"stages": 3, "stage_kb": 8})])
 @pytest.mark.parametrize("n", [4096, (1 << 22) + 8, 12345 * 4])
 def test_triad_put_matches_fp32_reference(native, dev, engine, tune, n):

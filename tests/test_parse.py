@@ -38,3 +38,16 @@ def test_roundtrip_with_real_driver_output(native):
                                         "fake:C=0.01,MD=0.0005,HD=0.0002,DH=0.0002,overlap=0.9")
     t = parse_log("export X=1\n" + out)
     assert t["X=1"]["C MD"]["nowait"] == "SUCCESS" and "HD DH" in t["X=1"]
+
+
+def test_clock_summary_flags_throttle_reasons():
+    from hpc_patterns_b200.utils.clocks import summarize
+
+    lines = ["0, 1965, 1965, 950.0, Not Active, Not Active, Not Active, Active",
+             "0, 1800, 1965, 980.0, Not Active, Not Active, Not Active, Active",
+             "0, 210, 1965, 140.0, Not Active, Not Active, Not Active, Not Active",
+             "garbage"]
+    s = summarize(lines)
+    assert s["sm_max_mhz"] == 1965 and s["reasons"] == ["sw_power_cap"] and s["samples"] == 3
+    assert s["sm_mhz"] in (1800, 1882.5, 1965)   # median of the samples under load
+    assert summarize([])["samples"] == 0
