@@ -318,6 +318,16 @@ PYBIND11_MODULE(_C, m) {
       py::arg("commands"), py::arg("engine") = "tma", py::arg("tune") = py::dict(),
       py::arg("device") = 0, py::arg("stream") = 0);
 
+  m.def("tc_busy_operand_bytes", &tc_busy_operand_bytes);
+  m.def("tc_busy_out_elems_per_cta", &tc_busy_out_elems_per_cta);
+  m.def("tc_fill_operands", [](uintptr_t operands, uintptr_t stream) {
+    launch_tc_fill_operands(as_ptr<void>(operands), as_stream(stream));
+  });
+  m.def("tc_busy", [](uintptr_t operands, uintptr_t out, int ctas, uint32_t tripcount, uintptr_t stream) {
+    launch_tc_busy(as_ptr<const void>(operands), as_ptr<float>(out), ctas, tripcount, as_stream(stream));
+  }, py::arg("operands"), py::arg("out"), py::arg("ctas"), py::arg("tripcount"), py::arg("stream") = 0,
+  "tcgen05 tile loop: out[cta] = tripcount * (A[128x64] . B[256x64]^T), operands via TMA, accumulator in TMEM.");
+
   // ------------------------------------------------------------ allreduce ----
   m.def("init3", [](uintptr_t va, uintptr_t vb, uintptr_t vc, size_t n, double a, double b, double c,
                     const std::string& dtype, uintptr_t stream) {

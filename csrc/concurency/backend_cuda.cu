@@ -59,6 +59,8 @@ struct DevCommand {
   void submit(cudaStream_t s) const {
     if (name == "C") {
       launch_busy_wait(a, n, tripcount, s);
+    } else if (name == "T") {
+      launch_tc_busy(b, a, static_cast<int>(n), static_cast<uint32_t>(tripcount), s);
     } else if (name == "A") {
       TriadPutArgs t;
       t.a_local = a;
@@ -89,7 +91,7 @@ class CudaBackend final : public Backend {
     return {"in_order", "out_of_order", "host_threads", "nowait", "fused"};
   }
   std::string memory_letters() const override { return peer_ >= 0 ? "MDHSP" : "MDHS"; }
-  std::string compute_letters() const override { return "CA"; }
+  std::string compute_letters() const override { return "CAT"; }
 
   BenchResult run(const BenchRequest& req) override {
     HPCP_CUDA(cudaSetDevice(device_));
@@ -138,6 +140,13 @@ class CudaBackend final : public Backend {
       if (name == "C") {
         c.tripcount = req.params.at("tripcount_C");
         c.a = static_cast<float*>(alloc_bytes(c.n * sizeof(float), AllocKind::kDevice, device_, true));
+      } else if (name == "T") {
+        // n = CTAs (one 128x256 accumulator tile each); b = bf16 operands A|B; a = fp32 results.
+        c.tripcount = req.params.at("tripcount_T");
+        c.a = static_cast<float*>(alloc_bytes(c.n * tc_busy_out_elems_per_cta() * sizeof(float),
+                                              AllocKind::kDevice, device_, true));
+        c.b = static_cast<float*>(alloc_bytes(tc_busy_operand_bytes(), AllocKind::kDevice, device_, true));
+        launch_tc_fill_operands(c.b, nullptr);
       } else if (name == "A") {
         c.a = static_cast<float*>(alloc_bytes(c.bytes(), AllocKind::kDevice, device_, true));
         c.b = static_cast<float*>(alloc_bytes(c.bytes(), AllocKind::kDevice, device_, true));
@@ -407,6 +416,9 @@ class CudaBackend final : public Backend {
         f.a = c.a;
         f.b = c.b;
         f.c = c.c;
+      } else if (c.name == "T") {
+        side.push_back(&c);  // tensor-core tile loop: its own (TMEM-allocating) kernel, launched alongside
+        continue;
       } else if (c.src_kind == AllocKind::kPageable || c.dst_kind == AllocKind::kPageable) {
         side.push_back(&c);  // a kernel cannot dereference pageable host memory on x86 B200
         continue;

@@ -81,7 +81,9 @@ bool is_compute_command(const std::string& cmd) {
 }
 
 std::string tuned_parameter_of(const std::string& cmd) {
-  return cmd == "C" ? "tripcount_C" : "globalsize_" + cmd;
+  if (cmd == "C") return "tripcount_C";
+  if (cmd == "T") return "tripcount_T";  // tensor-core tile loop: duration ~ passes over the tile
+  return "globalsize_" + cmd;
 }
 
 std::string usage_text(const std::string& program, const Backend& backend) {
@@ -197,12 +199,16 @@ Options parse_arguments(const std::vector<std::string>& args, const Backend& bac
 Params resolve_parameters(const Options& opt) {
   std::map<std::string, long> cli = opt.cli_params;
   for (const auto& g : opt.groups)
-    for (const auto& c : g) cli.emplace("globalsize_" + c, -1);
+    for (const auto& c : g) {
+      cli.emplace("globalsize_" + c, -1);
+      if (c == "T") cli.emplace("tripcount_T", -1);
+    }
 
   auto default_of = [&](const std::string& key) -> size_t {
     if (key == "globalsize_C") return 1;
     if (key == "tripcount_C") return 40000;
-    if (key == "globalsize_T") return 148;  // one tile loop per SM
+    if (key == "globalsize_T") return 148;  // one tile loop (CTA) per SM
+    if (key == "tripcount_T") return 20000; // passes over the 128x256x64 tile (4 tcgen05.mma each)
     if (starts_with(key, "globalsize_")) {
       const long dm = cli.at("globalsize_default_memory");
       if (dm != -1) return static_cast<size_t>(dm);
@@ -415,6 +421,7 @@ int run(const std::vector<std::string>& argv_tail, Backend& backend, std::ostrea
     const std::string key = tuned_parameter_of(c);
     out << "  " << key << ": " << params[key] << std::endl;
     if (c == "C") out << "  globalsize_C: " << params["globalsize_C"] << std::endl;
+    if (c == "T") out << "  globalsize_T: " << params["globalsize_T"] << std::endl;
   }
 
   int status = 0;

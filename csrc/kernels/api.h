@@ -121,6 +121,16 @@ int launch_fused_bench(const FusedCommand* cmds, int n_cmds, CopyEngine engine,
 // The stand-alone busy-wait command (N work-items x 64*tripcount dependent FMAs).
 void launch_busy_wait(float* out, size_t n_items, size_t tripcount, cudaStream_t stream);
 
+// --------------------------------------------- tensor-core compute command ----
+// `T`: per-CTA bf16 tile D[128x256] += A[128x64] . B[256x64]^T repeated `tripcount` times with
+// tcgen05.mma (TMEM accumulator), operands fetched once by TMA.  `operands` holds A then B
+// (tc_busy_operand_bytes()), `out` receives ctas * 128 * 256 floats = tripcount * (A . B^T).
+size_t tc_busy_operand_bytes();
+size_t tc_busy_out_elems_per_cta();
+void launch_tc_fill_operands(void* operands, cudaStream_t stream);
+void launch_tc_busy(const void* operands, float* out, int ctas, uint32_t tripcount,
+                    cudaStream_t stream);
+
 // ------------------------------------------------------ allreduce miniapp ----
 enum class ElemType : int { kFloat = 0, kInt = 1 };
 

@@ -273,3 +273,50 @@ def test_smoke_entry():
     import __graft_entry__ as g
 
     g.smoke()
+
+
+@pytest.mark.parametrize("tripcount,ctas", [(1, 1), (3, 5), (100, 148)])
+def test_tcgen05_tile_loop_matches_reference(native, dev, tripcount, ctas):
+    """T command: out[cta] = tripcount * (A . B^T) with bf16 operands, fp32 TMEM accumulation."""
+    ops = torch.zeros(native.tc_busy_operand_bytes() // 2, dtype=torch.bfloat16, device=dev)
+    per = native.tc_busy_out_elems_per_cta()
+    out = torch.full((ctas * per,), float("nan"), device=dev)
+    native.tc_fill_operands(ops.data_ptr(), _stream())
+    native.tc_busy(ops.data_ptr(), out.data_ptr(), ctas, tripcount, _stream())
+    torch.cuda.synchronize()
+    a = ops[:128 * 64].view(128, 64).float()
+    b = ops[128 * 64:].view(256, 64).float()
+    # plain PyTorch fp32 reference of the same op
+    ref = tripcount * (a @ b.t())
+    got = out.view(ctas, 128, 256)
+    assert torch.equal(got[0], ref), (got[0] - ref).abs().max()
+    assert bool((got == got[0]).all())
+    assert float(a.abs().max()) == 1.0 and float(b.abs().max()) == 2.0
+
+
+def test_tcgen05_duration_scales_with_tripcount(native, dev):
+    ops = torch.zeros(native.tc_busy_operand_bytes() // 2, dtype=torch.bfloat16, device=dev)
+    out = torch.zeros(148 * native.tc_busy_out_elems_per_cta(), device=dev)
+    native.tc_fill_operands(ops.data_ptr(), _stream())
+
+    def run(tc):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        native.tc_busy(ops.data_ptr(), out.data_ptr(), 148, tc, _stream())
+        torch.cuda.synchronize()
+        e0.record()
+        native.tc_busy(ops.data_ptr(), out.data_ptr(), 148, tc, _stream())
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    t1, t2 = run(20000), run(40000)
+    assert 1.6 < t2 / t1 < 2.4, (t1, t2)
+    flops = 148 * 40000 * 2.0 * 128 * 256 * 64
+    print(f"tcgen05 tile loop: {flops / (t2 * 1e-3) / 1e12:.0f} TFLOP/s bf16 over 148 CTAs")
+
+
+def test_concurency_tensor_command(native):
+    rc, out, err = native.concurency_main(["nowait", "--repetitions", "3", "--globalsize_default_memory", "8000000",
+                                           "--commands", "T", "H2D", "--commands", "T", "C"], "cuda")
+    assert out.count("## nowait | T") == 2, out + err
+    assert "tripcount_T" in out
