@@ -36,7 +36,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--bytes", type=int, default=1179648 * 40 * 4)
-    ap.add_argument("--engine", default=os.environ.get("HPCP_BENCH_ENGINE", "ldst"), choices=("ldst", "tma"))
+    ap.add_argument("--engine", default=os.environ.get("HPCP_BENCH_ENGINE", "tma"), choices=("ldst", "tma"))
     ap.add_argument("--ctas", type=int, default=int(os.environ.get("HPCP_BENCH_CTAS", "0")))
     ap.add_argument("--unroll", type=int, default=int(os.environ.get("HPCP_BENCH_UNROLL", "0")))
     ap.add_argument("--vec", type=int, default=int(os.environ.get("HPCP_BENCH_VEC", "0")))
