@@ -51,3 +51,24 @@ def test_clock_summary_flags_throttle_reasons():
     assert s["sm_max_mhz"] == 1965 and s["reasons"] == ["sw_power_cap"] and s["samples"] == 3
     assert s["sm_mhz"] in (1800, 1882.5, 1965)   # median of the samples under load
     assert summarize([])["samples"] == 0
+
+
+def test_report_tables(tmp_path):
+    import json
+
+    from hpc_patterns_b200.utils import report
+
+    rows = [{"pattern": "peer2pear", "label": "x", "transport": "put", "engine": "tma", "ranks": 2, "bytes": 1024,
+             "uni_GBps": 385.0, "bi_GBps": 700.0},
+            {"pattern": "allreduce", "algo": "ring", "type": "float", "ranks": 8, "elements": 1 << 25, "ms": 1.2,
+             "GBps_sent_per_rank": 770.0},
+            {"pattern": "concurency", "backend": "fake", "mode": "fused", "commands": ["C", "DP"],
+             "serial_total_us": 200, "concurrent_total_us": 105, "speedup": 1.9, "max_speedup": 2.0,
+             "overlap_fraction": 0.95, "verdict": "SUCCESS"}]
+    p = tmp_path / "rows.jsonl"
+    p.write_text("\n".join(json.dumps(r) for r in rows) + "\nnot json\n")
+    text = report.render(report.load_rows([str(p)]))
+    assert "| 0.50 | 0.43 |" in text          # 385 / 770 and 385 / 900
+    assert "| 1.00 | 0.86 |" in text          # 770 / 770 and 770 / 900
+    assert "95%" in text and "SUCCESS" in text
+    assert report.measured_hbm_gbps(str(tmp_path)) == report.HBM_FALLBACK_GBPS
