@@ -35,6 +35,7 @@ AllocKind alloc_kind_from_letter(char c) {
     case 'H': return AllocKind::kPinned;
     case 'S': return AllocKind::kManaged;
     case 'M': return AllocKind::kPageable;
+    case 'R': return AllocKind::kMapped;
     default: HPCP_FAIL(std::string("unknown allocation letter '") + c + "'");
   }
 }
@@ -45,6 +46,7 @@ const char* alloc_kind_name(AllocKind k) {
     case AllocKind::kPinned: return "pinned-host";
     case AllocKind::kManaged: return "managed";
     case AllocKind::kPageable: return "pageable-host";
+    case AllocKind::kMapped: return "mapped-host-malloc";
   }
   return "?";
 }
@@ -80,6 +82,25 @@ void* alloc_bytes(size_t bytes, AllocKind kind, int device, bool zero) {
       HPCP_REQUIRE(p != nullptr, "host allocation failed");
       break;
     }
+    case AllocKind::kMapped: {
+      DeviceGuard g(device);
+      const size_t rounded = (n + 4095) / 4096 * 4096;
+      void* host = std::aligned_alloc(4096, rounded);
+      HPCP_REQUIRE(host != nullptr, "host allocation failed");
+      if (zero) std::memset(host, 0, rounded);
+      const cudaError_t e = cudaHostRegister(host, rounded, cudaHostRegisterPortable | cudaHostRegisterMapped);
+      if (e != cudaSuccess) {
+        std::free(host);
+        HPCP_CUDA(e);
+      }
+      void* dev_alias = nullptr;
+      HPCP_CUDA(cudaHostGetDevicePointer(&dev_alias, host, 0));
+      // With unified addressing the alias equals the host pointer; the code below relies on it
+      // to unregister/free through the same address.
+      HPCP_REQUIRE(dev_alias == host, "mapped host memory has a distinct device alias on this platform");
+      p = host;
+      break;
+    }
   }
   return p;
 }
@@ -91,6 +112,10 @@ void free_bytes(void* p, AllocKind kind) {
     case AllocKind::kManaged: (void)cudaFree(p); break;
     case AllocKind::kPinned: (void)cudaFreeHost(p); break;
     case AllocKind::kPageable: std::free(p); break;
+    case AllocKind::kMapped:
+      (void)cudaHostUnregister(p);
+      std::free(p);
+      break;
   }
 }
 

@@ -30,6 +30,10 @@ enum class AllocKind : int {
   kPinned = 1,   // 'H' cudaHostAlloc(portable|mapped)
   kManaged = 2,  // 'S' cudaMallocManaged
   kPageable = 3, // 'M' plain calloc (copy-engine commands only; kernels cannot touch it)
+  kMapped = 4,   // 'R' host malloc *mapped* to the device: aligned_alloc + cudaHostRegister(mapped),
+                 //     kernels use the device alias from cudaHostGetDevicePointer — the analogue of
+                 //     OpenMP `target enter data map(alloc)` + `use_device_ptr`
+                 //     (allreduce-map-mpi-omp-offload.cpp:113-115,38)
 };
 
 AllocKind alloc_kind_from_letter(char c);  // 'D','H','S','M'

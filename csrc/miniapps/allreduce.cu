@@ -66,6 +66,8 @@ void print_help() {
                " -H          pinned host memory   (cudaHostAlloc)\n"
                " -D          device memory        (cudaMalloc, default)\n"
                " -S          managed memory       (cudaMallocManaged)\n"
+               " -R          host malloc mapped to the device (cudaHostRegister + device alias:\n"
+               "             the `map` variant of the reference)\n"
                " -n N        ranks (one host thread + one GPU each; default: all GPUs;\n"
                "             more ranks than GPUs are placed round-robin)\n"
                " --type float|int      element type (default float, or binary-name suffix)\n"
@@ -259,13 +261,14 @@ int main(int argc, char** argv) {
                                        {"help", no_argument, nullptr, 'h'},
                                        {nullptr, 0, nullptr, 0}};
     int opt;
-    while ((opt = getopt_long(argc, argv, "haHDSp:n:", long_opts, nullptr)) != -1) {
+    while ((opt = getopt_long(argc, argv, "haHDSRp:n:", long_opts, nullptr)) != -1) {
       switch (opt) {
         case 'h': print_help(); return 1;
         case 'a': cfg.use_collective = true; break;
         case 'H': cfg.kind = AllocKind::kPinned; break;
         case 'D': cfg.kind = AllocKind::kDevice; break;
         case 'S': cfg.kind = AllocKind::kManaged; break;
+        case 'R': cfg.kind = AllocKind::kMapped; break;
         case 'p': cfg.log2_elems = std::atoi(optarg); break;
         case 'n': cfg.ranks = std::atoi(optarg); break;
         case 1:
