@@ -3,7 +3,8 @@
 #   make            everything: static lib, CLIs in bin/, torch extension (_C.so)
 #   make cli        native CLIs only            make ext   torch extension only
 #   make omp_con    host-only concurrency bench (plain g++ -fopenmp, no CUDA)
-#   make sass       cuobjdump SASS listings -> docs/sass/
+#   make sass       trimmed SASS listings + mnemonic summary -> docs/sass/
+#   make sanitize   compute-sanitizer over the single-GPU kernel tests (needs a GPU)
 #   make test       CPU test-suite (pytest -m "not gpu")
 #
 # Capability parity with the reference's build files: concurency/run_sycl.sh:6,
@@ -29,7 +30,7 @@ LIB        := $(BUILD)/libhpcp.a
 CLIS := bin/concurency bin/omp_con bin/peer2pear bin/topology bin/allreduce bin/interop_torchless \
         bin/interop_driver
 
-.PHONY: all cli ext omp_con sass test clean
+.PHONY: all cli ext omp_con sass sanitize test clean
 all: cli ext
 cli: $(CLIS)
 
@@ -80,9 +81,11 @@ ext: $(LIB)
 	$(PYTHON) -m hpc_patterns_b200._build
 
 sass: $(LIB)
-	@mkdir -p docs/sass
-	for o in $(KERNEL_SRC:csrc/%.cu=$(BUILD)/%.o); do \
-	  cuobjdump -sass $$o > docs/sass/$$(basename $$o .o).sass; done
+	./scripts/make_sass.sh
+
+# compute-sanitizer memcheck / racecheck / synccheck over the single-GPU kernel tests (GPU box)
+sanitize: all
+	./scripts/sanitize.sh
 
 test:
 	$(PYTHON) -m pytest tests -x -q -m "not gpu"
