@@ -36,8 +36,24 @@ inline void cuda_check(cudaError_t e, const char* expr, const char* file, int li
   throw std::runtime_error(os.str());
 }
 
+// Opt a kernel into `bytes` of dynamic shared memory AND ask for the maximum shared-memory
+// carveout.  The carveout matters for co-residency: an SM configured for a small carveout by an
+// earlier launch cannot host a CTA of a later kernel that needs more until it drains, which
+// serialises kernels that were meant to overlap (measured: `fused | T C` 1.04x before, see
+// profiles/r1_call4_1gpu/call4_concurency.txt).
+template <typename Kernel>
+inline void enable_dynamic_smem(Kernel kernel, size_t bytes, const char* file, int line) {
+  cuda_check(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(bytes)),
+             "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", file, line);
+  cuda_check(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  static_cast<int>(cudaSharedmemCarveoutMaxShared)),
+             "cudaFuncSetAttribute(PreferredSharedMemoryCarveout)", file, line);
+}
+
 }  // namespace hpcp
 
+#define HPCP_ENABLE_SMEM(kernel, bytes) ::hpcp::enable_dynamic_smem((kernel), (bytes), __FILE__, __LINE__)
 #define HPCP_CUDA(expr) ::hpcp::cuda_check((expr), #expr, __FILE__, __LINE__)
 #define HPCP_FAIL(msg) ::hpcp::fail((msg), __FILE__, __LINE__)
 #define HPCP_REQUIRE(cond, msg) \

@@ -142,9 +142,13 @@ class CudaBackend final : public Backend {
         c.a = static_cast<float*>(alloc_bytes(c.n * sizeof(float), AllocKind::kDevice, device_, true));
       } else if (name == "T") {
         // n = CTAs (one 128x256 accumulator tile each); b = bf16 operands A|B; a = fp32 results.
+        // HPCP_T_OUT=P puts the accumulator tiles into the PEER GPU: the tcgen05.ld epilogue stores
+        // straight over NVLink, i.e. tensor-core tile compute -> P2P put in one kernel.
         c.tripcount = req.params.at("tripcount_T");
+        const char* t_out = std::getenv("HPCP_T_OUT");
+        const int out_dev = (t_out != nullptr && t_out[0] == 'P' && peer_ >= 0) ? peer_ : device_;
         c.a = static_cast<float*>(alloc_bytes(c.n * tc_busy_out_elems_per_cta() * sizeof(float),
-                                              AllocKind::kDevice, device_, true));
+                                              AllocKind::kDevice, out_dev, true));
         c.b = static_cast<float*>(alloc_bytes(tc_busy_operand_bytes(), AllocKind::kDevice, device_, true));
         launch_tc_fill_operands(c.b, nullptr);
       } else if (name == "A") {
@@ -402,7 +406,14 @@ class CudaBackend final : public Backend {
   BenchResult run_fused(const BenchRequest& req, const std::vector<DevCommand>& cmds) const {
     if (req.verbose) std::cout << "#n_queues used: 1" << std::endl;
     std::vector<FusedCommand> fused;
-    std::vector<const DevCommand*> side;  // pageable copies: copy engine on a side stream
+    std::vector<const DevCommand*> side;  // launched alongside the fused kernel, one stream each
+    // PCIe traffic driven from the SMs (zero-copy TMA / ld-st on pinned memory) reaches copy-engine
+    // speed in ONE direction (51-53 vs 55 GB/s) but not in both at once (74 vs 111 GB/s measured,
+    // profiles/r1_call4_1gpu): with two or more host copies in the group they go to the copy engines.
+    int host_copies = 0;
+    for (const auto& c : cmds)
+      if (c.is_copy() && (c.src_kind == AllocKind::kPinned || c.dst_kind == AllocKind::kPinned)) ++host_copies;
+    const bool host_copies_on_ce = host_copies >= 2 && std::getenv("HPCP_FUSED_HOST_ZERO_COPY") == nullptr;
     for (const auto& c : cmds) {
       FusedCommand f;
       if (c.name == "C") {
@@ -417,10 +428,13 @@ class CudaBackend final : public Backend {
         f.b = c.b;
         f.c = c.c;
       } else if (c.name == "T") {
-        side.push_back(&c);  // tensor-core tile loop: its own (TMEM-allocating) kernel, launched alongside
+        side.push_back(&c);  // tensor-core tile loop: its own (TMEM-allocating) kernel
         continue;
       } else if (c.src_kind == AllocKind::kPageable || c.dst_kind == AllocKind::kPageable) {
         side.push_back(&c);  // a kernel cannot dereference pageable host memory on x86 B200
+        continue;
+      } else if (host_copies_on_ce && (c.src_kind == AllocKind::kPinned || c.dst_kind == AllocKind::kPinned)) {
+        side.push_back(&c);
         continue;
       } else {
         f.kind = FusedKind::kCopy;
@@ -434,9 +448,10 @@ class CudaBackend final : public Backend {
     if (const char* e = std::getenv("HPCP_FUSED_COPY_ENGINE"))
       if (std::string(e) == "ldst") engine = CopyEngine::kLdSt;
 
-    cudaStream_t s, s2;
+    cudaStream_t s;
     HPCP_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    HPCP_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    std::vector<cudaStream_t> side_streams(side.size());
+    for (auto& q : side_streams) HPCP_CUDA(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
     cudaEvent_t g0, g1;
     HPCP_CUDA(cudaEventCreate(&g0));
     HPCP_CUDA(cudaEventCreate(&g1));
@@ -446,13 +461,14 @@ class CudaBackend final : public Backend {
     for (int r = 0; r < req.n_repetitions; ++r) {
       const auto t0 = Clock::now();
       if (req.enable_profiling) HPCP_CUDA(cudaEventRecord(g0, s));
+      // Side commands first: a resident-wave kernel launched earlier would otherwise hold the SMs.
+      for (size_t k = 0; k < side.size(); ++k) side[k]->submit(side_streams[k]);
       if (!fused.empty())
         launch_fused_bench(fused.data(), static_cast<int>(fused.size()), engine, CopyTuning{},
                            device_, s);
       if (req.enable_profiling) HPCP_CUDA(cudaEventRecord(g1, s));
-      for (const DevCommand* c : side) c->submit(s2);
       HPCP_CUDA(cudaStreamSynchronize(s));
-      HPCP_CUDA(cudaStreamSynchronize(s2));
+      for (auto& q : side_streams) HPCP_CUDA(cudaStreamSynchronize(q));
       const long t = elapsed_us(t0, Clock::now());
       note_rep(req, r, t);
       res.total_us = std::min(res.total_us, t);
@@ -466,7 +482,7 @@ class CudaBackend final : public Backend {
     (void)cudaEventDestroy(g0);
     (void)cudaEventDestroy(g1);
     (void)cudaStreamDestroy(s);
-    (void)cudaStreamDestroy(s2);
+    for (auto& q : side_streams) (void)cudaStreamDestroy(q);
     return res;
   }
 };

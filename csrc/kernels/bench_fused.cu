@@ -165,6 +165,12 @@ __global__ void busy_wait_kernel(float* __restrict__ out, size_t n, size_t tripc
 void launch_busy_wait(float* out, size_t n_items, size_t tripcount, cudaStream_t stream) {
   const int threads = static_cast<int>(std::min<size_t>(std::max<size_t>(n_items, 1), 128));
   const unsigned ctas = static_cast<unsigned>((std::max<size_t>(n_items, 1) + threads - 1) / threads);
+  // Keep the SM's shared-memory carveout at its maximum even though this kernel uses none: a
+  // smem-hungry kernel launched while `C` is running (TMA copies, the tcgen05 tile loop) must be
+  // able to co-reside on the same SM, which is the whole point of the benchmark.
+  static const cudaError_t carveout_once = cudaFuncSetAttribute(
+      busy_wait_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  (void)carveout_once;
   busy_wait_kernel<<<ctas, threads, 0, stream>>>(out, n_items, tripcount);
   HPCP_CUDA(cudaGetLastError());
 }
@@ -230,9 +236,7 @@ int launch_fused_bench(const FusedCommand* cmds, int n_cmds, CopyEngine engine,
                           ? static_cast<size_t>(stages) * stage_bytes + static_cast<size_t>(stages) * 8
                           : 0;
   HPCP_REQUIRE(smem <= 227 * 1024, "fused bench: TMA stages exceed 227 KiB of shared memory");
-  if (smem > 48 * 1024)
-    HPCP_CUDA(cudaFuncSetAttribute(fused_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(smem)));
+  HPCP_ENABLE_SMEM(fused_bench_kernel, smem);
   fused_bench_kernel<<<next, threads, smem, stream>>>(table, engine == CopyEngine::kTma ? 1 : 0,
                                                       stage_bytes, stages);
   HPCP_CUDA(cudaGetLastError());

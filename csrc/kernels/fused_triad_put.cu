@@ -293,16 +293,12 @@ int launch_triad_put(const TriadPutArgs& args, CopyEngine engine, const CopyTuni
     const int cap = tune.ctas > 0 ? tune.ctas : sms * per_sm;
     ctas = static_cast<int>(std::min<size_t>(tiles, static_cast<size_t>(cap)));
     if (put) {
-      HPCP_CUDA(cudaFuncSetAttribute(triad_put_tma_kernel<true>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(smem)));
+      HPCP_ENABLE_SMEM(triad_put_tma_kernel<true>, smem);
       triad_put_tma_kernel<true><<<ctas, kTmaThreads, smem, stream>>>(
           args.a_local, args.a_peer, args.b, args.c, args.s, n_bytes, tile_bytes, stages, sync,
           arrive_flag, arrive_epoch);
     } else {
-      HPCP_CUDA(cudaFuncSetAttribute(triad_put_tma_kernel<false>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(smem)));
+      HPCP_ENABLE_SMEM(triad_put_tma_kernel<false>, smem);
       triad_put_tma_kernel<false><<<ctas, kTmaThreads, smem, stream>>>(
           args.a_local, args.a_peer, args.b, args.c, args.s, n_bytes, tile_bytes, stages, sync,
           arrive_flag, arrive_epoch);

@@ -320,8 +320,7 @@ int launch_copy(void* dst, const void* src, size_t bytes, bool src_is_peer, Copy
     const int per_sm = std::max(1, static_cast<int>((227 * 1024) / smem));
     const int cap = tune.ctas > 0 ? tune.ctas : sms * std::min(per_sm, 2);
     ctas = static_cast<int>(std::min<size_t>(tiles, static_cast<size_t>(cap)));
-    HPCP_CUDA(cudaFuncSetAttribute(copy_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(smem)));
+    HPCP_ENABLE_SMEM(copy_tma_kernel, smem);
     copy_tma_kernel<<<ctas, 32, smem, stream>>>(static_cast<unsigned char*>(dst),
                                                 static_cast<const unsigned char*>(src), bytes16,
                                                 tail, stage_bytes, stages, sync);

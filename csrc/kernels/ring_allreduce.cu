@@ -246,12 +246,13 @@ __global__ void __launch_bounds__(512) nvls_kernel(const __grid_constant__ NvlsD
     return r;
   };
   size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  for (; i + 3 * stride < a.slice_vec; i += 4 * stride) {  // 4 in-switch reductions in flight
-    float4 r[4];
+  constexpr int kU = 8;  // in-switch reductions in flight per thread (latency ~ several us under load)
+  for (; i + (kU - 1) * stride < a.slice_vec; i += kU * stride) {
+    float4 r[kU];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) r[k] = reduce_at((base + i + k * stride) * 16);
+    for (int k = 0; k < kU; ++k) r[k] = reduce_at((base + i + k * stride) * 16);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) ptx::multimem_st_f32x4(a.vc_mc + (base + i + k * stride) * 16, r[k]);
+    for (int k = 0; k < kU; ++k) ptx::multimem_st_f32x4(a.vc_mc + (base + i + k * stride) * 16, r[k]);
   }
   for (; i < a.slice_vec; i += stride)
     ptx::multimem_st_f32x4(a.vc_mc + (base + i) * 16, reduce_at((base + i) * 16));
@@ -421,7 +422,7 @@ int launch_allreduce_nvls(const NvlsArgs& args, ElemType type, int ctas, int dev
   d.timeout_ns = args.timeout_ns;
   d.status = args.status;
   const int sms = device_sm_count(device);
-  const int grid = grid_for(std::max<size_t>(d.slice_vec, 1), 512, ctas > 0 ? ctas : sms);
+  const int grid = grid_for(std::max<size_t>(d.slice_vec, 1) / 4 + 1, 512, ctas > 0 ? ctas : sms * 2);
   d.ticket_target = args.ticket_base + static_cast<uint32_t>(grid);
   if (type == ElemType::kFloat)
     nvls_kernel<float><<<grid, 512, 0, stream>>>(d);

@@ -242,8 +242,7 @@ void launch_tc_busy(const void* operands, float* out, int ctas, uint32_t tripcou
   const CUtensorMap map_a = make_operand_map(a, kTileM);
   const CUtensorMap map_b = make_operand_map(a + kTileM * kTileK, kTileN);
   const size_t smem = kABytes + kBBytes + 1024;  // slack for the 1024-byte alignment
-  HPCP_CUDA(cudaFuncSetAttribute(tc_busy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(smem)));
+  HPCP_ENABLE_SMEM(tc_busy_kernel, smem);
   tc_busy_kernel<<<ctas, kThreads, smem, stream>>>(map_a, map_b, out, tripcount);
   HPCP_CUDA(cudaGetLastError());
 }

@@ -31,6 +31,7 @@
 
 #include "../common/cuda_check.h"
 #include "../common/dtype_traits.h"
+#include "../common/nvtx.h"
 #include "../common/peer_mem.h"
 #include "../common/rank_runtime.h"
 #include "../kernels/api.h"
@@ -117,6 +118,7 @@ void rank_main(RankCtx& ctx, Shared& sh) {
   double best_ms = std::numeric_limits<double>::max();
 
   for (int it = 0; it < cfg.warmup + cfg.iters; ++it) {
+    NvtxRange iter_range(it < cfg.warmup ? "allreduce warm-up" : "allreduce timed");
     // (Re-)initialise outside the timed region: VA = VB = rank, VC = 0.
     launch_init3(va, cfg.algo == "ring-unfused" && !cfg.use_collective ? sh.vb.ptr[me] : nullptr, vc,
                  sh.n, me, me, 0, cfg.type, stream);

@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "../common/cuda_check.h"
+#include "../common/nvtx.h"
 #include "../common/peer_mem.h"
 #include "../common/rank_runtime.h"
 #include "../kernels/api.h"
@@ -183,7 +184,10 @@ double timed_phase(RankCtx& ctx, Shared& sh, size_t bytes, int sends_to, int rec
   HPCP_CUDA(cudaEventCreate(&e1));
   double best_ns = std::numeric_limits<double>::max();
 
+  NvtxRange phase_range(cfg.transport + (sends_to >= 0 && recvs_from >= 0 ? " bi " : " uni ") +
+                        std::to_string(bytes) + " B");
   for (int it = 0; it < cfg.iters; ++it) {
+    NvtxRange iter_range("iteration");
     ++epoch;
     ctx.barrier();  // host: everybody has enqueued nothing yet for this iteration
     launch_barrier_all(pad_list.data(), me, ctx.world, ++barrier_epoch, cfg.timeout_ns, status, stream);

@@ -215,9 +215,11 @@ class AllreduceMiniapp:
             torch.cuda.synchronize(self.device)
             self.comm.barrier()
             self.pads.device_barrier(stream.cuda_stream)
+            torch.cuda.nvtx.range_push(f"allreduce {self.algo} {'warm-up' if it < warmup else 'timed'}")
             e0.record(stream)
             self.run_once()
             e1.record(stream)
+            torch.cuda.nvtx.range_pop()
             stream.synchronize()
             self.pads.check()
             t = self.comm.max(e0.elapsed_time(e1))

@@ -331,9 +331,11 @@ class P2PBench:
             self.epoch += 1
             self.comm.barrier()
             self.pads.device_barrier(stream.cuda_stream)
+            torch.cuda.nvtx.range_push(f"peer2pear {self.transport} {nbytes} B")
             e0.record(stream)
             self._enqueue(nbytes, sends_to, recvs_from)
             e1.record(stream)
+            torch.cuda.nvtx.range_pop()
             stream.synchronize()
             self.pads.check()
             best = min(best, self.comm.max(e0.elapsed_time(e1) * 1e6))
