@@ -181,15 +181,17 @@ template <typename T, int W, int U>
 __global__ void __launch_bounds__(512) two_shot_kernel(const __grid_constant__ TwoShotDev a) {
   const size_t base = static_cast<size_t>(a.rank) * a.slice_vec;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  for (; i + (U - 1) * stride < a.slice_vec; i += U * stride) {
+  const size_t block_vec = static_cast<size_t>(blockDim.x) * U;
+  const size_t n_blocks = a.slice_vec / block_vec;
+  for (size_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    const size_t i = blk * block_vec + threadIdx.x;  // CTA-contiguous block of U * blockDim vectors
     uint4 x[W][U];
 #pragma unroll
     for (int q = 0; q < W; ++q)
       if (q < a.world) {
         const int p = (a.rank + q) % a.world;  // start at self, then the neighbours: spreads load
 #pragma unroll
-        for (int u = 0; u < U; ++u) x[q][u] = ptx::ld_peer_v4(a.va[p] + base + i + u * stride);
+        for (int u = 0; u < U; ++u) x[q][u] = ptx::ld_peer_v4(a.va[p] + base + i + u * blockDim.x);
       }
 #pragma unroll
     for (int q = 1; q < W; ++q)
@@ -202,9 +204,10 @@ __global__ void __launch_bounds__(512) two_shot_kernel(const __grid_constant__ T
       if (q < a.world) {
         const int p = (a.rank + q) % a.world;
 #pragma unroll
-        for (int u = 0; u < U; ++u) ptx::st_stream_v4(a.vc[p] + base + i + u * stride, x[0][u]);
+        for (int u = 0; u < U; ++u) ptx::st_stream_v4(a.vc[p] + base + i + u * blockDim.x, x[0][u]);
       }
   }
+  size_t i = n_blocks * block_vec + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   for (; i < a.slice_vec; i += stride) {
     uint4 acc = ptx::ld_peer_v4(a.va[0] + base + i);
     for (int p = 1; p < a.world; ++p) acc = Vec4<T>::add(acc, ptx::ld_peer_v4(a.va[p] + base + i));
@@ -245,16 +248,21 @@ __global__ void __launch_bounds__(512) nvls_kernel(const __grid_constant__ NvlsD
     }
     return r;
   };
-  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // CTA-contiguous blocks: all kU requests of a CTA fall into one 64 KiB window (DRAM-page and
+  // TLB friendly on the eight GPUs that serve the in-switch read), CTAs stride over the blocks.
   constexpr int kU = 8;  // in-switch reductions in flight per thread (latency ~ several us under load)
-  for (; i + (kU - 1) * stride < a.slice_vec; i += kU * stride) {
+  const size_t block_vec = static_cast<size_t>(blockDim.x) * kU;
+  const size_t n_blocks = a.slice_vec / block_vec;
+  for (size_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    const size_t i0 = base + blk * block_vec + threadIdx.x;
     float4 r[kU];
 #pragma unroll
-    for (int k = 0; k < kU; ++k) r[k] = reduce_at((base + i + k * stride) * 16);
+    for (int k = 0; k < kU; ++k) r[k] = reduce_at((i0 + k * blockDim.x) * 16);
 #pragma unroll
-    for (int k = 0; k < kU; ++k) ptx::multimem_st_f32x4(a.vc_mc + (base + i + k * stride) * 16, r[k]);
+    for (int k = 0; k < kU; ++k) ptx::multimem_st_f32x4(a.vc_mc + (i0 + k * blockDim.x) * 16, r[k]);
   }
-  for (; i < a.slice_vec; i += stride)
+  for (size_t i = n_blocks * block_vec + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+       i < a.slice_vec; i += stride)
     ptx::multimem_st_f32x4(a.vc_mc + (base + i) * 16, reduce_at((base + i) * 16));
   grid_then_node_barrier(a.ticket, a.ticket_target, a.pads, a.rank, a.world, a.barrier_epoch,
                          a.timeout_ns, a.status);

@@ -1,0 +1,60 @@
+"""``python -m hpc_patterns_b200 <program> [args...]`` — one front door to every pattern program.
+
+  concurency   compute-while-copy overlap benchmark (native driver in-process)
+  peer2pear    P2P bandwidth, process-per-GPU (run under torchrun for >1 GPU)
+  allreduce    allreduce miniapp, process-per-GPU (run under torchrun)
+  topology     fabric planes / rank->GPU mapping (JSON)
+  tile-mapping per-rank launcher: <policy> <CVD|SET> cmd...
+  parse        concurrency log -> SUCCESS/FAILURE tables
+  report       JSONL rows -> roofline tables
+  interop      torch <-> native runtime interop demos
+  build        compile the native library, CLIs and the extension in-tree
+"""
+from __future__ import annotations
+
+import sys
+
+
+def main(argv=None) -> int:
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if not argv or argv[0] in ("-h", "--help"):
+        print(__doc__)
+        return 0 if argv else 2
+    prog, rest = argv[0], argv[1:]
+    if prog == "concurency":
+        from .models.concurency import main as m
+        return m(rest)
+    if prog == "peer2pear":
+        from .models.peer2pear import main as m
+        return m(rest)
+    if prog == "allreduce":
+        from .models.allreduce import main as m
+        return m(rest)
+    if prog == "topology":
+        from . import native
+        print(native().topology_discover(rest[0] if rest else ""))
+        return 0
+    if prog in ("tile-mapping", "tile_mapping"):
+        from .parallel.tile_mapping import main as m
+        return m(rest)
+    if prog == "parse":
+        from .utils.parse import main as m
+        return m(rest)
+    if prog == "report":
+        from .utils.report import main as m
+        return m(rest)
+    if prog == "interop":
+        from .models import interop
+        interop.demo_direct()
+        interop.demo_native_handles()
+        return 0
+    if prog == "build":
+        from . import _build
+        _build.build(cli="--no-cli" not in rest)
+        return 0
+    print(f"unknown program {prog!r}\n{__doc__}", file=sys.stderr)
+    return 2
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())
