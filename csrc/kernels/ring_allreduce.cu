@@ -248,21 +248,18 @@ __global__ void __launch_bounds__(512) nvls_kernel(const __grid_constant__ NvlsD
     }
     return r;
   };
-  // CTA-contiguous blocks: all kU requests of a CTA fall into one 64 KiB window (DRAM-page and
-  // TLB friendly on the eight GPUs that serve the in-switch read), CTAs stride over the blocks.
-  constexpr int kU = 8;  // in-switch reductions in flight per thread (latency ~ several us under load)
-  const size_t block_vec = static_cast<size_t>(blockDim.x) * kU;
-  const size_t n_blocks = a.slice_vec / block_vec;
-  for (size_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-    const size_t i0 = base + blk * block_vec + threadIdx.x;
-    float4 r[kU];
+  // Grid-stride with 4 independent in-switch reductions in flight per thread.  (A CTA-contiguous
+  // 64 KiB-block variant with 8 in flight and 2 CTAs/SM was measured slower on 8xB200:
+  // 0.345-0.371 ms vs 0.326 ms at 2^25 floats, no gain at 2^28 - see BASELINE.md 4.4.)
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < a.slice_vec; i += 4 * stride) {
+    float4 r[4];
 #pragma unroll
-    for (int k = 0; k < kU; ++k) r[k] = reduce_at((i0 + k * blockDim.x) * 16);
+    for (int k = 0; k < 4; ++k) r[k] = reduce_at((base + i + k * stride) * 16);
 #pragma unroll
-    for (int k = 0; k < kU; ++k) ptx::multimem_st_f32x4(a.vc_mc + (i0 + k * blockDim.x) * 16, r[k]);
+    for (int k = 0; k < 4; ++k) ptx::multimem_st_f32x4(a.vc_mc + (base + i + k * stride) * 16, r[k]);
   }
-  for (size_t i = n_blocks * block_vec + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-       i < a.slice_vec; i += stride)
+  for (; i < a.slice_vec; i += stride)
     ptx::multimem_st_f32x4(a.vc_mc + (base + i) * 16, reduce_at((base + i) * 16));
   grid_then_node_barrier(a.ticket, a.ticket_target, a.pads, a.rank, a.world, a.barrier_epoch,
                          a.timeout_ns, a.status);
@@ -430,7 +427,7 @@ int launch_allreduce_nvls(const NvlsArgs& args, ElemType type, int ctas, int dev
   d.timeout_ns = args.timeout_ns;
   d.status = args.status;
   const int sms = device_sm_count(device);
-  const int grid = grid_for(std::max<size_t>(d.slice_vec, 1) / 4 + 1, 512, ctas > 0 ? ctas : sms * 2);
+  const int grid = grid_for(std::max<size_t>(d.slice_vec, 1), 512, ctas > 0 ? ctas : sms);
   d.ticket_target = args.ticket_base + static_cast<uint32_t>(grid);
   if (type == ElemType::kFloat)
     nvls_kernel<float><<<grid, 512, 0, stream>>>(d);
