@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--unroll", type=int, default=int(os.environ.get("HPCP_BENCH_UNROLL", "0")))
     ap.add_argument("--vec", type=int, default=int(os.environ.get("HPCP_BENCH_VEC", "0")))
     ap.add_argument("--blocked", type=int, default=int(os.environ.get("HPCP_BENCH_BLOCKED", "0")))
+    ap.add_argument("--stages", type=int, default=int(os.environ.get("HPCP_BENCH_STAGES", "0")))
+    ap.add_argument("--stage-kb", type=int, default=int(os.environ.get("HPCP_BENCH_STAGE_KB", "0")))
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-extras", action="store_true", help="skip the unfused / stock comparison runs")
     return ap.parse_args()
@@ -79,6 +81,10 @@ def main() -> int:
         tune["vec_bytes"] = args.vec
     if args.blocked:
         tune["blocked"] = args.blocked
+    if args.stages:
+        tune["stages"] = args.stages
+    if args.stage_kb:
+        tune["stage_kb"] = args.stage_kb
     ex = FusedTriadExchange(comm, device, args.bytes, s=3.0, engine=args.engine, tune=tune)
     stream = torch.cuda.current_stream(device)
 
