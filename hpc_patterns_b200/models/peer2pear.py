@@ -25,7 +25,7 @@ import torch
 
 from .. import native
 from ..parallel.comm import Comm
-from ..parallel.symmetric import SignalPads, SymmetricBuffer, tensor_from_ptr
+from ..parallel.symmetric import SignalPads, SymmetricBuffer
 
 REFERENCE_MESSAGE_BYTES = 1179648 * 40 * 4  # 188 743 680, p2p/peer2pear.cpp:115-116
 

@@ -7,12 +7,12 @@
 """
 from __future__ import annotations
 
-from typing import Optional, Sequence
+from typing import Optional
 
 import torch
 
 from .. import native
-from ._util import PtrLike, current_stream, ptr
+from ._util import current_stream, ptr
 
 _DTYPE_NAME = {torch.float32: "float", torch.int32: "int"}
 

@@ -1,7 +1,7 @@
 """Device timing helpers: CUDA events on the launching stream, max over ranks."""
 from __future__ import annotations
 
-from typing import Callable, List
+from typing import Callable
 
 import torch
 

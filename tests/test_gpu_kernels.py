@@ -1,5 +1,4 @@
 """Single-GPU numerics tests: every sm_100a kernel against a plain PyTorch reference."""
-import math
 
 import pytest
 import torch
