@@ -323,9 +323,11 @@ PYBIND11_MODULE(_C, m) {
   m.def("tc_fill_operands", [](uintptr_t operands, uintptr_t stream) {
     launch_tc_fill_operands(as_ptr<void>(operands), as_stream(stream));
   });
-  m.def("tc_busy", [](uintptr_t operands, uintptr_t out, int ctas, uint32_t tripcount, uintptr_t stream) {
-    launch_tc_busy(as_ptr<const void>(operands), as_ptr<float>(out), ctas, tripcount, as_stream(stream));
+  m.def("tc_busy", [](uintptr_t operands, uintptr_t out, int ctas, uint32_t tripcount, uintptr_t stream,
+                      int cluster) {
+    launch_tc_busy(as_ptr<const void>(operands), as_ptr<float>(out), ctas, tripcount, as_stream(stream), cluster);
   }, py::arg("operands"), py::arg("out"), py::arg("ctas"), py::arg("tripcount"), py::arg("stream") = 0,
+  py::arg("cluster") = 1,
   "tcgen05 tile loop: out[cta] = tripcount * (A[128x64] . B[256x64]^T), operands via TMA, accumulator in TMEM.");
 
   // ------------------------------------------------------------ allreduce ----

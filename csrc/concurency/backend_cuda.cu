@@ -60,7 +60,12 @@ struct DevCommand {
     if (name == "C") {
       launch_busy_wait(a, n, tripcount, s);
     } else if (name == "T") {
-      launch_tc_busy(b, a, static_cast<int>(n), static_cast<uint32_t>(tripcount), s);
+      // HPCP_T_CLUSTER=2: thread-block clusters of two CTAs sharing the B tile via TMA multicast.
+      static const int cluster = [] {
+        const char* e = std::getenv("HPCP_T_CLUSTER");
+        return (e != nullptr && std::atoi(e) == 2) ? 2 : 1;
+      }();
+      launch_tc_busy(b, a, static_cast<int>(n), static_cast<uint32_t>(tripcount), s, cluster);
     } else if (name == "A") {
       TriadPutArgs t;
       t.a_local = a;

@@ -128,8 +128,9 @@ void launch_busy_wait(float* out, size_t n_items, size_t tripcount, cudaStream_t
 size_t tc_busy_operand_bytes();
 size_t tc_busy_out_elems_per_cta();
 void launch_tc_fill_operands(void* operands, cudaStream_t stream);
+// cluster = 2 launches thread-block clusters of two CTAs that share the B tile through TMA multicast.
 void launch_tc_busy(const void* operands, float* out, int ctas, uint32_t tripcount,
-                    cudaStream_t stream);
+                    cudaStream_t stream, int cluster = 1);
 
 // ------------------------------------------------------ allreduce miniapp ----
 enum class ElemType : int { kFloat = 0, kInt = 1 };

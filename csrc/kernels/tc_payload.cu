@@ -71,6 +71,27 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// Same load, multicast to every CTA of the cluster named in `cta_mask`: the tile lands at the same
+// shared-memory offset in each destination CTA and each destination's mbarrier (same offset) gets
+// the complete_tx — one L2 read feeds both SMs of the pair.
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* map, int x, int y,
+                                                      uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(ptx::smem_u32(smem_dst)),
+      "l"(map), "r"(x), "r"(y), "r"(ptx::smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -103,6 +124,9 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
 }
 
 // Dynamic smem (1024-aligned): A tile | B tile ; static smem: barriers + TMEM base.
+// kCluster == 2: launched as thread-block clusters of two CTAs that share the B tile — each CTA
+// fetches half of B (128 of its 256 rows) and TMA-multicasts it into both CTAs' shared memory.
+template <int kCluster>
 __global__ void __launch_bounds__(kThreads)
     tc_busy_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    float* __restrict__ out, uint32_t tripcount) {
@@ -135,12 +159,20 @@ __global__ void __launch_bounds__(kThreads)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_s;
+  // The peer CTA's mbarrier must be initialised before anything is multicast into it.
+  if (kCluster > 1) cluster_sync_all();
 
   if (warp == 0) {
     if (lane == 0) {  // TMA producer: both operand tiles, once
       ptx::mbar_arrive_expect_tx(&full_bar, kABytes + kBBytes);
       tma_load_2d(smem_a, &map_a, 0, 0, &full_bar);
-      tma_load_2d(smem_b, &map_b, 0, 0, &full_bar);
+      if (kCluster > 1) {
+        const uint32_t r = cluster_cta_rank();  // my half of B, delivered to both CTAs
+        tma_load_2d_multicast(smem_b + r * (kBBytes / 2), &map_b, 0, static_cast<int>(r) * (kTileN / 2),
+                              &full_bar, static_cast<uint16_t>(0x3));
+      } else {
+        tma_load_2d(smem_b, &map_b, 0, 0, &full_bar);
+      }
     }
   } else if (warp == 1) {
     ptx::mbar_wait(&full_bar, 0);  // operands landed in smem
@@ -183,6 +215,8 @@ __global__ void __launch_bounds__(kThreads)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d),
                  "r"(static_cast<uint32_t>(kTmemCols))
                  : "memory");
+  // Neither CTA of a pair may retire while the other could still be receiving its multicast.
+  if (kCluster > 1) cluster_sync_all();
 }
 
 __global__ void tc_fill_operands_kernel(__nv_bfloat16* a, __nv_bfloat16* b) {
@@ -209,11 +243,11 @@ PFN_cuTensorMapEncodeTiled tensor_map_encoder() {
   return fn;
 }
 
-CUtensorMap make_operand_map(const void* base, int rows) {
+CUtensorMap make_operand_map(const void* base, int rows, int box_rows) {
   CUtensorMap map;
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kTileK), static_cast<cuuint64_t>(rows)};
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kTileK) * 2};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kTileK), static_cast<cuuint32_t>(rows)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kTileK), static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t elem_strides[2] = {1, 1};
   const CUresult r = tensor_map_encoder()(
       &map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
@@ -235,16 +269,37 @@ void launch_tc_fill_operands(void* operands, cudaStream_t stream) {
 }
 
 void launch_tc_busy(const void* operands, float* out, int ctas, uint32_t tripcount,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, int cluster) {
   HPCP_REQUIRE(ctas >= 1, "tc_busy: need at least one CTA");
   HPCP_REQUIRE((reinterpret_cast<uintptr_t>(operands) & 127) == 0, "tc_busy: operands must be 128-byte aligned");
+  HPCP_REQUIRE(cluster == 1 || cluster == 2, "tc_busy: cluster size must be 1 or 2");
+  if (cluster == 2 && ctas % 2 != 0) cluster = 1;  // pairs only
   const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(operands);
-  const CUtensorMap map_a = make_operand_map(a, kTileM);
-  const CUtensorMap map_b = make_operand_map(a + kTileM * kTileK, kTileN);
+  const CUtensorMap map_a = make_operand_map(a, kTileM, kTileM);
   const size_t smem = kABytes + kBBytes + 1024;  // slack for the 1024-byte alignment
-  HPCP_ENABLE_SMEM(tc_busy_kernel, smem);
-  tc_busy_kernel<<<ctas, kThreads, smem, stream>>>(map_a, map_b, out, tripcount);
-  HPCP_CUDA(cudaGetLastError());
+  if (cluster == 1) {
+    const CUtensorMap map_b = make_operand_map(a + kTileM * kTileK, kTileN, kTileN);
+    HPCP_ENABLE_SMEM(tc_busy_kernel<1>, smem);
+    tc_busy_kernel<1><<<ctas, kThreads, smem, stream>>>(map_a, map_b, out, tripcount);
+    HPCP_CUDA(cudaGetLastError());
+    return;
+  }
+  // Thread-block clusters of 2: each CTA loads and multicasts one half (128 rows) of B.
+  const CUtensorMap map_b = make_operand_map(a + kTileM * kTileK, kTileN, kTileN / 2);
+  HPCP_ENABLE_SMEM(tc_busy_kernel<2>, smem);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(ctas));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  HPCP_CUDA(cudaLaunchKernelEx(&cfg, tc_busy_kernel<2>, map_a, map_b, out, tripcount));
 }
 
 }  // namespace hpcp

@@ -35,12 +35,15 @@ def tc_operands(device: int = 0, stream: Optional[int] = None) -> torch.Tensor:
     return ops
 
 
-def tc_busy(operands: torch.Tensor, ctas: int, tripcount: int, stream: Optional[int] = None) -> torch.Tensor:
-    """Returns out[ctas,128,256] = tripcount * (A @ B^T) computed on the tensor cores."""
+def tc_busy(operands: torch.Tensor, ctas: int, tripcount: int, stream: Optional[int] = None,
+            cluster: int = 1) -> torch.Tensor:
+    """Returns out[ctas,128,256] = tripcount * (A @ B^T) computed on the tensor cores.
+    ``cluster=2`` launches CTA pairs that share the B tile through TMA multicast."""
     C = native()
     dev = operands.device.index
     out = torch.empty(ctas * C.tc_busy_out_elems_per_cta(), dtype=torch.float32, device=operands.device)
-    C.tc_busy(operands.data_ptr(), out.data_ptr(), ctas, tripcount, current_stream(dev) if stream is None else stream)
+    C.tc_busy(operands.data_ptr(), out.data_ptr(), ctas, tripcount,
+              current_stream(dev) if stream is None else stream, cluster)
     return out.view(ctas, 128, 256)
 
 

@@ -274,14 +274,15 @@ def test_smoke_entry():
     g.smoke()
 
 
-@pytest.mark.parametrize("tripcount,ctas", [(1, 1), (3, 5), (100, 148)])
-def test_tcgen05_tile_loop_matches_reference(native, dev, tripcount, ctas):
+@pytest.mark.parametrize("cluster", [1, 2])
+@pytest.mark.parametrize("tripcount,ctas", [(1, 2), (3, 6), (100, 148)])
+def test_tcgen05_tile_loop_matches_reference(native, dev, tripcount, ctas, cluster):
     """T command: out[cta] = tripcount * (A . B^T) with bf16 operands, fp32 TMEM accumulation."""
     ops = torch.zeros(native.tc_busy_operand_bytes() // 2, dtype=torch.bfloat16, device=dev)
     per = native.tc_busy_out_elems_per_cta()
     out = torch.full((ctas * per,), float("nan"), device=dev)
     native.tc_fill_operands(ops.data_ptr(), _stream())
-    native.tc_busy(ops.data_ptr(), out.data_ptr(), ctas, tripcount, _stream())
+    native.tc_busy(ops.data_ptr(), out.data_ptr(), ctas, tripcount, _stream(), cluster)
     torch.cuda.synchronize()
     a = ops[:128 * 64].view(128, 64).float()
     b = ops[128 * 64:].view(256, 64).float()
