@@ -330,6 +330,17 @@ PYBIND11_MODULE(_C, m) {
   py::arg("cluster") = 1,
   "tcgen05 tile loop: out[cta] = tripcount * (A[128x64] . B[256x64]^T), operands via TMA, accumulator in TMEM.");
 
+  m.def(
+      "gemm_put",
+      [](uintptr_t a, uintptr_t b, uintptr_t c_local, uintptr_t c_peer, int m_, int n, int k,
+         const py::dict& sync, int ctas, int device, uintptr_t stream) {
+        return launch_gemm_put(as_ptr<const void>(a), as_ptr<const void>(b), as_ptr<float>(c_local),
+                               as_ptr<float>(c_peer), m_, n, k, sync_from(sync), ctas, device, as_stream(stream));
+      },
+      py::arg("a"), py::arg("b"), py::arg("c_local"), py::arg("c_peer"), py::arg("m"), py::arg("n"), py::arg("k"),
+      py::arg("sync") = py::dict(), py::arg("ctas") = 0, py::arg("device") = 0, py::arg("stream") = 0,
+      "tcgen05 GEMM C = A . B^T (bf16 in, fp32 out) whose epilogue stores to c_local and/or the peer-mapped c_peer.");
+
   // ------------------------------------------------------------ allreduce ----
   m.def("init3", [](uintptr_t va, uintptr_t vb, uintptr_t vc, size_t n, double a, double b, double c,
                     const std::string& dtype, uintptr_t stream) {

@@ -1,0 +1,327 @@
+// K-gemm-put: bf16 GEMM on the 5th-gen tensor cores whose epilogue PUTs the result tile into a
+// peer GPU over NVLink — "compute step followed by a transfer" as ONE kernel.
+//
+//     C[M,N] (fp32) = A[M,K] (bf16, K-major) . B[N,K]^T (bf16, K-major)
+//     C is written to c_local and/or to c_peer (a peer-mapped pointer), then the arrival epoch is
+//     published on the peer (same release/acquire protocol as every other kernel of the suite).
+//
+// Nothing in the reference is GEMM-shaped; this kernel is the tensor-core member of
+// the suite's "fuse the transfer into the producing kernel" family, next to K-fused-triad-put
+// (stream triad -> put) and K-ring (accumulate -> forward).  Stock comparison: cuBLAS GEMM followed
+// by cudaMemcpyPeerAsync (two operations, the C tile goes to HBM and is read back before it moves).
+//
+// Structure (persistent, one CTA per SM, 256 threads, canonical Blackwell warp specialisation):
+//   warp 0      TMA producer  : cp.async.bulk.tensor.2d (SWIZZLE_128B) A[128x64] + B[256x64] per stage,
+//                               4-stage smem ring, full/empty mbarriers
+//   warp 1      MMA issuer    : one elected thread, tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16),
+//                               tcgen05.commit frees the smem stage / publishes the accumulator
+//   warp 2      TMEM allocator: 512 columns = two 128x256 fp32 accumulators (epilogue of tile i overlaps
+//                               the main loop of tile i+1)
+//   warps 4..7  epilogue      : tcgen05.ld 32x32b.x32 -> padded smem transpose -> 128-byte row segments
+//                               -> st.global to c_local and/or the peer (coalesced NVLink stores)
+#include "api.h"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "../common/cuda_check.h"
+#include "../common/signal.cuh"
+
+namespace hpcp {
+
+namespace {
+
+constexpr int kBM = 128, kBN = 256, kBK = 64, kUmmaK = 16;
+constexpr int kStages = 4;
+constexpr int kThreads = 256;
+constexpr int kEpiWarps = 4;
+constexpr int kTmemCols = 512;                          // 2 accumulators x 256 columns
+constexpr uint32_t kABytes = kBM * kBK * 2;             // 16 KiB
+constexpr uint32_t kBBytes = kBN * kBK * 2;             // 32 KiB
+constexpr uint32_t kStageBytes = kABytes + kBBytes;     // 48 KiB
+constexpr int kStageRowWords = 36;                      // 32 payload floats + 4 pad (keeps float4 alignment)
+constexpr uint32_t kEpiWarpBytes = 32 * kStageRowWords * 4;  // 4608 B per epilogue warp
+constexpr size_t kSmemBytes = static_cast<size_t>(kStages) * kStageBytes + kEpiWarps * kEpiWarpBytes + 1024;
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);  // start address
+  d |= static_cast<uint64_t>(1) << 16;                      // LBO (unused for swizzled K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;              // SBO: 8 rows x 128 B
+  d |= static_cast<uint64_t>(1) << 46;                      // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                      // SWIZZLE_128B
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);  // D=f32, A=B=bf16, K-major both
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3}], [%4];" ::"r"(ptx::smem_u32(smem_dst)),
+      "l"(map), "r"(x), "r"(y), "r"(ptx::smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   ptx::smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+struct GemmDev {
+  float* c_local;   // may be null
+  float* c_peer;    // may be null
+  int m, n, k;
+  int tiles_m, tiles_n;
+  SyncOps sync;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm_put_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ GemmDev g) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kStages];
+  __shared__ __align__(8) uint64_t empty_bar[kStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* epi_smem = smem + static_cast<size_t>(kStages) * kStageBytes;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = g.tiles_m * g.tiles_n;
+  const int num_kb = g.k / kBK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], kEpiWarps);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     ptx::smem_u32(&tmem_base_s)),
+                 "r"(static_cast<uint32_t>(kTmemCols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    // The whole warp walks the loop (convergent barriers at kernel end); lane 0 issues the TMA.
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / g.tiles_n) * kBM;
+      const int n0 = (tile % g.tiles_n) * kBN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);  // slot released by the MMA warp
+        if (lane == 0) {
+          unsigned char* sa = smem + static_cast<size_t>(stage) * kStageBytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+          tma_load_2d(sa, &map_a, kb * kBK, m0, &full_bar[stage]);
+          tma_load_2d(sa + kABytes, &map_b, kb * kBK, n0, &full_bar[stage]);
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc(kBM, kBN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int local_tile = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+      const int acc = local_tile & 1;
+      const uint32_t acc_phase = static_cast<uint32_t>(local_tile >> 1) & 1;
+      ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kBN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);  // TMA bytes landed
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = ptx::smem_u32(smem + static_cast<size_t>(stage) * kStageBytes);
+          const uint64_t desc_a = make_smem_desc(sa);
+          const uint64_t desc_b = make_smem_desc(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint64_t adv = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+            umma_bf16(tmem_d, desc_a + adv, desc_b + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                              // frees the smem slot
+          if (kb == num_kb - 1) umma_commit(&tmem_full_bar[acc]);      // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;            // 0..3 == warp % 4 -> TMEM lane group
+    float* stage_buf = reinterpret_cast<float*>(epi_smem + static_cast<size_t>(ew) * kEpiWarpBytes);
+    int local_tile = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+      const int acc = local_tile & 1;
+      const uint32_t acc_phase = static_cast<uint32_t>(local_tile >> 1) & 1;
+      const int m0 = (tile / g.tiles_n) * kBM;
+      const int n0 = (tile % g.tiles_n) * kBN;
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kBN) + (static_cast<uint32_t>(ew * 32) << 16);
+      for (int col = 0; col < kBN; col += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + col, r);
+        // thread == accumulator row: park the 32-column row segment in padded smem ...
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stage_buf + lane * kStageRowWords + j) =
+              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                          __uint_as_float(r[j + 3]));
+        __syncwarp();
+        // ... and write it out as 128-byte row segments: 8 lanes per row, 4 rows per instruction.
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + (lane >> 3);
+          const int c4 = lane & 7;
+          const float4 v = *reinterpret_cast<const float4*>(stage_buf + row * kStageRowWords + c4 * 4);
+          const size_t off = static_cast<size_t>(m0 + ew * 32 + row) * g.n + n0 + col + c4 * 4;
+          if (g.c_peer != nullptr)
+            ptx::st_stream_v4(reinterpret_cast<uint4*>(g.c_peer + off),
+                              make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z),
+                                         __float_as_uint(v.w)));
+          if (g.c_local != nullptr) *reinterpret_cast<float4*>(g.c_local + off) = v;
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);  // accumulator may be overwritten
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(kTmemCols))
+                 : "memory");
+  // Put epilogue: the last CTA publishes the arrival epoch on the peer.
+  if (g.sync.ticket != nullptr)
+    last_cta_publish(g.sync.ticket, g.sync.ticket_base + gridDim.x, g.sync.signal_flag, g.sync.signal_epoch);
+}
+
+PFN_cuTensorMapEncodeTiled gemm_tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+    (void)cudaGetLastError();
+  });
+  HPCP_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available");
+  return fn;
+}
+
+CUtensorMap make_kmajor_map(const void* base, int rows, int k, int box_rows) {
+  CUtensorMap map;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(k) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t elem_strides[2] = {1, 1};
+  const CUresult r = gemm_tensor_map_encoder()(
+      &map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, elem_strides,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  HPCP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string(r));
+  return map;
+}
+
+}  // namespace
+
+int launch_gemm_put(const void* a_bf16, const void* b_bf16, float* c_local, float* c_peer, int m, int n,
+                    int k, const SyncOps& sync, int ctas, int device, cudaStream_t stream) {
+  HPCP_REQUIRE(m > 0 && n > 0 && k > 0 && m % kBM == 0 && n % kBN == 0 && k % kBK == 0,
+               "gemm_put: M, N, K must be multiples of 128, 256, 64");
+  HPCP_REQUIRE(c_local != nullptr || c_peer != nullptr, "gemm_put: no output");
+  HPCP_REQUIRE((reinterpret_cast<uintptr_t>(a_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(b_bf16) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(c_local) & 15) == 0 && (reinterpret_cast<uintptr_t>(c_peer) & 15) == 0,
+               "gemm_put: pointers must be 16-byte aligned");
+  HPCP_REQUIRE(sync.signal_flag == nullptr || sync.ticket != nullptr, "gemm_put: a signal needs a ticket counter");
+  const CUtensorMap map_a = make_kmajor_map(a_bf16, m, k, kBM);
+  const CUtensorMap map_b = make_kmajor_map(b_bf16, n, k, kBN);
+  GemmDev g{};
+  g.c_local = c_local;
+  g.c_peer = c_peer;
+  g.m = m;
+  g.n = n;
+  g.k = k;
+  g.tiles_m = m / kBM;
+  g.tiles_n = n / kBN;
+  g.sync = sync;
+  const int tiles = g.tiles_m * g.tiles_n;
+  const int sms = device_sm_count(device);
+  const int grid = std::min(tiles, ctas > 0 ? ctas : sms);
+  HPCP_ENABLE_SMEM(gemm_put_kernel, kSmemBytes);
+  gemm_put_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_a, map_b, g);
+  HPCP_CUDA(cudaGetLastError());
+  return grid;
+}
+
+}  // namespace hpcp

@@ -320,3 +320,43 @@ def test_concurency_tensor_command(native):
                                            "--commands", "T", "H2D", "--commands", "T", "C"], "cuda")
     assert out.count("## nowait | T") == 2, out + err
     assert "tripcount_T" in out
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (256, 512, 256), (1024, 1024, 512), (384, 768, 4096)])
+def test_gemm_put_matches_fp32_reference(native, dev, m, n, k):
+    """tcgen05 GEMM (TMA ring, TMEM accumulators) vs a plain PyTorch fp32 matmul; loop-back 'peer'."""
+    from hpc_patterns_b200.ops.gemm import gemm_put, gemm_reference
+
+    torch.manual_seed(m + n + k)
+    a = (torch.randint(-4, 5, (m, k), device=dev).float() / 4).to(torch.bfloat16)   # exactly representable
+    b = (torch.randint(-4, 5, (n, k), device=dev).float() / 4).to(torch.bfloat16)
+    c_local = torch.full((m, n), float("nan"), device=dev)
+    c_peer = torch.full((m, n), float("nan"), device=dev)
+    ctas = gemm_put(a, b, c_local, c_peer)
+    torch.cuda.synchronize()
+    ref = gemm_reference(a, b)
+    assert ctas >= 1
+    assert torch.equal(c_local, ref), float((c_local - ref).abs().max())   # sums of small dyadic rationals: exact
+    assert torch.equal(c_peer, c_local)
+    # random normal data: compare with tolerance against the fp32 reference
+    a = torch.randn(m, k, device=dev).to(torch.bfloat16)
+    b = torch.randn(n, k, device=dev).to(torch.bfloat16)
+    gemm_put(a, b, c_local, 0)
+    torch.cuda.synchronize()
+    ref = gemm_reference(a, b)
+    assert torch.allclose(c_local, ref, rtol=1e-3, atol=1e-2 * (k ** 0.5)), float((c_local - ref).abs().max())
+
+
+def test_gemm_put_signal_and_few_ctas(native, dev):
+    from hpc_patterns_b200.ops.gemm import gemm_put, gemm_reference
+
+    a = (torch.randint(-2, 3, (512, 256), device=dev).float()).to(torch.bfloat16)
+    b = (torch.randint(-2, 3, (1024, 256), device=dev).float()).to(torch.bfloat16)
+    c_peer = torch.zeros(512, 1024, device=dev)
+    pad = torch.zeros(256, dtype=torch.int32, device=dev)
+    sync = {"signal_flag": pad.data_ptr() + 4 * native.PAD_DONE, "signal_epoch": 7,
+            "ticket": pad.data_ptr() + 4 * native.PAD_LOCAL, "ticket_base": 0}
+    ctas = gemm_put(a, b, None, c_peer, sync=sync, ctas=3)     # 16 tiles on 3 persistent CTAs
+    torch.cuda.synchronize()
+    assert ctas == 3 and int(pad[native.PAD_DONE]) == 7 and int(pad[native.PAD_LOCAL]) == 3
+    assert torch.equal(c_peer, gemm_reference(a, b))
