@@ -136,8 +136,9 @@ void launch_tc_busy(const void* operands, float* out, int ctas, uint32_t tripcou
 // C[M,N] fp32 = A[M,K] . B[N,K]^T (bf16, K-major) with tcgen05/TMEM/TMA; the epilogue writes the tile to
 // c_local and/or straight into c_peer over NVLink, then publishes sync.signal_flag.  M % 128 == N % 256 ==
 // K % 64 == 0.  Returns the number of CTAs launched.
-int launch_gemm_put(const void* a_bf16, const void* b_bf16, float* c_local, float* c_peer, int m, int n,
-                    int k, const SyncOps& sync, int ctas, int device, cudaStream_t stream);
+// out_bf16: C is stored as bf16 (half the NVLink bytes) instead of fp32.
+int launch_gemm_put(const void* a_bf16, const void* b_bf16, void* c_local, void* c_peer, int m, int n,
+                    int k, bool out_bf16, const SyncOps& sync, int ctas, int device, cudaStream_t stream);
 
 // ------------------------------------------------------ allreduce miniapp ----
 enum class ElemType : int { kFloat = 0, kInt = 1 };

@@ -104,8 +104,9 @@ __device__ __forceinline__ void tc_fence_after() {
 }
 
 struct GemmDev {
-  float* c_local;   // may be null
-  float* c_peer;    // may be null
+  void* c_local;    // may be null; fp32 [M,N], or bf16 [M,N] when out_bf16
+  void* c_peer;     // may be null
+  int out_bf16;
   int m, n, k;
   int tiles_m, tiles_n;
   SyncOps sync;
@@ -240,11 +241,22 @@ __global__ void __launch_bounds__(kThreads, 1)
           const int c4 = lane & 7;
           const float4 v = *reinterpret_cast<const float4*>(stage_buf + row * kStageRowWords + c4 * 4);
           const size_t off = static_cast<size_t>(m0 + ew * 32 + row) * g.n + n0 + col + c4 * 4;
-          if (g.c_peer != nullptr)
-            ptx::st_stream_v4(reinterpret_cast<uint4*>(g.c_peer + off),
-                              make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z),
-                                         __float_as_uint(v.w)));
-          if (g.c_local != nullptr) *reinterpret_cast<float4*>(g.c_local + off) = v;
+          if (g.out_bf16) {  // 4 fp32 -> 4 bf16 (8 bytes per lane, 64-byte row segments)
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+            const uint2 packed = make_uint2(*reinterpret_cast<const uint32_t*>(&lo),
+                                            *reinterpret_cast<const uint32_t*>(&hi));
+            if (g.c_peer != nullptr)
+              *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(g.c_peer) + off) = packed;
+            if (g.c_local != nullptr)
+              *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(g.c_local) + off) = packed;
+          } else {
+            if (g.c_peer != nullptr)
+              ptx::st_stream_v4(reinterpret_cast<uint4*>(static_cast<float*>(g.c_peer) + off),
+                                make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z),
+                                           __float_as_uint(v.w)));
+            if (g.c_local != nullptr) *reinterpret_cast<float4*>(static_cast<float*>(g.c_local) + off) = v;
+          }
         }
         __syncwarp();
       }
@@ -295,8 +307,8 @@ CUtensorMap make_kmajor_map(const void* base, int rows, int k, int box_rows) {
 
 }  // namespace
 
-int launch_gemm_put(const void* a_bf16, const void* b_bf16, float* c_local, float* c_peer, int m, int n,
-                    int k, const SyncOps& sync, int ctas, int device, cudaStream_t stream) {
+int launch_gemm_put(const void* a_bf16, const void* b_bf16, void* c_local, void* c_peer, int m, int n,
+                    int k, bool out_bf16, const SyncOps& sync, int ctas, int device, cudaStream_t stream) {
   HPCP_REQUIRE(m > 0 && n > 0 && k > 0 && m % kBM == 0 && n % kBN == 0 && k % kBK == 0,
                "gemm_put: M, N, K must be multiples of 128, 256, 64");
   HPCP_REQUIRE(c_local != nullptr || c_peer != nullptr, "gemm_put: no output");
@@ -309,6 +321,7 @@ int launch_gemm_put(const void* a_bf16, const void* b_bf16, float* c_local, floa
   GemmDev g{};
   g.c_local = c_local;
   g.c_peer = c_peer;
+  g.out_bf16 = out_bf16 ? 1 : 0;
   g.m = m;
   g.n = n;
   g.k = k;

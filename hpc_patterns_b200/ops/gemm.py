@@ -19,8 +19,12 @@ from ._util import PtrLike, current_stream, ptr
 
 
 def gemm_put(a: torch.Tensor, b: torch.Tensor, c_local: Optional[torch.Tensor] = None, c_peer: PtrLike = 0,
-             sync: Optional[dict] = None, ctas: int = 0, stream: Optional[int] = None) -> int:
-    """Launch the fused GEMM(+put).  Returns the number of CTAs launched (for ticket bookkeeping)."""
+             sync: Optional[dict] = None, ctas: int = 0, stream: Optional[int] = None,
+             out_dtype: torch.dtype = torch.float32) -> int:
+    """Launch the fused GEMM(+put).  ``out_dtype`` fp32 or bf16 (c_local / c_peer hold that type).
+    Returns the number of CTAs launched (for ticket bookkeeping)."""
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("out_dtype must be float32 or bfloat16")
     if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
         raise TypeError("gemm_put takes bf16 operands")
     if a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[1]:
@@ -29,12 +33,13 @@ def gemm_put(a: torch.Tensor, b: torch.Tensor, c_local: Optional[torch.Tensor] =
     n = b.shape[0]
     if m % 128 or n % 256 or k % 64:
         raise ValueError("M, N, K must be multiples of 128, 256, 64")
-    if c_local is not None and (c_local.dtype != torch.float32 or tuple(c_local.shape) != (m, n)):
-        raise ValueError("c_local must be fp32 [M,N]")
+    if c_local is not None and (c_local.dtype != out_dtype or tuple(c_local.shape) != (m, n)):
+        raise ValueError("c_local must be [M,N] of out_dtype")
     dev = a.device.index
     return native().gemm_put(ptr(a), ptr(b), ptr(c_local) if c_local is not None else 0,
-                             ptr(c_peer) if not isinstance(c_peer, int) else c_peer, m, n, k, sync or {}, ctas,
-                             dev, current_stream(dev) if stream is None else stream)
+                             ptr(c_peer) if not isinstance(c_peer, int) else c_peer, m, n, k,
+                             out_dtype == torch.bfloat16, sync or {}, ctas, dev,
+                             current_stream(dev) if stream is None else stream)
 
 
 def gemm_reference(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:

@@ -345,6 +345,11 @@ def test_gemm_put_matches_fp32_reference(native, dev, m, n, k):
     torch.cuda.synchronize()
     ref = gemm_reference(a, b)
     assert torch.allclose(c_local, ref, rtol=1e-3, atol=1e-2 * (k ** 0.5)), float((c_local - ref).abs().max())
+    # bf16 output: the fp32 accumulator rounded once
+    c_bf = torch.zeros(m, n, device=dev, dtype=torch.bfloat16)
+    gemm_put(a, b, c_bf, 0, out_dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    assert torch.equal(c_bf, c_local.to(torch.bfloat16))
 
 
 def test_gemm_put_signal_and_few_ctas(native, dev):
