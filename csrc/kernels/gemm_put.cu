@@ -103,6 +103,20 @@ __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
+// Tile rasterisation: groups of kGroupM tile-rows, m fastest inside a group, so the ~148 tiles that
+// are in flight at any time cover a near-square block of C (8 x ~18 tiles): fewer distinct A/B
+// panels per k-step than row-major order -> less HBM traffic once A and B exceed the 126 MB L2.
+constexpr int kGroupM = 8;
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int* m_blk, int* n_blk) {
+  const int group_size = kGroupM * tiles_n;
+  const int group = tile / group_size;
+  const int first_m = group * kGroupM;
+  const int gm = tiles_m - first_m < kGroupM ? tiles_m - first_m : kGroupM;
+  const int in_group = tile - group * group_size;
+  *m_blk = first_m + in_group % gm;
+  *n_blk = in_group / gm;
+}
+
 struct GemmDev {
   void* c_local;    // may be null; fp32 [M,N], or bf16 [M,N] when out_bf16
   void* c_peer;     // may be null
@@ -160,8 +174,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / g.tiles_n) * kBM;
-      const int n0 = (tile % g.tiles_n) * kBN;
+      int m_blk, n_blk;
+      tile_coords(tile, g.tiles_m, g.tiles_n, &m_blk, &n_blk);
+      const int m0 = m_blk * kBM;
+      const int n0 = n_blk * kBN;
       for (int kb = 0; kb < num_kb; ++kb) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);  // slot released by the MMA warp
         if (lane == 0) {
@@ -219,8 +235,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
       const int acc = local_tile & 1;
       const uint32_t acc_phase = static_cast<uint32_t>(local_tile >> 1) & 1;
-      const int m0 = (tile / g.tiles_n) * kBM;
-      const int n0 = (tile % g.tiles_n) * kBN;
+      int m_blk, n_blk;
+      tile_coords(tile, g.tiles_m, g.tiles_n, &m_blk, &n_blk);
+      const int m0 = m_blk * kBM;
+      const int n0 = n_blk * kBN;
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kBN) + (static_cast<uint32_t>(ew * 32) << 16);
