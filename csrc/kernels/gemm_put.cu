@@ -26,6 +26,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "../common/cuda_check.h"
@@ -68,6 +69,34 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(x), "r"(y), "r"(ptx::smem_u32(bar))
       : "memory");
 }
+// Multicast variant: the box lands at the same smem offset in every CTA of `cta_mask`, and each of
+// those CTAs' mbarrier (same offset) receives the complete_tx.
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* map, int x, int y,
+                                                      uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(ptx::smem_u32(smem_dst)),
+      "l"(map), "r"(x), "r"(y), "r"(ptx::smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+// tcgen05.commit that arrives on the barrier at this offset in every CTA of `cta_mask`.
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          ptx::smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -126,6 +155,12 @@ struct GemmDev {
   SyncOps sync;
 };
 
+// kCluster == 2: thread-block clusters of two CTAs working on vertically adjacent tiles (same n_blk).
+// Both need the same B tile, so each CTA fetches half of it (128 rows) and TMA-multicasts it into both
+// CTAs' shared memory: L2->SM operand traffic drops from 48 to 32 KiB per CTA per k-block.  A stage
+// may only be refilled when BOTH CTAs' MMAs have consumed it: the empty barriers count 2 arrivals and
+// every tcgen05.commit is multicast to the pair.
+template <int kCluster>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_put_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ GemmDev g) {
@@ -142,13 +177,19 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int lane = threadIdx.x & 31;
   const int num_tiles = g.tiles_m * g.tiles_n;
   const int num_kb = g.k / kBK;
+  const int crank = kCluster > 1 ? static_cast<int>(cluster_cta_rank()) : 0;
+  // Work items are tile pairs in cluster mode: pair p -> tiles 2p, 2p+1 (consecutive tiles of the
+  // grouped rasterisation share n_blk when the group height is even).
+  const int first_item = static_cast<int>(blockIdx.x) / kCluster;
+  const int item_stride = static_cast<int>(gridDim.x) / kCluster;
+  const int num_items = num_tiles / kCluster;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], kCluster);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
@@ -167,24 +208,30 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  if (kCluster > 1) cluster_sync_all();  // the peer's barriers exist before anything remote touches them
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     // The whole warp walks the loop (convergent barriers at kernel end); lane 0 issues the TMA.
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int item = first_item; item < num_items; item += item_stride) {
+      const int tile = item * kCluster + crank;
       int m_blk, n_blk;
       tile_coords(tile, g.tiles_m, g.tiles_n, &m_blk, &n_blk);
       const int m0 = m_blk * kBM;
       const int n0 = n_blk * kBN;
       for (int kb = 0; kb < num_kb; ++kb) {
-        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);  // slot released by the MMA warp
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);  // slot released by the MMA warp(s)
         if (lane == 0) {
           unsigned char* sa = smem + static_cast<size_t>(stage) * kStageBytes;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
           tma_load_2d(sa, &map_a, kb * kBK, m0, &full_bar[stage]);
-          tma_load_2d(sa + kABytes, &map_b, kb * kBK, n0, &full_bar[stage]);
+          if (kCluster > 1)  // my half of the shared B tile, delivered to both CTAs of the pair
+            tma_load_2d_multicast(sa + kABytes + crank * (kBBytes / 2), &map_b, kb * kBK,
+                                  n0 + crank * (kBN / 2), &full_bar[stage], static_cast<uint16_t>(0x3));
+          else
+            tma_load_2d(sa + kABytes, &map_b, kb * kBK, n0, &full_bar[stage]);
         }
         __syncwarp();
         if (++stage == kStages) {
@@ -199,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     int stage = 0;
     uint32_t phase = 0;
     int local_tile = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+    for (int item = first_item; item < num_items; item += item_stride, ++local_tile) {
       const int acc = local_tile & 1;
       const uint32_t acc_phase = static_cast<uint32_t>(local_tile >> 1) & 1;
       ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
@@ -217,7 +264,10 @@ __global__ void __launch_bounds__(kThreads, 1)
             const uint64_t adv = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
             umma_bf16(tmem_d, desc_a + adv, desc_b + adv, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);                              // frees the smem slot
+          if (kCluster > 1)
+            umma_commit_multicast(&empty_bar[stage], static_cast<uint16_t>(0x3));  // frees the slot in both CTAs
+          else
+            umma_commit(&empty_bar[stage]);                            // frees the smem slot
           if (kb == num_kb - 1) umma_commit(&tmem_full_bar[acc]);      // accumulator complete
         }
         __syncwarp();
@@ -232,7 +282,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int ew = warp - 4;            // 0..3 == warp % 4 -> TMEM lane group
     float* stage_buf = reinterpret_cast<float*>(epi_smem + static_cast<size_t>(ew) * kEpiWarpBytes);
     int local_tile = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+    for (int item = first_item; item < num_items; item += item_stride, ++local_tile) {
+      const int tile = item * kCluster + crank;
       const int acc = local_tile & 1;
       const uint32_t acc_phase = static_cast<uint32_t>(local_tile >> 1) & 1;
       int m_blk, n_blk;
@@ -289,6 +340,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"(static_cast<uint32_t>(kTmemCols))
                  : "memory");
+  // A CTA of a pair must not retire while its partner can still multicast into it.
+  if (kCluster > 1) cluster_sync_all();
   // Put epilogue: the last CTA publishes the arrival epoch on the peer.
   if (g.sync.ticket != nullptr)
     last_cta_publish(g.sync.ticket, g.sync.ticket_base + gridDim.x, g.sync.signal_flag, g.sync.signal_epoch);
@@ -326,7 +379,8 @@ CUtensorMap make_kmajor_map(const void* base, int rows, int k, int box_rows) {
 }  // namespace
 
 int launch_gemm_put(const void* a_bf16, const void* b_bf16, void* c_local, void* c_peer, int m, int n,
-                    int k, bool out_bf16, const SyncOps& sync, int ctas, int device, cudaStream_t stream) {
+                    int k, bool out_bf16, const SyncOps& sync, int ctas, int device, cudaStream_t stream,
+                    int cluster) {
   HPCP_REQUIRE(m > 0 && n > 0 && k > 0 && m % kBM == 0 && n % kBN == 0 && k % kBK == 0,
                "gemm_put: M, N, K must be multiples of 128, 256, 64");
   HPCP_REQUIRE(c_local != nullptr || c_peer != nullptr, "gemm_put: no output");
@@ -334,8 +388,13 @@ int launch_gemm_put(const void* a_bf16, const void* b_bf16, void* c_local, void*
                    (reinterpret_cast<uintptr_t>(c_local) & 15) == 0 && (reinterpret_cast<uintptr_t>(c_peer) & 15) == 0,
                "gemm_put: pointers must be 16-byte aligned");
   HPCP_REQUIRE(sync.signal_flag == nullptr || sync.ticket != nullptr, "gemm_put: a signal needs a ticket counter");
+  // Cluster mode needs an even number of tile rows per raster group (pairs share n_blk).
+  HPCP_REQUIRE(cluster == 0 || cluster == 1 || cluster == 2, "gemm_put: cluster must be 0 (auto), 1 or 2");
+  const bool pairable = (m / kBM) % 2 == 0 && ((m / kBM) % kGroupM) % 2 == 0;
+  HPCP_REQUIRE(cluster != 2 || pairable, "gemm_put: cluster=2 needs an even number of 128-row tiles per raster group");
+  const bool use_cluster = cluster != 1 && pairable;
   const CUtensorMap map_a = make_kmajor_map(a_bf16, m, k, kBM);
-  const CUtensorMap map_b = make_kmajor_map(b_bf16, n, k, kBN);
+  const CUtensorMap map_b = make_kmajor_map(b_bf16, n, k, use_cluster ? kBN / 2 : kBN);
   GemmDev g{};
   g.c_local = c_local;
   g.c_peer = c_peer;
@@ -348,10 +407,29 @@ int launch_gemm_put(const void* a_bf16, const void* b_bf16, void* c_local, void*
   g.sync = sync;
   const int tiles = g.tiles_m * g.tiles_n;
   const int sms = device_sm_count(device);
-  const int grid = std::min(tiles, ctas > 0 ? ctas : sms);
-  HPCP_ENABLE_SMEM(gemm_put_kernel, kSmemBytes);
-  gemm_put_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_a, map_b, g);
-  HPCP_CUDA(cudaGetLastError());
+  int grid = std::min(tiles, ctas > 0 ? ctas : sms);
+  if (!use_cluster || grid < 2) {
+    const CUtensorMap map_b_full = use_cluster ? make_kmajor_map(b_bf16, n, k, kBN) : map_b;
+    HPCP_ENABLE_SMEM(gemm_put_kernel<1>, kSmemBytes);
+    gemm_put_kernel<1><<<grid, kThreads, kSmemBytes, stream>>>(map_a, map_b_full, g);
+    HPCP_CUDA(cudaGetLastError());
+    return grid;
+  }
+  grid &= ~1;  // whole pairs
+  HPCP_ENABLE_SMEM(gemm_put_kernel<2>, kSmemBytes);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  HPCP_CUDA(cudaLaunchKernelEx(&cfg, gemm_put_kernel<2>, map_a, map_b, g));
   return grid;
 }
 

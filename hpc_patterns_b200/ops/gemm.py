@@ -20,8 +20,9 @@ from ._util import PtrLike, current_stream, ptr
 
 def gemm_put(a: torch.Tensor, b: torch.Tensor, c_local: Optional[torch.Tensor] = None, c_peer: PtrLike = 0,
              sync: Optional[dict] = None, ctas: int = 0, stream: Optional[int] = None,
-             out_dtype: torch.dtype = torch.float32) -> int:
+             out_dtype: torch.dtype = torch.float32, cluster: int = 0) -> int:
     """Launch the fused GEMM(+put).  ``out_dtype`` fp32 or bf16 (c_local / c_peer hold that type).
+    ``cluster``: 0 auto, 1 = single CTAs, 2 = CTA pairs sharing the B tile through TMA multicast.
     Returns the number of CTAs launched (for ticket bookkeeping)."""
     if out_dtype not in (torch.float32, torch.bfloat16):
         raise TypeError("out_dtype must be float32 or bfloat16")
@@ -39,7 +40,7 @@ def gemm_put(a: torch.Tensor, b: torch.Tensor, c_local: Optional[torch.Tensor] =
     return native().gemm_put(ptr(a), ptr(b), ptr(c_local) if c_local is not None else 0,
                              ptr(c_peer) if not isinstance(c_peer, int) else c_peer, m, n, k,
                              out_dtype == torch.bfloat16, sync or {}, ctas, dev,
-                             current_stream(dev) if stream is None else stream)
+                             current_stream(dev) if stream is None else stream, cluster)
 
 
 def gemm_reference(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:

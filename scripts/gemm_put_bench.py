@@ -50,11 +50,13 @@ def main():
         recv = SymmetricBuffer(comm, m * n * 2, dev, zero=False)
         flops = 2.0 * m * n * k
         st = lambda: torch.cuda.current_stream(dev).cuda_stream  # noqa: E731
+        t_single = timed(lambda: gemm_put(a, b, c, 0, out_dtype=torch.bfloat16, cluster=1), comm, dev)
         t_ours = timed(lambda: gemm_put(a, b, c, 0, out_dtype=torch.bfloat16), comm, dev)
         c_ref = torch.empty(m, n, device=f"cuda:{dev}", dtype=torch.bfloat16)
         t_cublas = timed(lambda: torch.matmul(a, b.t(), out=c_ref), comm, dev)
         row = {"m": m, "n": n, "k": k, "ranks": comm.world, "out": "bf16", "gemm_ms": t_ours,
-               "gemm_tflops": flops / t_ours / 1e9, "cublas_ms": t_cublas, "cublas_tflops": flops / t_cublas / 1e9,
+               "gemm_tflops": flops / t_ours / 1e9, "gemm_tflops_no_cluster": flops / t_single / 1e9,
+               "cublas_ms": t_cublas, "cublas_tflops": flops / t_cublas / 1e9,
                "max_abs_diff_vs_cublas": float((c.float() - c_ref.float()).abs().max())}
         epoch = [0]
 

@@ -322,8 +322,10 @@ def test_concurency_tensor_command(native):
     assert "tripcount_T" in out
 
 
-@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (256, 512, 256), (1024, 1024, 512), (384, 768, 4096)])
-def test_gemm_put_matches_fp32_reference(native, dev, m, n, k):
+@pytest.mark.parametrize("cluster", [1, 0])
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (256, 512, 256), (1024, 1024, 512), (384, 768, 4096),
+                                   (2048, 2048, 1024), (1280, 512, 192)])
+def test_gemm_put_matches_fp32_reference(native, dev, m, n, k, cluster):
     """tcgen05 GEMM (TMA ring, TMEM accumulators) vs a plain PyTorch fp32 matmul; loop-back 'peer'."""
     from hpc_patterns_b200.ops.gemm import gemm_put, gemm_reference
 
@@ -332,7 +334,7 @@ def test_gemm_put_matches_fp32_reference(native, dev, m, n, k):
     b = (torch.randint(-4, 5, (n, k), device=dev).float() / 4).to(torch.bfloat16)
     c_local = torch.full((m, n), float("nan"), device=dev)
     c_peer = torch.full((m, n), float("nan"), device=dev)
-    ctas = gemm_put(a, b, c_local, c_peer)
+    ctas = gemm_put(a, b, c_local, c_peer, cluster=cluster)
     torch.cuda.synchronize()
     ref = gemm_reference(a, b)
     assert ctas >= 1
@@ -341,7 +343,7 @@ def test_gemm_put_matches_fp32_reference(native, dev, m, n, k):
     # random normal data: compare with tolerance against the fp32 reference
     a = torch.randn(m, k, device=dev).to(torch.bfloat16)
     b = torch.randn(n, k, device=dev).to(torch.bfloat16)
-    gemm_put(a, b, c_local, 0)
+    gemm_put(a, b, c_local, 0, cluster=cluster)
     torch.cuda.synchronize()
     ref = gemm_reference(a, b)
     assert torch.allclose(c_local, ref, rtol=1e-3, atol=1e-2 * (k ** 0.5)), float((c_local - ref).abs().max())
