@@ -363,7 +363,13 @@ def test_gemm_put_signal_and_few_ctas(native, dev):
     pad = torch.zeros(256, dtype=torch.int32, device=dev)
     sync = {"signal_flag": pad.data_ptr() + 4 * native.PAD_DONE, "signal_epoch": 7,
             "ticket": pad.data_ptr() + 4 * native.PAD_LOCAL, "ticket_base": 0}
-    ctas = gemm_put(a, b, None, c_peer, sync=sync, ctas=3)     # 16 tiles on 3 persistent CTAs
+    ctas = gemm_put(a, b, None, c_peer, sync=sync, ctas=3, cluster=1)   # 16 tiles on 3 persistent CTAs
     torch.cuda.synchronize()
     assert ctas == 3 and int(pad[native.PAD_DONE]) == 7 and int(pad[native.PAD_LOCAL]) == 3
+    assert torch.equal(c_peer, gemm_reference(a, b))
+    c_peer.zero_()
+    sync.update(signal_epoch=8, ticket_base=3)
+    ctas = gemm_put(a, b, None, c_peer, sync=sync, ctas=5, cluster=2)   # CTA pairs: 5 -> 4 CTAs
+    torch.cuda.synchronize()
+    assert ctas == 4 and int(pad[native.PAD_DONE]) == 8 and int(pad[native.PAD_LOCAL]) == 7
     assert torch.equal(c_peer, gemm_reference(a, b))
