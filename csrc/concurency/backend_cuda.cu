@@ -415,10 +415,16 @@ class CudaBackend final : public Backend {
     // PCIe traffic driven from the SMs (zero-copy TMA / ld-st on pinned memory) reaches copy-engine
     // speed in ONE direction (51-53 vs 55 GB/s) but not in both at once (74 vs 111 GB/s measured,
     // profiles/r1_call4_1gpu): with two or more host copies in the group they go to the copy engines.
-    int host_copies = 0;
-    for (const auto& c : cmds)
-      if (c.is_copy() && (c.src_kind == AllocKind::kPinned || c.dst_kind == AllocKind::kPinned)) ++host_copies;
+    // The same holds for NVLink when one GPU drives both directions at once (put + get from the same
+    // SMs: 866 vs ~1400 GB/s with the copy engines, profiles/r1_call12_2gpu).
+    int host_copies = 0, peer_copies = 0;
+    for (const auto& c : cmds) {
+      if (!c.is_copy()) continue;
+      if (c.src_kind == AllocKind::kPinned || c.dst_kind == AllocKind::kPinned) ++host_copies;
+      if (c.name[0] == 'P' || c.name[1] == 'P') ++peer_copies;
+    }
     const bool host_copies_on_ce = host_copies >= 2 && std::getenv("HPCP_FUSED_HOST_ZERO_COPY") == nullptr;
+    const bool peer_copies_on_ce = peer_copies >= 2 && std::getenv("HPCP_FUSED_PEER_IN_KERNEL") == nullptr;
     for (const auto& c : cmds) {
       FusedCommand f;
       if (c.name == "C") {
@@ -439,6 +445,9 @@ class CudaBackend final : public Backend {
         side.push_back(&c);  // a kernel cannot dereference pageable host memory on x86 B200
         continue;
       } else if (host_copies_on_ce && (c.src_kind == AllocKind::kPinned || c.dst_kind == AllocKind::kPinned)) {
+        side.push_back(&c);
+        continue;
+      } else if (peer_copies_on_ce && (c.name[0] == 'P' || c.name[1] == 'P')) {
         side.push_back(&c);
         continue;
       } else {

@@ -293,39 +293,53 @@ __global__ void __launch_bounds__(kThreads, 1)
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kBN) + (static_cast<uint32_t>(ew * 32) << 16);
-      for (int col = 0; col < kBN; col += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + col, r);
-        // thread == accumulator row: park the 32-column row segment in padded smem ...
+      // One round moves a 128-byte row segment per accumulator row: 32 fp32 columns, or 64 bf16
+      // columns (two TMEM loads, converted before staging), so the NVLink / HBM stores below are
+      // always full 128-byte segments.
+      const int cols_per_round = g.out_bf16 ? 64 : 32;
+      const size_t elem = g.out_bf16 ? 2 : 4;
+      unsigned char* stage_row = reinterpret_cast<unsigned char*>(stage_buf) + lane * (kStageRowWords * 4);
+      for (int col = 0; col < kBN; col += cols_per_round) {
+        if (g.out_bf16) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(stage_buf + lane * kStageRowWords + j) =
-              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                          __uint_as_float(r[j + 3]));
+          for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(taddr + col + half * 32, r);
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              __nv_bfloat162 t;
+              t = __floats2bfloat162_rn(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+              pk.x = *reinterpret_cast<uint32_t*>(&t);
+              t = __floats2bfloat162_rn(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+              pk.y = *reinterpret_cast<uint32_t*>(&t);
+              t = __floats2bfloat162_rn(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
+              pk.z = *reinterpret_cast<uint32_t*>(&t);
+              t = __floats2bfloat162_rn(__uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
+              pk.w = *reinterpret_cast<uint32_t*>(&t);
+              *reinterpret_cast<uint4*>(stage_row + half * 64 + j * 2) = pk;
+            }
+          }
+        } else {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + col, r);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(stage_row + j * 4) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        }
         __syncwarp();
-        // ... and write it out as 128-byte row segments: 8 lanes per row, 4 rows per instruction.
+        // 8 lanes x 16 B per row, 4 rows per instruction.
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int row = it * 4 + (lane >> 3);
-          const int c4 = lane & 7;
-          const float4 v = *reinterpret_cast<const float4*>(stage_buf + row * kStageRowWords + c4 * 4);
-          const size_t off = static_cast<size_t>(m0 + ew * 32 + row) * g.n + n0 + col + c4 * 4;
-          if (g.out_bf16) {  // 4 fp32 -> 4 bf16 (8 bytes per lane, 64-byte row segments)
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
-            const __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
-            const uint2 packed = make_uint2(*reinterpret_cast<const uint32_t*>(&lo),
-                                            *reinterpret_cast<const uint32_t*>(&hi));
-            if (g.c_peer != nullptr)
-              *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(g.c_peer) + off) = packed;
-            if (g.c_local != nullptr)
-              *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(g.c_local) + off) = packed;
-          } else {
-            if (g.c_peer != nullptr)
-              ptx::st_stream_v4(reinterpret_cast<uint4*>(static_cast<float*>(g.c_peer) + off),
-                                make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z),
-                                           __float_as_uint(v.w)));
-            if (g.c_local != nullptr) *reinterpret_cast<float4*>(static_cast<float*>(g.c_local) + off) = v;
-          }
+          const int c16 = lane & 7;
+          const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(stage_buf) +
+                                                          row * (kStageRowWords * 4) + c16 * 16);
+          const size_t off = (static_cast<size_t>(m0 + ew * 32 + row) * g.n + n0 + col) * elem + c16 * 16;
+          if (g.c_peer != nullptr)
+            ptx::st_stream_v4(reinterpret_cast<uint4*>(static_cast<unsigned char*>(g.c_peer) + off), v);
+          if (g.c_local != nullptr)
+            *reinterpret_cast<uint4*>(static_cast<unsigned char*>(g.c_local) + off) = v;
         }
         __syncwarp();
       }
