@@ -43,6 +43,9 @@ def parse_args():
     ap.add_argument("--blocked", type=int, default=int(os.environ.get("HPCP_BENCH_BLOCKED", "0")))
     ap.add_argument("--stages", type=int, default=int(os.environ.get("HPCP_BENCH_STAGES", "0")))
     ap.add_argument("--stage-kb", type=int, default=int(os.environ.get("HPCP_BENCH_STAGE_KB", "0")))
+    ap.add_argument("--compute-ratio", type=int, default=int(os.environ.get("HPCP_BENCH_RATIO", "3")),
+                    help="triad runs over R x the message (local domain), the halo (= message) is put; "
+                         "R=3 balances HBM time against NVLink time like the reference's autotuner; R=1 puts all")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-extras", action="store_true", help="skip the unfused / stock comparison runs")
     return ap.parse_args()
@@ -85,7 +88,8 @@ def main() -> int:
         tune["stages"] = args.stages
     if args.stage_kb:
         tune["stage_kb"] = args.stage_kb
-    ex = FusedTriadExchange(comm, device, args.bytes, s=3.0, engine=args.engine, tune=tune)
+    ex = FusedTriadExchange(comm, device, args.bytes, s=3.0, engine=args.engine, tune=tune,
+                            compute_ratio=args.compute_ratio)
     stream = torch.cuda.current_stream(device)
 
     def timed(fn, steps, sampler=None):
@@ -156,9 +160,32 @@ def main() -> int:
             "per_gpu_GBps": round(per_gpu, 1),
             "frac_of_nvlink_770_measured": round(per_gpu / 770.0, 3) if world > 1 else None,
             "frac_of_nvlink_900_nominal": round(per_gpu / 900.0, 3) if world > 1 else None,
-            # N=1 is HBM-bound: 2 reads + 2 writes of the message per step
-            "hbm_traffic_GBps": round(4 * args.bytes / (ms_per_step * 1e-3) / 1e9, 1) if world == 1 else None,
+            # HBM traffic per step: R x (2 reads + 1 write) of the message, + the loop-back write at N=1
+            "hbm_traffic_GBps": round((3 * args.compute_ratio + (1 if world == 1 else 0)) * args.bytes
+                                      / (ms_per_step * 1e-3) / 1e9, 1),
         })
+        if args.compute_ratio != 1:
+            # Same step with compute_ratio = 1 (everything that is computed is put): NVLink-bound at N >= 2.
+            ex1 = FusedTriadExchange(comm, device, args.bytes, s=3.0, engine=args.engine, tune=tune, compute_ratio=1)
+            for _ in range(3):
+                ex1.step()
+            k1 = max(5, min(args.steps, 50))
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(device)
+            comm.barrier()
+            e0.record(stream)
+            for _ in range(k1):
+                ex1.step()
+            e1.record(stream)
+            torch.cuda.synchronize(device)
+            comm.barrier()
+            ms1 = comm.max(e0.elapsed_time(e1)) / k1
+            ex1.check()
+            extras["compute_ratio_1"] = {"ms_per_step": round(ms1, 5),
+                                         "value": round(world * args.bytes / (ms1 * 1e-3) / 1e9, 2),
+                                         "wrong_words": int(comm.sum(ex1.verify()))}
+            ex1.close()
 
     # ---- end to end through the public API: H2D of the step input + D2H of the result ----
     c_host = ex.make_host_input()
@@ -184,6 +211,7 @@ def main() -> int:
 
     if comm.rank == 0:
         out = {
+            "impl": "ours",
             "metric": "p2p_bus_GBps (fused stream-triad + P2P put, 188743680 B message, aggregate over GPUs)",
             "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 5),
@@ -193,8 +221,12 @@ def main() -> int:
                 "model": "concurency/bench fused stream-triad + peer2pear P2P put (ring neighbour)",
                 "global_batch": world, "seq_len": args.bytes // 4, "parallelism": f"ring{world}",
                 "message_bytes": args.bytes, "engine": args.engine,
+                "compute_ratio": args.compute_ratio,
+                "compute": f"stream triad over {args.compute_ratio} x the message per GPU (local domain), the first "
+                           "1/R of the result (the halo) is put; R chosen so that the triad's HBM time ~ the put's "
+                           "NVLink time, as the reference's autotuner balances the commands of a group",
                 "peer": "self loop-back (no NVLink at N=1)" if world == 1 else "rank+1 over NVLink/NVSwitch",
-                "l2": "inputs larger than L2: 3 x 180 MiB streamed per step, no reuse between steps",
+                "l2": f"inputs larger than L2: {3 * args.compute_ratio} x 180 MiB streamed per step, no reuse between steps",
                 "timing": "cuda events on the launching stream, max over ranks",
                 "note": "fp32 is the reference's dtype (APP_DATA_TYPE float); bytes moved, not FLOPs, are the metric",
             },

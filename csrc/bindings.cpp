@@ -262,7 +262,7 @@ PYBIND11_MODULE(_C, m) {
       "triad_put",
       [](uintptr_t a_local, uintptr_t a_peer, uintptr_t b, uintptr_t c, float s, size_t n,
          const std::string& engine, const py::dict& tune, const py::dict& sync, uintptr_t arrive_flag,
-         uint32_t arrive_epoch, int device, uintptr_t stream) {
+         uint32_t arrive_epoch, int device, uintptr_t stream, size_t n_put) {
         TriadPutArgs t;
         t.a_local = as_ptr<float>(a_local);
         t.a_peer = as_ptr<float>(a_peer);
@@ -270,6 +270,7 @@ PYBIND11_MODULE(_C, m) {
         t.c = as_ptr<const float>(c);
         t.s = s;
         t.n = n;
+        t.n_put = n_put;
         return launch_triad_put(t, engine_from(engine), tuning_from(tune), sync_from(sync),
                                 as_ptr<const uint32_t>(arrive_flag), arrive_epoch, device,
                                 as_stream(stream));
@@ -277,8 +278,9 @@ PYBIND11_MODULE(_C, m) {
       py::arg("a_local"), py::arg("a_peer"), py::arg("b"), py::arg("c"), py::arg("s"), py::arg("n"),
       py::arg("engine") = "ldst", py::arg("tune") = py::dict(), py::arg("sync") = py::dict(),
       py::arg("arrive_flag") = 0, py::arg("arrive_epoch") = 0, py::arg("device") = 0,
-      py::arg("stream") = 0,
-      "Fused a = b + s*c written to a_local AND the peer-mapped a_peer (0 = no put), then signal.");
+      py::arg("stream") = 0, py::arg("n_put") = 0,
+      "Fused a = b + s*c written to a_local AND the peer-mapped a_peer (0 = no put), then signal. "
+      "n_put < n: halo mode, only a[0:n_put) is put to the peer.");
   m.def("fill_triad_inputs", [](uintptr_t b, uintptr_t c, size_t n, int rank, uintptr_t stream) {
     launch_fill_triad_inputs(as_ptr<float>(b), as_ptr<float>(c), n, rank, as_stream(stream));
   });

@@ -88,7 +88,9 @@ struct TriadPutArgs {
   const float* b = nullptr;
   const float* c = nullptr;
   float s = 0.f;
-  size_t n = 0;             // elements, multiple of 4
+  size_t n = 0;             // elements the triad runs over, multiple of 4
+  size_t n_put = 0;         // halo: only a[0:n_put) also goes to the peer; 0 -> n.  n % n_put == 0 and
+                            // (when n_put < n) n_put * 4 a multiple of the 16 KiB tile
 };
 int launch_triad_put(const TriadPutArgs& args, CopyEngine engine, const CopyTuning& tune,
                      const SyncOps& sync, const uint32_t* arrive_flag, uint32_t arrive_epoch,

@@ -114,6 +114,42 @@ __global__ void __launch_bounds__(512)
   cta_epilogue(sync, arrive_flag, arrive_epoch);
 }
 
+// Halo mode of the LdSt engine: triad over `ratio` * n_put_vec vectors, the first n_put_vec of them
+// (the halo) are also stored into the peer.  Work is dealt in 16 KiB tiles, one halo tile followed by
+// ratio-1 interior tiles, so NVLink-bound and HBM-bound tiles interleave inside every CTA.
+constexpr int kHaloTileVec = 1024;  // uint4 per tile = 16 KiB
+template <bool kPut>
+__global__ void __launch_bounds__(512)
+    triad_halo_ldst_kernel(uint4* __restrict__ a_local, uint4* __restrict__ a_peer,
+                           const uint4* __restrict__ b, const uint4* __restrict__ c, float s,
+                           size_t n_put_vec, int ratio, SyncOps sync, const uint32_t* arrive_flag,
+                           uint32_t arrive_epoch) {
+  if (!cta_prologue_wait(sync)) return;
+  const size_t halo_tiles = n_put_vec / kHaloTileVec;
+  const size_t total_tiles = halo_tiles * ratio;
+  for (size_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const size_t g = t / ratio, r = t % ratio;
+    const bool halo = r == 0;
+    const size_t base = (halo ? g : halo_tiles + (ratio - 1) * g + (r - 1)) * kHaloTileVec;
+#pragma unroll
+    for (int v0 = 0; v0 < kHaloTileVec; v0 += 1024) {
+      uint4 vb[2], vc[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        vb[k] = ld_in(b + base + v0 + threadIdx.x + k * 512);
+        vc[k] = ld_in(c + base + v0 + threadIdx.x + k * 512);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const uint4 va = triad_vec(vb[k], vc[k], s);
+        if (kPut && halo) st_out(a_peer + base + v0 + threadIdx.x + k * 512, va);
+        st_out(a_local + base + v0 + threadIdx.x + k * 512, va);
+      }
+    }
+  }
+  cta_epilogue(sync, arrive_flag, arrive_epoch);
+}
+
 // ------------------------------------------------------------- TMA engine ----
 constexpr int kMathWarps = 4;
 constexpr int kTmaThreads = 32 * (1 + kMathWarps);
@@ -124,7 +160,9 @@ __global__ void __launch_bounds__(kTmaThreads)
     triad_put_tma_kernel(float* __restrict__ a_local, float* __restrict__ a_peer,
                          const float* __restrict__ b, const float* __restrict__ c, float s,
                          size_t n_bytes /*multiple of 16*/, uint32_t tile_bytes, int stages,
-                         SyncOps sync, const uint32_t* arrive_flag, uint32_t arrive_epoch) {
+                         size_t put_bytes /*halo: multiple of tile_bytes; == n_bytes when ratio == 1*/,
+                         int ratio /*n_bytes == ratio * put_bytes*/, SyncOps sync,
+                         const uint32_t* arrive_flag, uint32_t arrive_epoch) {
   extern __shared__ __align__(128) unsigned char smem[];
   const size_t stage_stride = 2 * static_cast<size_t>(tile_bytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * stage_stride);
@@ -145,8 +183,18 @@ __global__ void __launch_bounds__(kTmaThreads)
   const size_t n = tiles_total > blockIdx.x
                        ? (tiles_total - blockIdx.x + gridDim.x - 1) / gridDim.x
                        : 0;
+  // Halo mode (ratio R > 1): the triad runs over R * put_bytes but only the first put_bytes (the
+  // halo) travel to the peer.  Logical tiles interleave one halo tile with R-1 interior tiles, so
+  // the NVLink stream and the HBM-only stream of every CTA advance together instead of one after
+  // the other (the reference's autotuner balances command durations the same way).
   auto tile_off = [&](size_t j) {
-    return (static_cast<size_t>(blockIdx.x) + j * gridDim.x) * tile_bytes;
+    const size_t t = static_cast<size_t>(blockIdx.x) + j * gridDim.x;
+    if (ratio <= 1) return t * tile_bytes;
+    const size_t g = t / ratio, r = t % ratio;
+    return r == 0 ? g * tile_bytes : put_bytes + ((ratio - 1) * g + (r - 1)) * tile_bytes;
+  };
+  auto tile_is_halo = [&](size_t j) {
+    return ratio <= 1 || (static_cast<size_t>(blockIdx.x) + j * gridDim.x) % ratio == 0;
   };
   auto tile_len = [&](size_t j) {
     const size_t off = tile_off(j);
@@ -175,7 +223,7 @@ __global__ void __launch_bounds__(kTmaThreads)
         ptx::mbar_wait(&computed[st], static_cast<uint32_t>((j / stages) & 1));
         const unsigned char* sa = smem + st * stage_stride;  // `a` overwrote the b tile
         ptx::bulk_s2g(alb + tile_off(j), sa, tile_len(j));
-        if (kPut) ptx::bulk_s2g(apb + tile_off(j), sa, tile_len(j));
+        if (kPut && tile_is_halo(j)) ptx::bulk_s2g(apb + tile_off(j), sa, tile_len(j));
         ptx::bulk_commit();
         const size_t nxt = j + lookahead;
         if (nxt < n) {
@@ -238,13 +286,31 @@ int launch_triad_put(const TriadPutArgs& args, CopyEngine engine, const CopyTuni
                      const SyncOps& sync, const uint32_t* arrive_flag, uint32_t arrive_epoch,
                      int device, cudaStream_t stream) {
   HPCP_REQUIRE(args.n % 4 == 0, "triad_put: n must be a multiple of 4 elements");
+  const size_t n_put = args.n_put == 0 ? args.n : args.n_put;
+  HPCP_REQUIRE(n_put <= args.n && args.n % n_put == 0, "triad_put: n must be a multiple of n_put");
+  const int ratio = static_cast<int>(args.n / n_put);
   HPCP_REQUIRE(sync.signal_flag == nullptr || sync.ticket != nullptr,
                "triad_put: a signal needs a ticket counter");
   const int sms = device_sm_count(device);
   const size_t nvec = args.n / 4;
   const bool put = args.a_peer != nullptr;
   int ctas = 0;
-  if (engine == CopyEngine::kLdSt) {
+  if (engine == CopyEngine::kLdSt && ratio > 1) {
+    HPCP_REQUIRE((n_put / 4) % kHaloTileVec == 0, "triad_put: halo (n_put) must be a multiple of 16 KiB");
+    const size_t tiles = (n_put / 4 / kHaloTileVec) * static_cast<size_t>(ratio);
+    const int cap = tune.ctas > 0 ? tune.ctas : sms * 2;
+    ctas = static_cast<int>(std::min<size_t>(tiles, static_cast<size_t>(cap)));
+    uint4* al = reinterpret_cast<uint4*>(args.a_local);
+    uint4* ap = reinterpret_cast<uint4*>(args.a_peer);
+    const uint4* b = reinterpret_cast<const uint4*>(args.b);
+    const uint4* c = reinterpret_cast<const uint4*>(args.c);
+    if (put)
+      triad_halo_ldst_kernel<true><<<ctas, 512, 0, stream>>>(al, ap, b, c, args.s, n_put / 4, ratio, sync,
+                                                             arrive_flag, arrive_epoch);
+    else
+      triad_halo_ldst_kernel<false><<<ctas, 512, 0, stream>>>(al, ap, b, c, args.s, n_put / 4, ratio, sync,
+                                                              arrive_flag, arrive_epoch);
+  } else if (engine == CopyEngine::kLdSt) {
     const int threads = tune.threads > 0 ? std::min(tune.threads, 512) : 512;
     const int unroll = tune.unroll > 0 ? tune.unroll : 2;
     const size_t per_cta = static_cast<size_t>(threads) * unroll * (tune.vec_bytes == 32 ? 2 : 1);
@@ -288,6 +354,9 @@ int launch_triad_put(const TriadPutArgs& args, CopyEngine engine, const CopyTuni
     const size_t smem = static_cast<size_t>(stages) * 2 * tile_bytes + static_cast<size_t>(stages) * 16;
     HPCP_REQUIRE(smem <= 227 * 1024, "triad_put: TMA stages exceed 227 KiB of shared memory");
     const size_t n_bytes = args.n * sizeof(float);
+    const size_t put_bytes = n_put * sizeof(float);
+    HPCP_REQUIRE(ratio == 1 || put_bytes % tile_bytes == 0,
+                 "triad_put: halo (n_put) must be a multiple of the TMA tile size");
     const size_t tiles = std::max<size_t>(1, (n_bytes + tile_bytes - 1) / tile_bytes);
     const int per_sm = std::max(1, static_cast<int>((227 * 1024) / smem));
     const int cap = tune.ctas > 0 ? tune.ctas : sms * per_sm;
@@ -295,13 +364,13 @@ int launch_triad_put(const TriadPutArgs& args, CopyEngine engine, const CopyTuni
     if (put) {
       HPCP_ENABLE_SMEM(triad_put_tma_kernel<true>, smem);
       triad_put_tma_kernel<true><<<ctas, kTmaThreads, smem, stream>>>(
-          args.a_local, args.a_peer, args.b, args.c, args.s, n_bytes, tile_bytes, stages, sync,
-          arrive_flag, arrive_epoch);
+          args.a_local, args.a_peer, args.b, args.c, args.s, n_bytes, tile_bytes, stages, put_bytes, ratio,
+          sync, arrive_flag, arrive_epoch);
     } else {
       HPCP_ENABLE_SMEM(triad_put_tma_kernel<false>, smem);
       triad_put_tma_kernel<false><<<ctas, kTmaThreads, smem, stream>>>(
-          args.a_local, args.a_peer, args.b, args.c, args.s, n_bytes, tile_bytes, stages, sync,
-          arrive_flag, arrive_epoch);
+          args.a_local, args.a_peer, args.b, args.c, args.s, n_bytes, tile_bytes, stages, put_bytes, ratio,
+          sync, arrive_flag, arrive_epoch);
     }
   }
   HPCP_CUDA(cudaGetLastError());

@@ -57,9 +57,19 @@ class FusedTriadExchange:
     """
 
     def __init__(self, comm: Comm, device: int, nbytes: int = REFERENCE_MESSAGE_BYTES, s: float = 3.0,
-                 engine: str = "ldst", tune: Optional[dict] = None, timeout_s: float = 30.0):
+                 engine: str = "ldst", tune: Optional[dict] = None, timeout_s: float = 30.0,
+                 compute_ratio: int = 1):
+        """``compute_ratio`` R: the triad runs over R x the message (the local domain) and only the
+        first ``nbytes`` of the result (the halo) are put to the neighbour.  R balances the HBM time of
+        the compute against the NVLink time of the put, like the reference's autotuner balances the
+        commands of a group; R = 1 puts everything that is computed."""
         if nbytes % 16:
             raise ValueError("message size must be a multiple of 16 bytes")
+        if compute_ratio < 1:
+            raise ValueError("compute_ratio must be >= 1")
+        if compute_ratio > 1 and nbytes % (16 << 10):
+            raise ValueError("halo mode needs a message size that is a multiple of 16 KiB")
+        self.compute_ratio = int(compute_ratio)
         self.C = native()
         self.comm, self.device = comm, device
         self.rank, self.world = comm.rank, comm.world
@@ -71,10 +81,11 @@ class FusedTriadExchange:
         self.pads = SignalPads(comm, device, timeout_s=timeout_s)
         self.recv = SymmetricBuffer(comm, nbytes, device)          # neighbour writes here
         dev = torch.device("cuda", device)
-        self.a = torch.empty(self.n, dtype=torch.float32, device=dev)
-        self.b = torch.empty(self.n, dtype=torch.float32, device=dev)
-        self.c = torch.empty(self.n, dtype=torch.float32, device=dev)
-        self.C.fill_triad_inputs(self.b.data_ptr(), self.c.data_ptr(), self.n, self.rank, self._stream())
+        self.n_total = self.n * self.compute_ratio
+        self.a = torch.empty(self.n_total, dtype=torch.float32, device=dev)
+        self.b = torch.empty(self.n_total, dtype=torch.float32, device=dev)
+        self.c = torch.empty(self.n_total, dtype=torch.float32, device=dev)
+        self.C.fill_triad_inputs(self.b.data_ptr(), self.c.data_ptr(), self.n_total, self.rank, self._stream())
         self.epoch = 0
         self.launches = 0
         self._counter = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -96,15 +107,15 @@ class FusedTriadExchange:
                                   epoch=self.epoch)
         arrive = self.pads.word(self.rank, C.PAD_DONE + self.left) if put else 0
         ctas = C.triad_put(self.a.data_ptr(), self.recv.ptrs[self.right] if put else 0,
-                           self.b.data_ptr(), self.c.data_ptr(), self.s, self.n, self.engine, self.tune,
-                           sync, arrive, self.epoch, self.device, self._stream())
+                           self.b.data_ptr(), self.c.data_ptr(), self.s, self.n_total, self.engine, self.tune,
+                           sync, arrive, self.epoch, self.device, self._stream(), self.n)
         self.pads.advance_tickets(ctas)
         self.launches += 1
 
     # ---- unfused building blocks (for overlap % and the stock comparison) --------------
     def triad_only(self) -> None:
-        self.C.triad_put(self.a.data_ptr(), 0, self.b.data_ptr(), self.c.data_ptr(), self.s, self.n,
-                         self.engine, self.tune, {}, 0, 0, self.device, self._stream())
+        self.C.triad_put(self.a.data_ptr(), 0, self.b.data_ptr(), self.c.data_ptr(), self.s, self.n_total,
+                         self.engine, self.tune, {}, 0, 0, self.device, self._stream(), self.n)
         self.launches += 1
 
     def put_only(self) -> None:
@@ -139,9 +150,10 @@ class FusedTriadExchange:
 
     # ---- end-to-end step through host memory -------------------------------------------
     def make_host_input(self) -> torch.Tensor:
-        """Pinned host copy of this rank's `c` (what a caller would hand in every step)."""
+        """Pinned host copy of the halo part of this rank's `c` — the per-step input a caller hands in
+        (the interior of the local domain stays resident on the device)."""
         if self._host_c is None:
-            self._host_c = self.c.cpu().pin_memory()
+            self._host_c = self.c[:self.n].cpu().pin_memory()
         return self._host_c
 
     def step_from_host(self, c_host: torch.Tensor, chunks: int = 8) -> int:
@@ -155,6 +167,12 @@ class FusedTriadExchange:
         per = ((n + chunks - 1) // chunks + 3) // 4 * 4
         main = torch.cuda.current_stream(self.device)
         self._h2d.wait_stream(main)
+        if self.compute_ratio > 1:
+            # Interior of the local domain: needs nothing from the host, runs under the H2D copies.
+            C.triad_put(self.a.data_ptr() + 4 * n, 0, self.b.data_ptr() + 4 * n, self.c.data_ptr() + 4 * n,
+                        self.s, self.n_total - n, self.engine, self.tune, {}, 0, 0, self.device,
+                        main.cuda_stream, 0)
+            self.launches += 1
         off = 0
         k = 0
         while off < n:

@@ -25,8 +25,8 @@ def main():
                 assert r.uni_gbps > 0 and r.bi_gbps > 0
             b.close()
     # fused exchange over NVLink
-    for engine in ("ldst", "tma"):
-        ex = FusedTriadExchange(comm, dev, nbytes=16 << 20, engine=engine)
+    for engine, ratio in (("ldst", 1), ("tma", 1), ("ldst", 3), ("tma", 3)):
+        ex = FusedTriadExchange(comm, dev, nbytes=16 << 20, engine=engine, compute_ratio=ratio)
         for _ in range(4):
             ex.step()
         torch.cuda.synchronize()

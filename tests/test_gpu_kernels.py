@@ -157,12 +157,32 @@ def test_fill_triad_inputs_and_verify(native, dev):
     assert int(cnt) == 1
 
 
-def test_fused_exchange_loopback(native):
+@pytest.mark.parametrize("engine", ["ldst", "tma"])
+@pytest.mark.parametrize("ratio", [2, 3, 4])
+def test_triad_put_halo_mode(native, dev, engine, ratio):
+    """Triad over ratio x the halo; only the halo reaches the (loop-back) peer buffer."""
+    n_put = (3 * 16384) // 4 * 8          # 24 tiles of 16 KiB
+    n = n_put * ratio
+    b = torch.randn(n, device=dev)
+    c = torch.randn(n, device=dev)
+    a = torch.zeros(n, device=dev)
+    peer = torch.full((n_put + 1024,), -7.0, device=dev)
+    native.triad_put(a.data_ptr(), peer.data_ptr(), b.data_ptr(), c.data_ptr(), 2.0, n, engine, {}, {}, 0, 0, 0,
+                     _stream(), n_put)
+    torch.cuda.synchronize()
+    ref = torch.addcmul(b, c, torch.tensor(2.0, device=dev))
+    assert torch.allclose(a, ref, rtol=1e-6, atol=1e-6)
+    assert torch.equal(peer[:n_put], a[:n_put])
+    assert bool((peer[n_put:] == -7.0).all())      # nothing but the halo was put
+
+
+@pytest.mark.parametrize("ratio", [1, 3])
+def test_fused_exchange_loopback(native, ratio):
     from hpc_patterns_b200.models.peer2pear import FusedTriadExchange
     from hpc_patterns_b200.parallel.comm import Comm
 
     for engine in ("ldst", "tma"):
-        ex = FusedTriadExchange(Comm(), 0, nbytes=8 << 20, engine=engine)
+        ex = FusedTriadExchange(Comm(), 0, nbytes=8 << 20, engine=engine, compute_ratio=ratio)
         for _ in range(3):
             ex.step()
         torch.cuda.synchronize()
