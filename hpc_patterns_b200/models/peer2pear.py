@@ -142,7 +142,8 @@ class FusedTriadExchange:
         elif how == "nccl":
             import torch.distributed as dist
             recv_t = self.recv.tensor(torch.float32)
-            ops = [dist.P2POp(dist.isend, self.a, self.right), dist.P2POp(dist.irecv, recv_t, self.left)]
+            # the message is the halo: the first n elements of `a` (a holds compute_ratio * n elements)
+            ops = [dist.P2POp(dist.isend, self.a[:self.n], self.right), dist.P2POp(dist.irecv, recv_t, self.left)]
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
         else:

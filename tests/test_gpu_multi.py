@@ -19,13 +19,27 @@ needs2 = pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
 
 
 def _run(cmd, timeout=600, env=None):
+    """Run a command in its own process group and kill the WHOLE group on timeout, so that a hung
+    torchrun cannot leave rank processes spinning on the GPUs behind the test."""
+    import signal
+
     e = dict(os.environ)
     e.update(env or {})
-    p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout, env=e)
-    return p.returncode, p.stdout, p.stderr
+    p = subprocess.Popen(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=e,
+                         start_new_session=True)
+    try:
+        out, err = p.communicate(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        try:
+            os.killpg(p.pid, signal.SIGKILL)
+        except ProcessLookupError:
+            pass
+        out, err = p.communicate()
+        return 124, out, err + f"\n[timeout after {timeout}s: process group killed]"
+    return p.returncode, out, err
 
 
-def _torchrun(n, script_args, timeout=900, port=29601):
+def _torchrun(n, script_args, timeout=240, port=29601):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
            "--master-addr", "127.0.0.1", "--master-port", str(port)] + script_args
     return _run(cmd, timeout)
