@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--compute-ratio", type=int, default=int(os.environ.get("HPCP_BENCH_RATIO", "3")),
                     help="triad runs over R x the message (local domain), the halo (= message) is put; "
                          "R=3 balances HBM time against NVLink time like the reference's autotuner; R=1 puts all")
+    ap.add_argument("--halo-ctas", type=int, default=int(os.environ.get("HPCP_BENCH_HALO_CTAS", "0")),
+                    help="EXPERIMENTAL (TMA engine, compute-ratio > 1): dedicate this many CTAs to the halo tiles")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-extras", action="store_true", help="skip the unfused / stock comparison runs")
     return ap.parse_args()
@@ -88,6 +90,8 @@ def main() -> int:
         tune["stages"] = args.stages
     if args.stage_kb:
         tune["stage_kb"] = args.stage_kb
+    if args.halo_ctas:
+        tune["halo_ctas"] = args.halo_ctas
     ex = FusedTriadExchange(comm, device, args.bytes, s=3.0, engine=args.engine, tune=tune,
                             compute_ratio=args.compute_ratio)
     stream = torch.cuda.current_stream(device)

@@ -54,6 +54,7 @@ CopyTuning tuning_from(const py::dict& d) {
   if (d.contains("stages")) t.stages = d["stages"].cast<int>();
   if (d.contains("vec_bytes")) t.vec_bytes = d["vec_bytes"].cast<int>();
   if (d.contains("blocked")) t.blocked = d["blocked"].cast<int>();
+  if (d.contains("halo_ctas")) t.halo_ctas = d["halo_ctas"].cast<int>();
   return t;
 }
 

@@ -161,8 +161,9 @@ __global__ void __launch_bounds__(kTmaThreads)
                          const float* __restrict__ b, const float* __restrict__ c, float s,
                          size_t n_bytes /*multiple of 16*/, uint32_t tile_bytes, int stages,
                          size_t put_bytes /*halo: multiple of tile_bytes; == n_bytes when ratio == 1*/,
-                         int ratio /*n_bytes == ratio * put_bytes*/, SyncOps sync,
-                         const uint32_t* arrive_flag, uint32_t arrive_epoch) {
+                         int ratio /*n_bytes == ratio * put_bytes*/,
+                         int halo_ctas /*EXPERIMENTAL: > 0 dedicates CTAs [0,halo_ctas) to the halo*/,
+                         SyncOps sync, const uint32_t* arrive_flag, uint32_t arrive_epoch) {
   extern __shared__ __align__(128) unsigned char smem[];
   const size_t stage_stride = 2 * static_cast<size_t>(tile_bytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * stage_stride);
@@ -180,20 +181,29 @@ __global__ void __launch_bounds__(kTmaThreads)
   __syncthreads();
 
   const size_t tiles_total = (n_bytes + tile_bytes - 1) / tile_bytes;
-  const size_t n = tiles_total > blockIdx.x
-                       ? (tiles_total - blockIdx.x + gridDim.x - 1) / gridDim.x
-                       : 0;
+  // Split scheduling (experimental, halo mode only): CTAs [0, halo_ctas) stream the halo tiles (the
+  // NVLink-bound work), the remaining CTAs stream the interior (HBM-bound), so neither stream queues
+  // behind the other inside a CTA's in-order DMA thread.
+  const bool split = ratio > 1 && halo_ctas > 0 && halo_ctas < static_cast<int>(gridDim.x);
+  const bool halo_cta = split && static_cast<int>(blockIdx.x) < halo_ctas;
+  const size_t split_idx = halo_cta ? blockIdx.x : blockIdx.x - halo_ctas;
+  const size_t split_stride = halo_cta ? halo_ctas : gridDim.x - halo_ctas;
+  const size_t split_tiles = halo_cta ? put_bytes / tile_bytes : (n_bytes - put_bytes) / tile_bytes;
+  const size_t n = split ? (split_tiles > split_idx ? (split_tiles - split_idx + split_stride - 1) / split_stride : 0)
+                         : (tiles_total > blockIdx.x ? (tiles_total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
   // Halo mode (ratio R > 1): the triad runs over R * put_bytes but only the first put_bytes (the
   // halo) travel to the peer.  Logical tiles interleave one halo tile with R-1 interior tiles, so
   // the NVLink stream and the HBM-only stream of every CTA advance together instead of one after
   // the other (the reference's autotuner balances command durations the same way).
   auto tile_off = [&](size_t j) {
+    if (split) return (halo_cta ? 0 : put_bytes) + (split_idx + j * split_stride) * tile_bytes;
     const size_t t = static_cast<size_t>(blockIdx.x) + j * gridDim.x;
     if (ratio <= 1) return t * tile_bytes;
     const size_t g = t / ratio, r = t % ratio;
     return r == 0 ? g * tile_bytes : put_bytes + ((ratio - 1) * g + (r - 1)) * tile_bytes;
   };
   auto tile_is_halo = [&](size_t j) {
+    if (split) return halo_cta;
     return ratio <= 1 || (static_cast<size_t>(blockIdx.x) + j * gridDim.x) % ratio == 0;
   };
   auto tile_len = [&](size_t j) {
@@ -365,12 +375,12 @@ int launch_triad_put(const TriadPutArgs& args, CopyEngine engine, const CopyTuni
       HPCP_ENABLE_SMEM(triad_put_tma_kernel<true>, smem);
       triad_put_tma_kernel<true><<<ctas, kTmaThreads, smem, stream>>>(
           args.a_local, args.a_peer, args.b, args.c, args.s, n_bytes, tile_bytes, stages, put_bytes, ratio,
-          sync, arrive_flag, arrive_epoch);
+          tune.halo_ctas, sync, arrive_flag, arrive_epoch);
     } else {
       HPCP_ENABLE_SMEM(triad_put_tma_kernel<false>, smem);
       triad_put_tma_kernel<false><<<ctas, kTmaThreads, smem, stream>>>(
           args.a_local, args.a_peer, args.b, args.c, args.s, n_bytes, tile_bytes, stages, put_bytes, ratio,
-          sync, arrive_flag, arrive_epoch);
+          tune.halo_ctas, sync, arrive_flag, arrive_epoch);
     }
   }
   HPCP_CUDA(cudaGetLastError());

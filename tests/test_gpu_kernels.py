@@ -393,3 +393,20 @@ def test_gemm_put_signal_and_few_ctas(native, dev):
     torch.cuda.synchronize()
     assert ctas == 4 and int(pad[native.PAD_DONE]) == 8 and int(pad[native.PAD_LOCAL]) == 7
     assert torch.equal(c_peer, gemm_reference(a, b))
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("HPCP_EXPERIMENTAL"), reason="experimental path, opt-in")
+@pytest.mark.parametrize("halo_ctas", [8, 48, 147])
+def test_triad_put_halo_split_scheduling(native, dev, halo_ctas):
+    """EXPERIMENTAL: dedicated halo CTAs instead of interleaved halo/interior tiles (TMA engine)."""
+    n_put = (64 * 16384) // 4
+    n = n_put * 3
+    b = torch.randn(n, device=dev)
+    c = torch.randn(n, device=dev)
+    a = torch.zeros(n, device=dev)
+    peer = torch.full((n_put + 64,), -7.0, device=dev)
+    native.triad_put(a.data_ptr(), peer.data_ptr(), b.data_ptr(), c.data_ptr(), 2.0, n, "tma",
+                     {"halo_ctas": halo_ctas}, {}, 0, 0, 0, _stream(), n_put)
+    torch.cuda.synchronize()
+    assert torch.allclose(a, torch.addcmul(b, c, torch.tensor(2.0, device=dev)), rtol=1e-6, atol=1e-6)
+    assert torch.equal(peer[:n_put], a[:n_put]) and bool((peer[n_put:] == -7.0).all())
