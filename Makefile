@@ -28,7 +28,7 @@ LIB_OBJS   := $(KERNEL_SRC:csrc/%.cu=$(BUILD)/%.o) $(COMMON_CPP:csrc/%.cpp=$(BUI
 LIB        := $(BUILD)/libhpcp.a
 
 CLIS := bin/concurency bin/omp_con bin/peer2pear bin/topology bin/allreduce bin/interop_torchless \
-        bin/interop_driver
+        bin/interop_driver bin/native_selftest
 
 .PHONY: all cli ext omp_con sass sanitize test clean
 all: cli ext
@@ -76,6 +76,13 @@ bin/interop_torchless: csrc/interop/interop_runtime_streams.cu $(LIB)
 bin/interop_driver: csrc/interop/interop_driver_runtime.cu $(LIB)
 	@mkdir -p bin
 	$(NVCC) $(NVFLAGS) $< $(LIB) -o $@ -lgomp
+
+# host-only unit tests of the native runtime (no GPU needed to run)
+bin/native_selftest: csrc/tests/native_selftest.cpp csrc/concurency/driver.cpp csrc/p2p/topology_core.cpp \
+                     $(wildcard csrc/common/*.h) csrc/miniapps/devices.hpp
+	@mkdir -p bin
+	$(CXX) $(CXXFLAGS) csrc/tests/native_selftest.cpp csrc/concurency/driver.cpp csrc/p2p/topology_core.cpp \
+	    -o $@ -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
 
 ext: $(LIB)
 	$(PYTHON) -m hpc_patterns_b200._build
