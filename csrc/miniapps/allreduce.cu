@@ -22,6 +22,8 @@
 #include <getopt.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
@@ -57,6 +59,7 @@ struct Config {
   size_t chunk_elems = 0;
   uint64_t timeout_ns = 30ull * 1000 * 1000 * 1000;
   std::string json_path;
+  bool cpu = false;  // --cpu: host-only plumbing run (threads as ranks, memcpy as send/recv)
 };
 
 void print_help() {
@@ -77,7 +80,8 @@ void print_help() {
                " --coll auto|nvls|twoshot   collective used with -a\n"
                " --iters N --warmup N  timed / untimed repetitions (min is reported)\n"
                " --ctas N --chunk N    kernel tuning (CTAs per rank, elements per ring chunk)\n"
-               " --json FILE           append one JSON row\n";
+               " --json FILE           append one JSON row\n"
+               " --cpu                 host-only plumbing run: ranks are threads, send/recv are memcpy\n";
 }
 
 struct Shared {
@@ -240,6 +244,64 @@ void rank_main(RankCtx& ctx, Shared& sh) {
   (void)cudaStreamDestroy(stream);
 }
 
+
+// ---------------------------------------------------------------- host-only path ----
+// The reference pattern on the CPU: ranks are threads of the rank runtime, "send to the right
+// neighbour" is a memcpy into its VB, the collective is a direct sum over every rank's VA.  No GPU,
+// no kernels: this is the plumbing configuration used to test the program logic (options, ring
+// order, verification, output) on a machine without a device.
+template <typename T>
+int run_on_host_typed(const Config& cfg) {
+  const int P = cfg.ranks > 0 ? cfg.ranks : 4;
+  const size_t n = size_t{1} << cfg.log2_elems;
+  std::vector<std::vector<T>> va(P), vb(P), vc(P);
+  double elapsed_ms = 0;
+  unsigned long long total_bad = 0;
+  run_ranks(P, [&](RankCtx& ctx) {
+    const int me = ctx.rank, right = (me + 1) % P;
+    va[me].assign(n, static_cast<T>(me));
+    vb[me].assign(n, static_cast<T>(me));
+    vc[me].assign(n, static_cast<T>(0));
+    ctx.barrier();
+    const auto t0 = std::chrono::steady_clock::now();
+    if (cfg.use_collective) {
+      for (int r = 0; r < P; ++r)
+        for (size_t i = 0; i < n; ++i) vc[me][i] += va[r][i];
+    } else {
+      for (size_t i = 0; i < n; ++i) vc[me][i] += va[me][i];
+      for (int s = 1; s < P; ++s) {
+        std::memcpy(vb[right].data(), va[me].data(), n * sizeof(T));  // "send right"
+        ctx.barrier();                                                 // everybody received
+        va[me].swap(vb[me]);
+        ctx.barrier();                                                 // nobody still reads the old VA
+        for (size_t i = 0; i < n; ++i) vc[me][i] += va[me][i];
+      }
+    }
+    const double ms =
+        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    const double t = ctx.max(ms);
+    const T want = static_cast<T>(P * (P - 1) / 2);
+    unsigned long long bad = 0;
+    for (size_t i = 0; i < n; ++i) bad += std::abs(static_cast<double>(vc[me][i]) - static_cast<double>(want)) >= 1e-6;
+    const double all_bad = ctx.sum(static_cast<double>(bad));
+    if (bad == 0)
+      std::cout << "Passed " << me << std::endl;
+    else
+      std::cout << "FAILED " << me << ": " << bad << " wrong elements" << std::endl;
+    if (me == 0) {
+      elapsed_ms = t;
+      total_bad = static_cast<unsigned long long>(all_bad);
+    }
+  });
+  std::cout << "Elapsed (max over ranks): " << elapsed_ms << " ms | "
+            << (cfg.use_collective ? "collective" : "ring") << " " << elem_type_name(cfg.type)
+            << " host-threads P=" << P << " N=2^" << cfg.log2_elems << std::endl;
+  return total_bad == 0 ? 0 : 1;
+}
+
+int run_on_host(const Config& cfg) {
+  return cfg.type == ElemType::kFloat ? run_on_host_typed<float>(cfg) : run_on_host_typed<int>(cfg);
+}
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -260,6 +322,7 @@ int main(int argc, char** argv) {
                                        {"ctas", required_argument, nullptr, 6},
                                        {"chunk", required_argument, nullptr, 7},
                                        {"json", required_argument, nullptr, 8},
+                                       {"cpu", no_argument, nullptr, 9},
                                        {"help", no_argument, nullptr, 'h'},
                                        {nullptr, 0, nullptr, 0}};
     int opt;
@@ -283,12 +346,14 @@ int main(int argc, char** argv) {
         case 6: cfg.ctas = std::atoi(optarg); break;
         case 7: cfg.chunk_elems = static_cast<size_t>(std::atoll(optarg)); break;
         case 8: cfg.json_path = optarg; break;
+        case 9: cfg.cpu = true; break;
         default: print_help(); return 1;
       }
     }
     HPCP_REQUIRE(cfg.algo == "ring" || cfg.algo == "ring-unfused", "unknown --algo " + cfg.algo);
     HPCP_REQUIRE(cfg.log2_elems >= 4 && cfg.log2_elems <= 32, "-p must be in [4,32]");
 
+    if (cfg.cpu) return run_on_host(cfg);
     const int ndev = visible_device_count();
     if (ndev == 0) {
       std::cerr << "Error: No devices" << std::endl;

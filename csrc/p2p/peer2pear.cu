@@ -20,6 +20,7 @@
 // and receives into the same buffer, :128,142), exact device-side verification
 // (upstream: float sorted-sum, :55-63), optional size sweep 1 KiB..1 GiB.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -56,6 +57,7 @@ struct Config {
   int iters = 10;
   bool fused_triad = false;
   bool verify = true;
+  bool cpu = false;  // --cpu: host-only plumbing run (threads as ranks, memcpy as the transport)
   std::string json_path;
   CopyTuning tune;
   uint64_t timeout_ns = 20ull * 1000 * 1000 * 1000;
@@ -81,7 +83,8 @@ void usage() {
          "  --fused-triad            fused a=b+s*c + put of a (one kernel) instead of a plain copy\n"
          "  --no-verify              skip the exact receiver-side check\n"
          "  --ctas N --threads N --unroll N --vec 16|32 --blocked --stages N --stage-kb N   kernel tuning\n"
-         "  --json FILE              append one JSON row per size/direction\n";
+         "  --json FILE              append one JSON row per size/direction\n"
+         "  --cpu                    host-only plumbing run: ranks are threads, the transport is memcpy\n";
 }
 
 Config parse(int argc, char** argv) {
@@ -114,6 +117,8 @@ Config parse(int argc, char** argv) {
       c.fused_triad = true;
     } else if (a == "--no-verify") {
       c.verify = false;
+    } else if (a == "--cpu") {
+      c.cpu = true;
     } else if (a == "--json") {
       c.json_path = val();
     } else if (a == "--ctas") {
@@ -328,11 +333,88 @@ void rank_main(RankCtx& ctx, Shared& sh) {
   (void)cudaStreamDestroy(stream);
 }
 
+
+// ---------------------------------------------------------------- host-only path ----
+// Same pairing, phases, iteration/min logic, bandwidth formulas, payload and exact verification, with
+// host buffers and memcpy standing in for the NVLink transports: the program logic can be exercised on a
+// machine without a GPU.
+uint32_t host_mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+uint32_t host_pattern_word(size_t i, uint32_t seed) {
+  return host_mix32(static_cast<uint32_t>(i) * 2654435761u ^ seed);
+}
+
+int run_on_host(const Config& cfg) {
+  const int P = cfg.ranks > 0 ? cfg.ranks : 2;
+  HPCP_REQUIRE(P >= 2 && P % 2 == 0, "peer2pear: need an even number of ranks >= 2");
+  const int pairs = P / 2;
+  int rc = 0;
+  for (size_t bytes : cfg.sizes) {
+    const size_t words = bytes / 4;
+    std::vector<std::vector<uint32_t>> send(P, std::vector<uint32_t>(words)), recv(P, std::vector<uint32_t>(words));
+    double uni_ns = 0, bi_ns = 0;
+    unsigned long long mismatches = 0;
+    run_ranks(P, [&](RankCtx& ctx) {
+      const int me = ctx.rank, partner = me ^ 1;
+      const bool even = me % 2 == 0;
+      const uint32_t seed = 0x9E3779B9u * static_cast<uint32_t>(me + 1);
+      for (size_t i = 0; i < words; ++i) send[me][i] = host_pattern_word(i, seed);
+      auto phase = [&](bool sends, bool receives) {
+        double best = std::numeric_limits<double>::max();
+        for (int it = 0; it < cfg.iters; ++it) {
+          ctx.barrier();
+          const auto t0 = std::chrono::steady_clock::now();
+          if (sends) std::memcpy(recv[partner].data(), send[me].data(), bytes);  // "put" into the partner
+          ctx.barrier();                                                         // fence: all puts landed
+          (void)receives;
+          const double ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count();
+          best = std::min(best, ctx.max(ns));
+        }
+        return best;
+      };
+      auto check = [&](int from) {
+        const uint32_t s = 0x9E3779B9u * static_cast<uint32_t>(from + 1);
+        unsigned long long bad = 0;
+        for (size_t i = 0; i < words; ++i) bad += recv[me][i] != host_pattern_word(i, s);
+        return bad;
+      };
+      const double uni = phase(even, !even);
+      unsigned long long bad = (cfg.verify && !even) ? check(partner) : 0;
+      std::fill(recv[me].begin(), recv[me].end(), 0u);
+      const double bi = phase(true, true);
+      if (cfg.verify) bad += check(partner);
+      const double all_bad = ctx.sum(static_cast<double>(bad));
+      if (me == 0) {
+        uni_ns = uni;
+        bi_ns = bi;
+        mismatches = static_cast<unsigned long long>(all_bad);
+      }
+    });
+    std::string label = cfg.label;
+    if (cfg.sizes.size() > 1) label += " [" + std::to_string(bytes) + " B]";
+    std::cout << label << " Unidirectional Bandwidth: " << static_cast<double>(bytes) * pairs / uni_ns << " GB/s"
+              << std::endl;
+    std::cout << label << " Bidirectional Bandwidth: " << 2.0 * static_cast<double>(bytes) * pairs / bi_ns << " GB/s"
+              << std::endl;
+    if (mismatches != 0) {
+      std::cout << label << " VERIFICATION FAILED: " << mismatches << " wrong words" << std::endl;
+      rc = 1;
+    }
+  }
+  return rc;
+}
 }  // namespace
 
 int main(int argc, char** argv) {
   try {
     Config cfg = parse(argc, argv);
+    if (cfg.cpu) return run_on_host(cfg);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
       std::cerr << "peer2pear: no CUDA device visible" << std::endl;

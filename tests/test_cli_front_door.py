@@ -46,3 +46,24 @@ def test_native_clis_fail_cleanly_without_gpu(bin_dir, gpu_count):
     p = subprocess.run([os.path.join(bin_dir, "peer2pear"), "--transport", "carrier-pigeon"], capture_output=True,
                        text=True)
     assert p.returncode == 1 and "unknown transport" in p.stderr
+
+
+def test_native_clis_host_only_plumbing(bin_dir):
+    """--cpu: the pattern logic (pairing, ring order, verification, output lines) without a GPU."""
+    import re
+
+    p = subprocess.run([os.path.join(bin_dir, "peer2pear"), "host", "--cpu", "-n", "4", "--bytes", "65536",
+                        "--bytes", "1048576", "--iters", "3"], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert len(re.findall(r"host \[\d+ B\] Unidirectional Bandwidth: [\d.e+]+ GB/s", p.stdout)) == 2
+    assert len(re.findall(r"host \[\d+ B\] Bidirectional Bandwidth: [\d.e+]+ GB/s", p.stdout)) == 2
+    assert "VERIFICATION FAILED" not in p.stdout
+    for args, n in ((["-n", "4", "-p", "14"], 4), (["-n", "6", "-p", "10", "-a"], 6),
+                    (["-n", "2", "-p", "12", "--type", "int"], 2)):
+        p = subprocess.run([os.path.join(bin_dir, "allreduce"), "--cpu", *args], capture_output=True, text=True,
+                           timeout=120)
+        assert p.returncode == 0, p.stdout + p.stderr
+        assert p.stdout.count("Passed") == n and "Elapsed (max over ranks)" in p.stdout
+    p = subprocess.run([os.path.join(bin_dir, "allreduce.int"), "--cpu", "-n", "4", "-p", "8"], capture_output=True,
+                       text=True, timeout=60)
+    assert p.returncode == 0 and " int host-threads" in p.stdout
