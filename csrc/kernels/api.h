@@ -141,7 +141,8 @@ void launch_tc_busy(const void* operands, float* out, int ctas, uint32_t tripcou
 // c_local and/or straight into c_peer over NVLink, then publishes sync.signal_flag.  M % 128 == N % 256 ==
 // K % 64 == 0.  Returns the number of CTAs launched.
 // out_bf16: C is stored as bf16 (half the NVLink bytes) instead of fp32.
-// cluster: 0 = auto (CTA pairs sharing the B tile by TMA multicast when the shape allows), 1 = off, 2 = force.
+// cluster: 0 = auto (CTA pairs sharing the B tile by TMA multicast when the shape allows), 1 = off, 2 = force,
+// 3 = 2-SM UMMA (tcgen05.mma.cta_group::2, one 256x256 tile per CTA pair; opt-in).
 int launch_gemm_put(const void* a_bf16, const void* b_bf16, void* c_local, void* c_peer, int m, int n,
                     int k, bool out_bf16, const SyncOps& sync, int ctas, int device, cudaStream_t stream,
                     int cluster = 0);

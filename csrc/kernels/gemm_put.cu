@@ -111,6 +111,58 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                    ptx::smem_u32(bar))
                : "memory");
 }
+// ---- cta_group::2 ("2-SM UMMA") forms: a CTA pair executes ONE M=256 MMA; each CTA holds its own 128 rows
+// of A and HALF of the B tile, the tensor cores of the two SMs exchange the B halves themselves.
+// Issued by both CTAs; the transaction bytes are counted on the LEADER's barrier (same offset in CTA 0 of
+// the pair, address obtained with mapa).
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, int x, int y,
+                                                uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .b32 lb;\n\t"
+      "mapa.shared::cluster.u32 lb, %4, 0;\n\t"
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3}], [lb];\n\t}" ::"r"(ptx::smem_u32(smem_dst)),
+      "l"(map), "r"(x), "r"(y), "r"(ptx::smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          ptx::smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+// Arrive on the barrier at the same offset in CTA `cta` of the cluster.
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(ptx::smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+// Wait on a local barrier whose arrivals may come from the other CTA of the cluster.
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(ptx::smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (ok == 0);
+}
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -154,6 +206,62 @@ struct GemmDev {
   int tiles_m, tiles_n;
   SyncOps sync;
 };
+
+// Epilogue of one 128x256 accumulator (one epilogue warp = 32 accumulator rows): TMEM -> registers ->
+// padded smem transpose -> full 128-byte row segments to c_local and/or the peer.
+__device__ __forceinline__ void epilogue_store_tile(const GemmDev& g, uint32_t taddr, float* stage_buf, int m0,
+                                                    int n0, int ew, int lane) {
+  // One round moves a 128-byte row segment per accumulator row: 32 fp32 columns, or 64 bf16
+  // columns (two TMEM loads, converted before staging), so the NVLink / HBM stores below are
+  // always full 128-byte segments.
+  const int cols_per_round = g.out_bf16 ? 64 : 32;
+  const size_t elem = g.out_bf16 ? 2 : 4;
+  unsigned char* stage_row = reinterpret_cast<unsigned char*>(stage_buf) + lane * (kStageRowWords * 4);
+  for (int col = 0; col < kBN; col += cols_per_round) {
+    if (g.out_bf16) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + col + half * 32, r);
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 pk;
+          __nv_bfloat162 t;
+          t = __floats2bfloat162_rn(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+          pk.x = *reinterpret_cast<uint32_t*>(&t);
+          t = __floats2bfloat162_rn(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          pk.y = *reinterpret_cast<uint32_t*>(&t);
+          t = __floats2bfloat162_rn(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
+          pk.z = *reinterpret_cast<uint32_t*>(&t);
+          t = __floats2bfloat162_rn(__uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
+          pk.w = *reinterpret_cast<uint32_t*>(&t);
+          *reinterpret_cast<uint4*>(stage_row + half * 64 + j * 2) = pk;
+        }
+      }
+    } else {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(taddr + col, r);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<uint4*>(stage_row + j * 4) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+    }
+    __syncwarp();
+    // 8 lanes x 16 B per row, 4 rows per instruction.
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = it * 4 + (lane >> 3);
+      const int c16 = lane & 7;
+      const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(stage_buf) +
+                                                      row * (kStageRowWords * 4) + c16 * 16);
+      const size_t off = (static_cast<size_t>(m0 + ew * 32 + row) * g.n + n0 + col) * elem + c16 * 16;
+      if (g.c_peer != nullptr)
+        ptx::st_stream_v4(reinterpret_cast<uint4*>(static_cast<unsigned char*>(g.c_peer) + off), v);
+      if (g.c_local != nullptr)
+        *reinterpret_cast<uint4*>(static_cast<unsigned char*>(g.c_local) + off) = v;
+    }
+    __syncwarp();
+  }
+}
 
 // kCluster == 2: thread-block clusters of two CTAs working on vertically adjacent tiles (same n_blk).
 // Both need the same B tile, so each CTA fetches half of it (128 rows) and TMA-multicasts it into both
@@ -293,56 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kBN) + (static_cast<uint32_t>(ew * 32) << 16);
-      // One round moves a 128-byte row segment per accumulator row: 32 fp32 columns, or 64 bf16
-      // columns (two TMEM loads, converted before staging), so the NVLink / HBM stores below are
-      // always full 128-byte segments.
-      const int cols_per_round = g.out_bf16 ? 64 : 32;
-      const size_t elem = g.out_bf16 ? 2 : 4;
-      unsigned char* stage_row = reinterpret_cast<unsigned char*>(stage_buf) + lane * (kStageRowWords * 4);
-      for (int col = 0; col < kBN; col += cols_per_round) {
-        if (g.out_bf16) {
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(taddr + col + half * 32, r);
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 pk;
-              __nv_bfloat162 t;
-              t = __floats2bfloat162_rn(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
-              pk.x = *reinterpret_cast<uint32_t*>(&t);
-              t = __floats2bfloat162_rn(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-              pk.y = *reinterpret_cast<uint32_t*>(&t);
-              t = __floats2bfloat162_rn(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
-              pk.z = *reinterpret_cast<uint32_t*>(&t);
-              t = __floats2bfloat162_rn(__uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
-              pk.w = *reinterpret_cast<uint32_t*>(&t);
-              *reinterpret_cast<uint4*>(stage_row + half * 64 + j * 2) = pk;
-            }
-          }
-        } else {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(taddr + col, r);
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<uint4*>(stage_row + j * 4) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-        }
-        __syncwarp();
-        // 8 lanes x 16 B per row, 4 rows per instruction.
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int row = it * 4 + (lane >> 3);
-          const int c16 = lane & 7;
-          const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(stage_buf) +
-                                                          row * (kStageRowWords * 4) + c16 * 16);
-          const size_t off = (static_cast<size_t>(m0 + ew * 32 + row) * g.n + n0 + col) * elem + c16 * 16;
-          if (g.c_peer != nullptr)
-            ptx::st_stream_v4(reinterpret_cast<uint4*>(static_cast<unsigned char*>(g.c_peer) + off), v);
-          if (g.c_local != nullptr)
-            *reinterpret_cast<uint4*>(static_cast<unsigned char*>(g.c_local) + off) = v;
-        }
-        __syncwarp();
-      }
+      epilogue_store_tile(g, taddr, stage_buf, m0, n0, ew, lane);
       tc_fence_before();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);  // accumulator may be overwritten
     }
@@ -357,6 +416,164 @@ __global__ void __launch_bounds__(kThreads, 1)
   // A CTA of a pair must not retire while its partner can still multicast into it.
   if (kCluster > 1) cluster_sync_all();
   // Put epilogue: the last CTA publishes the arrival epoch on the peer.
+  if (g.sync.ticket != nullptr)
+    last_cta_publish(g.sync.ticket, g.sync.ticket_base + gridDim.x, g.sync.signal_flag, g.sync.signal_epoch);
+}
+
+// ---------------------------------------------------------------- 2-SM UMMA variant ----
+// The CTA pair of a cluster computes ONE 256x256 tile with tcgen05.mma.cta_group::2 (M=256, N=256, K=16):
+// CTA r owns rows [128r, 128r+128) of the tile (its A rows, its TMEM accumulator, its epilogue) and stages
+// only HALF of the B tile, so a pipeline stage is 32 KiB per CTA instead of 48 (6 stages instead of 4) and
+// each SM reads 8 instead of 12 KiB of operands from its shared memory per MMA.  Only the leader (rank 0)
+// issues MMAs and owns the pair-wide barriers:
+//   full[s]       (leader)  2 arrivals: leader's expect_tx(2 x 32 KiB) + the peer's remote arrive; the TMA
+//                           loads of BOTH CTAs complete_tx on it
+//   empty[s]      (each)    1 arrival: tcgen05.commit multicast to the pair
+//   tmem_full[a]  (each)    1 arrival: tcgen05.commit multicast to the pair
+//   tmem_empty[a] (leader)  2 x 4 arrivals: the epilogue warps of both CTAs
+constexpr int kStages2 = 6;
+constexpr uint32_t kStageBytes2 = kABytes + kBBytes / 2;  // 32 KiB per CTA
+constexpr size_t kSmemBytes2 = static_cast<size_t>(kStages2) * kStageBytes2 + kEpiWarps * kEpiWarpBytes + 1024;
+
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm_put_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                        const __grid_constant__ GemmDev g) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kStages2];
+  __shared__ __align__(8) uint64_t empty_bar[kStages2];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* epi_smem = smem + static_cast<size_t>(kStages2) * kStageBytes2;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = g.k / kBK;
+  const int crank = static_cast<int>(cluster_cta_rank());
+  const bool leader = crank == 0;
+  // Work items are 256x256 tiles = vertically adjacent pairs (2p, 2p+1) of the grouped rasterisation.
+  const int first_item = static_cast<int>(blockIdx.x) / 2;
+  const int item_stride = static_cast<int>(gridDim.x) / 2;
+  const int num_items = g.tiles_m * g.tiles_n / 2;
+
+  cluster_sync_all();  // both CTAs of the pair are resident before the pair-wide TMEM allocation
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < kStages2; ++s) {
+      ptx::mbar_init(&full_bar[s], 2);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], 2 * kEpiWarps);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {  // the same warp of both CTAs allocates collectively
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     ptx::smem_u32(&tmem_base_s)),
+                 "r"(static_cast<uint32_t>(kTmemCols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the partner's barriers and TMEM exist before anything remote touches them
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = first_item; item < num_items; item += item_stride) {
+      int m_blk, n_blk;
+      tile_coords(item * 2 + crank, g.tiles_m, g.tiles_n, &m_blk, &n_blk);
+      const int m0 = m_blk * kBM;
+      const int n0 = n_blk * kBN + crank * (kBN / 2);  // my half of the shared B tile
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);  // slot released by the pair's MMA (multicast commit)
+        if (lane == 0) {
+          unsigned char* sa = smem + static_cast<size_t>(stage) * kStageBytes2;
+          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes2);
+          tma_load_2d_2sm(sa, &map_a, kb * kBK, m0, &full_bar[stage]);
+          tma_load_2d_2sm(sa + kABytes, &map_b, kb * kBK, n0, &full_bar[stage]);
+          if (!leader) mbar_arrive_cluster(&full_bar[stage], 0);
+        }
+        __syncwarp();
+        if (++stage == kStages2) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    const uint32_t idesc = make_idesc(2 * kBM, kBN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int local_tile = 0;
+    for (int item = first_item; item < num_items; item += item_stride, ++local_tile) {
+      const int acc = local_tile & 1;
+      const uint32_t acc_phase = static_cast<uint32_t>(local_tile >> 1) & 1;
+      mbar_wait_cluster(&tmem_empty_bar[acc], acc_phase ^ 1);  // both epilogues drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kBN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait_cluster(&full_bar[stage], phase);  // both CTAs' TMA bytes landed
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = ptx::smem_u32(smem + static_cast<size_t>(stage) * kStageBytes2);
+          const uint64_t desc_a = make_smem_desc(sa);
+          const uint64_t desc_b = make_smem_desc(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint64_t adv = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+            umma_bf16_2sm(tmem_d, desc_a + adv, desc_b + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage], static_cast<uint16_t>(0x3));  // frees the slot in both CTAs
+          if (kb == num_kb - 1) umma_commit_2sm(&tmem_full_bar[acc], static_cast<uint16_t>(0x3));
+        }
+        __syncwarp();
+        if (++stage == kStages2) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int ew = warp - 4;
+    float* stage_buf = reinterpret_cast<float*>(epi_smem + static_cast<size_t>(ew) * kEpiWarpBytes);
+    int local_tile = 0;
+    for (int item = first_item; item < num_items; item += item_stride, ++local_tile) {
+      const int acc = local_tile & 1;
+      const uint32_t acc_phase = static_cast<uint32_t>(local_tile >> 1) & 1;
+      int m_blk, n_blk;
+      tile_coords(item * 2 + crank, g.tiles_m, g.tiles_n, &m_blk, &n_blk);
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kBN) + (static_cast<uint32_t>(ew * 32) << 16);
+      epilogue_store_tile(g, taddr, stage_buf, m_blk * kBM, n_blk * kBN, ew, lane);
+      tc_fence_before();
+      if (lane == 0) {  // the leader's MMA warp may overwrite this accumulator in both CTAs
+        if (leader)
+          ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        else
+          mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA may free TMEM or retire while its partner can still touch it
+  if (warp == 2)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(kTmemCols))
+                 : "memory");
   if (g.sync.ticket != nullptr)
     last_cta_publish(g.sync.ticket, g.sync.ticket_base + gridDim.x, g.sync.signal_flag, g.sync.signal_epoch);
 }
@@ -403,10 +620,11 @@ int launch_gemm_put(const void* a_bf16, const void* b_bf16, void* c_local, void*
                "gemm_put: pointers must be 16-byte aligned");
   HPCP_REQUIRE(sync.signal_flag == nullptr || sync.ticket != nullptr, "gemm_put: a signal needs a ticket counter");
   // Cluster mode needs an even number of tile rows per raster group (pairs share n_blk).
-  HPCP_REQUIRE(cluster == 0 || cluster == 1 || cluster == 2, "gemm_put: cluster must be 0 (auto), 1 or 2");
+  HPCP_REQUIRE(cluster >= 0 && cluster <= 3, "gemm_put: cluster must be 0 (auto), 1, 2 or 3 (2-SM UMMA)");
   const bool pairable = (m / kBM) % 2 == 0 && ((m / kBM) % kGroupM) % 2 == 0;
-  HPCP_REQUIRE(cluster != 2 || pairable, "gemm_put: cluster=2 needs an even number of 128-row tiles per raster group");
+  HPCP_REQUIRE(cluster < 2 || pairable, "gemm_put: cluster=2/3 needs an even number of 128-row tiles per raster group");
   const bool use_cluster = cluster != 1 && pairable;
+  const bool two_sm = cluster == 3;
   const CUtensorMap map_a = make_kmajor_map(a_bf16, m, k, kBM);
   const CUtensorMap map_b = make_kmajor_map(b_bf16, n, k, use_cluster ? kBN / 2 : kBN);
   GemmDev g{};
@@ -429,12 +647,16 @@ int launch_gemm_put(const void* a_bf16, const void* b_bf16, void* c_local, void*
     HPCP_CUDA(cudaGetLastError());
     return grid;
   }
+  HPCP_REQUIRE(!two_sm || grid >= 2, "gemm_put: cluster=3 needs at least two CTAs");
   grid &= ~1;  // whole pairs
-  HPCP_ENABLE_SMEM(gemm_put_kernel<2>, kSmemBytes);
+  if (two_sm)
+    HPCP_ENABLE_SMEM(gemm_put_2sm_kernel, kSmemBytes2);
+  else
+    HPCP_ENABLE_SMEM(gemm_put_kernel<2>, kSmemBytes);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.dynamicSmemBytes = two_sm ? kSmemBytes2 : kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -443,7 +665,10 @@ int launch_gemm_put(const void* a_bf16, const void* b_bf16, void* c_local, void*
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  HPCP_CUDA(cudaLaunchKernelEx(&cfg, gemm_put_kernel<2>, map_a, map_b, g));
+  if (two_sm)
+    HPCP_CUDA(cudaLaunchKernelEx(&cfg, gemm_put_2sm_kernel, map_a, map_b, g));
+  else
+    HPCP_CUDA(cudaLaunchKernelEx(&cfg, gemm_put_kernel<2>, map_a, map_b, g));
   return grid;
 }
 

@@ -22,7 +22,8 @@ def gemm_put(a: torch.Tensor, b: torch.Tensor, c_local: Optional[torch.Tensor] =
              sync: Optional[dict] = None, ctas: int = 0, stream: Optional[int] = None,
              out_dtype: torch.dtype = torch.float32, cluster: int = 0) -> int:
     """Launch the fused GEMM(+put).  ``out_dtype`` fp32 or bf16 (c_local / c_peer hold that type).
-    ``cluster``: 0 auto, 1 = single CTAs, 2 = CTA pairs sharing the B tile through TMA multicast.
+    ``cluster``: 0 auto, 1 = single CTAs, 2 = CTA pairs sharing the B tile through TMA multicast,
+    3 = 2-SM UMMA (``tcgen05.mma.cta_group::2``: one 256x256 tile per CTA pair; opt-in).
     Returns the number of CTAs launched (for ticket bookkeeping)."""
     if out_dtype not in (torch.float32, torch.bfloat16):
         raise TypeError("out_dtype must be float32 or bfloat16")

@@ -396,6 +396,31 @@ def test_gemm_put_signal_and_few_ctas(native, dev):
 
 
 @pytest.mark.skipif(not __import__("os").environ.get("HPCP_EXPERIMENTAL"), reason="experimental path, opt-in")
+@pytest.mark.parametrize("m,n,k", [(256, 256, 64), (256, 512, 256), (1024, 1024, 512), (2048, 2048, 1024),
+                                   (512, 768, 4096), (8192, 8192, 512)])
+def test_gemm_put_2sm_umma(native, dev, m, n, k):
+    """EXPERIMENTAL (written without GPU access, not yet run): tcgen05.mma.cta_group::2, one 256x256 tile per
+    CTA pair (`cluster=3`).  Run under `timeout`: a protocol error here is a hang, not a wrong number."""
+    from hpc_patterns_b200.ops.gemm import gemm_put, gemm_reference
+
+    torch.manual_seed(m + n + k)
+    a = (torch.randint(-4, 5, (m, k), device=dev).float() / 4).to(torch.bfloat16)
+    b = (torch.randint(-4, 5, (n, k), device=dev).float() / 4).to(torch.bfloat16)
+    c_local = torch.full((m, n), float("nan"), device=dev)
+    c_peer = torch.full((m, n), float("nan"), device=dev)
+    ctas = gemm_put(a, b, c_local, c_peer, cluster=3)
+    torch.cuda.synchronize()
+    ref = gemm_reference(a, b)
+    assert ctas >= 2 and ctas % 2 == 0
+    assert torch.equal(c_local, ref), float((c_local - ref).abs().max())
+    assert torch.equal(c_peer, c_local)
+    c_bf = torch.zeros(m, n, device=dev, dtype=torch.bfloat16)
+    gemm_put(a, b, c_bf, 0, out_dtype=torch.bfloat16, cluster=3, ctas=6)   # several tiles per pair
+    torch.cuda.synchronize()
+    assert torch.equal(c_bf, ref.to(torch.bfloat16))
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("HPCP_EXPERIMENTAL"), reason="experimental path, opt-in")
 @pytest.mark.parametrize("halo_ctas", [8, 48, 147])
 def test_triad_put_halo_split_scheduling(native, dev, halo_ctas):
     """EXPERIMENTAL: dedicated halo CTAs instead of interleaved halo/interior tiles (TMA engine)."""
