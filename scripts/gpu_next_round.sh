@@ -1,0 +1,29 @@
+#!/usr/bin/env bash
+# First 1-GPU call of the next round: validate what was written after the round-1 GPU budget ran out.
+#   1. the opt-in 2-SM UMMA GEMM (tcgen05.mma.cta_group::2) under a short timeout (a protocol error = hang)
+#   2. if it passes: time it next to the cluster-multicast kernel and cuBLAS, and take one ncu capture
+#   3. the regular GPU suite + the N=1 bench (regression check)
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+OUT=gpurun_out; mkdir -p $OUT
+export HPCP_EXPERIMENTAL=1
+if timeout 240 python -m pytest tests/test_gpu_kernels.py -k "2sm" -x -q --timeout 120 2>&1 | tail -5 | tee $OUT/next_2sm_pytest.txt | grep -q passed; then
+  timeout 300 python scripts/gemm_put_bench.py 2>/dev/null | grep '^{' | tee $OUT/next_gemm_2sm.jsonl | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in d.items() if 'tflops' in k or k in 'mnk'})"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_put_2sm -c 1 -f -o $OUT/prof_gemm_2sm \
+    python -c "
+import torch
+from hpc_patterns_b200.ops.gemm import gemm_put
+a = torch.randn(8192, 4096, device='cuda').bfloat16(); b = torch.randn(8192, 4096, device='cuda').bfloat16()
+c = torch.empty(8192, 8192, device='cuda', dtype=torch.bfloat16)
+for _ in range(3): gemm_put(a, b, c, 0, out_dtype=torch.bfloat16, cluster=3)
+torch.cuda.synchronize()" > $OUT/next_ncu.log 2>&1
+  ncu -i $OUT/prof_gemm_2sm.ncu-rep --page raw --csv > $OUT/prof_gemm_2sm.raw.csv 2>/dev/null
+else
+  echo "2-SM UMMA variant FAILED or hung: see $OUT/next_2sm_pytest.txt"
+fi
+unset HPCP_EXPERIMENTAL
+timeout 900 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -6 | tee $OUT/next_pytest.txt
+timeout 200 python bench.py --gpus 1 | tee $OUT/next_bench_n1.json | cut -c1-300
+echo "== next-round check done"
