@@ -17,6 +17,7 @@
 #include "common/cuda_check.h"
 #include "common/driver_api.h"
 #include "common/peer_mem.h"
+#include "common/signal_layout.h"
 #include "concurency/bench.hpp"
 #include "concurency/driver.hpp"
 #include "kernels/api.h"
@@ -89,15 +90,16 @@ PYBIND11_MODULE(_C, m) {
   m.doc() = "hpc-patterns-b200 native extension (sm_100a kernels + peer memory + topology)";
 
   // ------------------------------------------------------------ constants ----
-  m.attr("PAD_WORDS") = 128;
-  m.attr("PAD_BARRIER") = 0;
-  m.attr("PAD_READY") = 16;
-  m.attr("PAD_DONE") = 32;
-  m.attr("PAD_ACK") = 48;
-  m.attr("PAD_LOCAL") = 64;
-  m.attr("STATUS_OK") = 0u;
-  m.attr("STATUS_TIMEOUT") = 0x7100DEADu;
-  m.attr("STATUS_MISMATCH") = 0x0BADDA7Au;
+  m.attr("PAD_WORDS") = kPadWords;
+  m.attr("PAD_BARRIER") = kPadBarrier;
+  m.attr("PAD_READY") = kPadReady;
+  m.attr("PAD_DONE") = kPadDone;
+  m.attr("PAD_ACK") = kPadAck;
+  m.attr("PAD_LOCAL") = kPadLocal;
+  m.attr("PAD_TAIL_WORDS") = kPadTailWords;
+  m.attr("STATUS_OK") = static_cast<uint32_t>(kStatusOk);
+  m.attr("STATUS_TIMEOUT") = static_cast<uint32_t>(kStatusTimeout);
+  m.attr("STATUS_MISMATCH") = static_cast<uint32_t>(kStatusMismatch);
   m.attr("IPC_HANDLE_BYTES") = static_cast<int>(kIpcHandleBytes);
   m.attr("REFERENCE_MESSAGE_BYTES") = 1179648ull * 40 * 4;
 

@@ -7,6 +7,7 @@
 
 #include "cuda_check.h"
 #include "driver_api.h"
+#include "signal_layout.h"
 
 namespace hpcp {
 
@@ -20,10 +21,6 @@ struct DeviceGuard {
   }
   ~DeviceGuard() { (void)cudaSetDevice(prev); }
 };
-
-// Words per pad as laid out in signal.cuh (kept in sync by a static_assert there
-// would need CUDA; the value is re-declared for host-only translation units).
-constexpr size_t kHostPadWords = 128;
 
 size_t round_up(size_t v, size_t g) { return (v + g - 1) / g * g; }
 
@@ -167,7 +164,12 @@ SymmetricBuffer NodeMemory::alloc(size_t bytes, AllocKind kind, bool zero) {
   SymmetricBuffer b;
   b.bytes = bytes;
   b.kind = kind;
-  for (int r = 0; r < world(); ++r) b.ptr.push_back(alloc_bytes(bytes, kind, devices_[r], zero));
+  try {
+    for (int r = 0; r < world(); ++r) b.ptr.push_back(alloc_bytes(bytes, kind, devices_[r], zero));
+  } catch (...) {
+    free(b);  // do not leak the ranks that were already allocated
+    throw;
+  }
   return b;
 }
 
@@ -178,8 +180,8 @@ void NodeMemory::free(SymmetricBuffer& b) {
 }
 
 SymmetricBuffer NodeMemory::alloc_pads(size_t extra_words) {
-  // +32 words: status word lives at word index kHostPadWords + extra_words.
-  return alloc((kHostPadWords + extra_words + 32) * sizeof(uint32_t), AllocKind::kDevice, true);
+  // The status word lives at word index kPadWords + extra_words (first word of the tail).
+  return alloc((kPadWords + extra_words + kPadTailWords) * sizeof(uint32_t), AllocKind::kDevice, true);
 }
 
 bool NodeMemory::multicast_supported(int device) {
@@ -209,63 +211,68 @@ MulticastBuffer NodeMemory::alloc_multicast(size_t bytes) {
   MulticastBuffer mb;
   mb.bytes = bytes;
 
-  CUmulticastObjectProp mprop{};
-  mprop.numDevices = static_cast<unsigned>(world());
-  mprop.handleTypes = 0;
-  mprop.flags = 0;
-  mprop.size = bytes;
-  size_t mc_gran = 0;
-  HPCP_CU(d.cuMulticastGetGranularity(&mc_gran, &mprop, CU_MULTICAST_GRANULARITY_RECOMMENDED));
+  try {
+    CUmulticastObjectProp mprop{};
+    mprop.numDevices = static_cast<unsigned>(world());
+    mprop.handleTypes = 0;
+    mprop.flags = 0;
+    mprop.size = bytes;
+    size_t mc_gran = 0;
+    HPCP_CU(d.cuMulticastGetGranularity(&mc_gran, &mprop, CU_MULTICAST_GRANULARITY_RECOMMENDED));
 
-  CUmemAllocationProp aprop{};
-  aprop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
-  aprop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
-  aprop.location.id = devices_[0];
-  aprop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_NONE;
-  size_t mem_gran = 0;
-  HPCP_CU(d.cuMemGetAllocationGranularity(&mem_gran, &aprop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
-  const size_t gran = mc_gran > mem_gran ? mc_gran : mem_gran;
-  mb.mapped = round_up(bytes == 0 ? 1 : bytes, gran);
-  mprop.size = mb.mapped;
+    CUmemAllocationProp aprop{};
+    aprop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    aprop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    aprop.location.id = devices_[0];
+    aprop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_NONE;
+    size_t mem_gran = 0;
+    HPCP_CU(d.cuMemGetAllocationGranularity(&mem_gran, &aprop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+    const size_t gran = mc_gran > mem_gran ? mc_gran : mem_gran;
+    mb.mapped = round_up(bytes == 0 ? 1 : bytes, gran);
+    mprop.size = mb.mapped;
 
-  CUmemGenericAllocationHandle mc_handle;
-  HPCP_CU(d.cuMulticastCreate(&mc_handle, &mprop));
-  mb.mc_handle = mc_handle;
-  for (int dev : devices_) {
-    CUdevice cudev;
-    HPCP_CU(d.cuDeviceGet(&cudev, dev));
-    HPCP_CU(d.cuMulticastAddDevice(mc_handle, cudev));
+    CUmemGenericAllocationHandle mc_handle;
+    HPCP_CU(d.cuMulticastCreate(&mc_handle, &mprop));
+    mb.mc_handle = mc_handle;
+    for (int dev : devices_) {
+      CUdevice cudev;
+      HPCP_CU(d.cuDeviceGet(&cudev, dev));
+      HPCP_CU(d.cuMulticastAddDevice(mc_handle, cudev));
+    }
+
+    std::vector<CUmemAccessDesc> access;
+    for (int dev : devices_) {
+      CUmemAccessDesc a{};
+      a.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+      a.location.id = dev;
+      a.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+      access.push_back(a);
+    }
+
+    for (int r = 0; r < world(); ++r) {
+      DeviceGuard g(devices_[r]);
+      aprop.location.id = devices_[r];
+      CUmemGenericAllocationHandle mem;
+      HPCP_CU(d.cuMemCreate(&mem, mb.mapped, &aprop, 0));
+      mb.mem_handles.push_back(mem);
+      HPCP_CU(d.cuMulticastBindMem(mc_handle, 0, mem, 0, mb.mapped, 0));
+      CUdeviceptr va = 0;
+      HPCP_CU(d.cuMemAddressReserve(&va, mb.mapped, gran, 0, 0));
+      mb.uc.push_back(reinterpret_cast<void*>(va));  // recorded first: free_multicast releases it on failure
+      HPCP_CU(d.cuMemMap(va, mb.mapped, 0, mem, 0));
+      HPCP_CU(d.cuMemSetAccess(va, mb.mapped, access.data(), access.size()));
+      HPCP_CUDA(cudaMemset(reinterpret_cast<void*>(va), 0, mb.mapped));
+      HPCP_CUDA(cudaDeviceSynchronize());
+    }
+    CUdeviceptr mc_va = 0;
+    HPCP_CU(d.cuMemAddressReserve(&mc_va, mb.mapped, gran, 0, 0));
+    mb.mc = reinterpret_cast<void*>(mc_va);
+    HPCP_CU(d.cuMemMap(mc_va, mb.mapped, 0, mc_handle, 0));
+    HPCP_CU(d.cuMemSetAccess(mc_va, mb.mapped, access.data(), access.size()));
+  } catch (...) {
+    free_multicast(mb);  // unmap / release whatever was created before the failure
+    throw;
   }
-
-  std::vector<CUmemAccessDesc> access;
-  for (int dev : devices_) {
-    CUmemAccessDesc a{};
-    a.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
-    a.location.id = dev;
-    a.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
-    access.push_back(a);
-  }
-
-  for (int r = 0; r < world(); ++r) {
-    DeviceGuard g(devices_[r]);
-    aprop.location.id = devices_[r];
-    CUmemGenericAllocationHandle mem;
-    HPCP_CU(d.cuMemCreate(&mem, mb.mapped, &aprop, 0));
-    mb.mem_handles.push_back(mem);
-    HPCP_CU(d.cuMulticastBindMem(mc_handle, 0, mem, 0, mb.mapped, 0));
-    CUdeviceptr va = 0;
-    HPCP_CU(d.cuMemAddressReserve(&va, mb.mapped, gran, 0, 0));
-    HPCP_CU(d.cuMemMap(va, mb.mapped, 0, mem, 0));
-    HPCP_CU(d.cuMemSetAccess(va, mb.mapped, access.data(), access.size()));
-    mb.uc.push_back(reinterpret_cast<void*>(va));
-    HPCP_CUDA(cudaMemset(reinterpret_cast<void*>(va), 0, mb.mapped));
-    HPCP_CUDA(cudaDeviceSynchronize());
-  }
-  CUdeviceptr mc_va = 0;
-  HPCP_CU(d.cuMemAddressReserve(&mc_va, mb.mapped, gran, 0, 0));
-  HPCP_CU(d.cuMemMap(mc_va, mb.mapped, 0, mc_handle, 0));
-  HPCP_CU(d.cuMemSetAccess(mc_va, mb.mapped, access.data(), access.size()));
-  mb.mc = reinterpret_cast<void*>(mc_va);
   return mb;
 }
 

@@ -36,7 +36,7 @@ enum class AllocKind : int {
                  //     (allreduce-map-mpi-omp-offload.cpp:113-115,38)
 };
 
-AllocKind alloc_kind_from_letter(char c);  // 'D','H','S','M'
+AllocKind alloc_kind_from_letter(char c);  // 'D','H','S','M','R'
 const char* alloc_kind_name(AllocKind k);
 
 void* alloc_bytes(size_t bytes, AllocKind kind, int device, bool zero);

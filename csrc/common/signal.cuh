@@ -18,25 +18,9 @@
 #pragma once
 
 #include "ptx.cuh"
+#include "signal_layout.h"
 
 namespace hpcp {
-
-// Status codes written to the per-rank device status word.
-enum : uint32_t {
-  kStatusOk = 0,
-  kStatusTimeout = 0x7100DEAD,   // a spin-wait hit its deadline
-  kStatusMismatch = 0x0BADDA7A,  // fused verification found wrong payload
-};
-
-// Fixed pad layout (in 32-bit words).  kMaxRanks peers per section.
-constexpr int kMaxRanks = 16;
-constexpr int kPadBarrier = 0;                  // [0,16)   barrier arrival words
-constexpr int kPadReady = kPadBarrier + 16;     // [16,32)  "receive posted" words (rendezvous)
-constexpr int kPadDone = kPadReady + 16;        // [32,48)  "data landed" words
-constexpr int kPadAck = kPadDone + 16;          // [48,64)  "data consumed" words
-constexpr int kPadLocal = kPadAck + 16;         // [64,128) rank-local counters (CTA tickets)
-constexpr int kPadWords = 128;                  // fixed part; chunk flags follow
-constexpr int kPadChunkBase = kPadWords;        // per-chunk arrival words start here
 
 __device__ __forceinline__ bool epoch_reached(uint32_t seen, uint32_t want) {
   return static_cast<int32_t>(seen - want) >= 0;

@@ -36,6 +36,7 @@
 #include "../common/nvtx.h"
 #include "../common/peer_mem.h"
 #include "../common/rank_runtime.h"
+#include "../common/signal_layout.h"
 #include "../kernels/api.h"
 #include "devices.hpp"
 
@@ -43,7 +44,6 @@ namespace {
 
 using namespace hpcp;
 
-constexpr int kPadReady = 16, kPadDone = 32, kPadLocal = 64, kPadWords = 128;  // see signal.cuh
 
 struct Config {
   int ranks = 0;

@@ -35,6 +35,7 @@
 #include "../common/nvtx.h"
 #include "../common/peer_mem.h"
 #include "../common/rank_runtime.h"
+#include "../common/signal_layout.h"
 #include "../kernels/api.h"
 #include "topology_core.hpp"
 
@@ -42,9 +43,6 @@ namespace {
 
 using namespace hpcp;
 
-// signal.cuh constants re-declared for host code (kept identical; see signal.cuh).
-constexpr int kPadReady = 16, kPadDone = 32, kPadAck = 48, kPadLocal = 64, kPadWords = 128;
-constexpr uint32_t kStatusOk = 0;
 
 struct Config {
   std::string label = "Tile2Tile";

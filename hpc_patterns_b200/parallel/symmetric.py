@@ -79,7 +79,7 @@ class SignalPads:
         self.device = device
         self.rank, self.world = comm.rank, comm.world
         self.extra_words = int(extra_words)
-        words = self.C.PAD_WORDS + self.extra_words + 32
+        words = self.C.PAD_WORDS + self.extra_words + self.C.PAD_TAIL_WORDS
         self.buf = SymmetricBuffer(comm, words * 4, device, zero=True)
         self.timeout_ns = int(timeout_s * 1e9)
         self.ticket_issued = 0
