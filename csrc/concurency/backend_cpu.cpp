@@ -104,8 +104,8 @@ class CpuBackend final : public Backend {
     std::vector<HostCommand> cmds(nc);
     for (size_t i = 0; i < nc; ++i) {
       cmds[i].name = req.commands[i];
-      cmds[i].n = req.params.at("globalsize_" + req.commands[i]);
-      if (cmds[i].name == "C") cmds[i].tripcount = req.params.at("tripcount_C");
+      cmds[i].n = require_param(req, "globalsize_" + req.commands[i]);
+      if (cmds[i].name == "C") cmds[i].tripcount = require_param(req, "tripcount_C");
       cmds[i].allocate();
     }
 

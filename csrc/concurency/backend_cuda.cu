@@ -141,15 +141,15 @@ class CudaBackend final : public Backend {
       DevCommand c;
       c.name = name;
       c.device = device_;
-      c.n = req.params.at("globalsize_" + name);
+      c.n = require_param(req, "globalsize_" + name);
       if (name == "C") {
-        c.tripcount = req.params.at("tripcount_C");
+        c.tripcount = require_param(req, "tripcount_C");
         c.a = static_cast<float*>(alloc_bytes(c.n * sizeof(float), AllocKind::kDevice, device_, true));
       } else if (name == "T") {
         // n = CTAs (one 128x256 accumulator tile each); b = bf16 operands A|B; a = fp32 results.
         // HPCP_T_OUT=P puts the accumulator tiles into the PEER GPU: the tcgen05.ld epilogue stores
         // straight over NVLink, i.e. tensor-core tile compute -> P2P put in one kernel.
-        c.tripcount = req.params.at("tripcount_T");
+        c.tripcount = require_param(req, "tripcount_T");
         const char* t_out = std::getenv("HPCP_T_OUT");
         const int out_dev = (t_out != nullptr && t_out[0] == 'P' && peer_ >= 0) ? peer_ : device_;
         c.a = static_cast<float*>(alloc_bytes(c.n * tc_busy_out_elems_per_cta() * sizeof(float),

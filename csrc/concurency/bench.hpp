@@ -20,6 +20,7 @@
 #include <cstddef>
 #include <map>
 #include <memory>
+#include <stdexcept>
 #include <string>
 #include <unordered_map>
 #include <utility>
@@ -39,6 +40,14 @@ struct BenchRequest {
   int n_repetitions = 10;
   bool verbose = false;
 };
+
+// Parameter lookup with a usable error (the API is also reachable from Python with hand-made dicts).
+inline size_t require_param(const BenchRequest& req, const std::string& key) {
+  const auto it = req.params.find(key);
+  if (it == req.params.end())
+    throw std::invalid_argument("concurency bench: missing parameter '" + key + "' (commands are sanitised: M2D -> MD)");
+  return it->second;
+}
 
 struct BenchResult {
   long total_us = 0;                  // min over repetitions of the whole group

@@ -464,7 +464,7 @@ class FakeBackend final : public Backend {
     double sum = 0, mx = 0;
     for (const auto& c : req.commands) {
       const double coef = coef_.count(c) ? coef_.at(c) : 1e-3;
-      const double t = coef * static_cast<double>(req.params.at(tuned_parameter_of(c)));
+      const double t = coef * static_cast<double>(require_param(req, tuned_parameter_of(c)));
       r.per_command_us.push_back(static_cast<long>(std::llround(t)));
       sum += t;
       mx = std::max(mx, t);

@@ -27,8 +27,13 @@ def sanitize_command(token: str) -> str:
 def bench(mode: str, commands: Sequence[str], params: Dict[str, int], *, backend: str = "auto",
           enable_profiling: bool = False, n_queues: int = -1, n_repetitions: int = 10,
           verbose: bool = False) -> Tuple[int, List[int]]:
-    r = native().concurency_bench(backend, mode, [sanitize_command(c) for c in commands],
-                                  {k: int(v) for k, v in params.items()}, enable_profiling, n_queues,
+    # Parameter keys name commands too (globalsize_M2D); sanitise them like the command tokens.
+    clean = {}
+    for k, v in params.items():
+        head, sep, cmd = k.partition("_")
+        clean[head + sep + sanitize_command(cmd) if head == "globalsize" else k] = int(v)
+    r = native().concurency_bench(backend, mode, [sanitize_command(c) for c in commands], clean, enable_profiling,
+                                  n_queues,
                                   n_repetitions, verbose)
     return int(r["total_us"]), [int(x) for x in r["per_command_us"]]
 

@@ -72,3 +72,32 @@ def test_report_tables(tmp_path):
     assert "| 1.00 | 0.86 |" in text          # 770 / 770 and 770 / 900
     assert "95%" in text and "SUCCESS" in text
     assert report.measured_hbm_gbps(str(tmp_path)) == report.HBM_FALLBACK_GBPS
+
+
+def test_clock_sampler_without_a_driver_reports_no_samples():
+    from hpc_patterns_b200.utils.clocks import ClockSampler
+
+    import torch
+
+    if torch.cuda.is_available():
+        return  # covered by the GPU bench test
+    s = ClockSampler(0).start().stop()
+    assert s["samples"] == 0 and s["sm_mhz"] is None and s["reasons"] == []
+
+
+def test_python_sweep_renders_tables_with_the_cpu_backend(native):
+    """models.concurency.sweep == run_omp.sh in Python: env matrix x modes x groups -> tables."""
+    from hpc_patterns_b200.models import concurency as cc
+
+    text = cc.sweep(["nowait"], groups=[["C", "C"], ["C", "M2D"]], backend="cpu",
+                    envs=[{}, {"OMP_NUM_THREADS": "2"}],
+                    extra_args=["--repetitions", "2", "--tripcount_C", "2000", "--globalsize_C", "64",
+                                "--globalsize_default_memory", "100000"])
+    assert "OMP_NUM_THREADS=2" in text and "DEFAULT=1" in text
+    assert text.count("nowait") >= 2 and ("SUCCESS" in text or "FAILURE" in text)
+    total, per = cc.bench("serial", ["C", "M2D"], {"tripcount_C": 1000, "globalsize_C": 64,
+                                                  "globalsize_M2D": 100000}, backend="cpu", n_repetitions=2)
+    assert total > 0 and len(per) == 2
+    total, per = cc.bench("nowait", ["C", "MD"], {"tripcount_C": 1000, "globalsize_C": 64,
+                                                 "globalsize_MD": 100000}, backend="cpu", n_repetitions=2)
+    assert total > 0 and per == []
