@@ -137,8 +137,19 @@ class CudaBackend final : public Backend {
 
   std::vector<DevCommand> build(const BenchRequest& req) const {
     std::vector<DevCommand> cmds;
+    try {
+      build_into(req, cmds);
+    } catch (...) {
+      destroy(cmds);  // a failed allocation must not leak the buffers of the commands before it
+      throw;
+    }
+    return cmds;
+  }
+
+  void build_into(const BenchRequest& req, std::vector<DevCommand>& cmds) const {
     for (const auto& name : req.commands) {
-      DevCommand c;
+      cmds.emplace_back();
+      DevCommand& c = cmds.back();
       c.name = name;
       c.device = device_;
       c.n = require_param(req, "globalsize_" + name);
@@ -164,10 +175,8 @@ class CudaBackend final : public Backend {
         c.src = make_buffer(name[0], c.bytes(), &c.src_kind);
         c.dst = make_buffer(name[1], c.bytes(), &c.dst_kind);
       }
-      cmds.push_back(c);
     }
     HPCP_CUDA(cudaDeviceSynchronize());
-    return cmds;
   }
 
   void destroy(std::vector<DevCommand>& cmds) const {

@@ -235,6 +235,14 @@ void rank_main(RankCtx& ctx, Shared& sh) {
     std::cout << "Passed " << me << std::endl;
   else
     std::cout << "FAILED " << me << ": " << bad << " wrong elements" << std::endl;
+  // The map-clause variant of the reference also prints "<rank> <VC[0]>" (allreduce-map-mpi-omp-offload.cpp:161);
+  // with -R the buffer IS host memory (registered + mapped), so the host reads it in place.
+  if (cfg.kind == AllocKind::kMapped && !sh.nvls) {
+    if (cfg.type == ElemType::kInt)
+      std::cout << me << " " << static_cast<const int*>(vc)[0] << std::endl;
+    else
+      std::cout << me << " " << static_cast<const float*>(vc)[0] << std::endl;
+  }
   if (me == 0) {
     sh.best_ms = best_ms;
     sh.total_bad = static_cast<unsigned long long>(total_bad);
