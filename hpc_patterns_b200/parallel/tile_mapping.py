@@ -25,6 +25,9 @@ from typing import List, Optional, Sequence
 
 POLICIES = ("compact", "spread", "compact_plan")
 MECHANISMS = ("CVD", "SET")
+# The reference's spellings are accepted so its launch lines keep working (p2p/tile_mapping.sh:22-37):
+# ZAM (ZE_AFFINITY_MASK: the process sees only its tile) and ODS (ONEAPI_DEVICE_SELECTOR: select by id).
+MECHANISM_ALIASES = {"ZAM": "CVD", "ODS": "SET"}
 _RANK_VARS = ("LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "PALS_LOCAL_RANKID", "SLURM_LOCALID",
               "MPI_LOCALRANKID")
 
@@ -88,6 +91,7 @@ def count_devices(env=os.environ) -> int:
 def environment_for(policy: str, mechanism: str, rank: int, n_devices: int,
                     planes: Optional[Sequence[Sequence[int]]] = None) -> dict:
     """The variables the launcher exports for one rank."""
+    mechanism = MECHANISM_ALIASES.get(mechanism, mechanism)
     if mechanism not in MECHANISMS:
         raise ValueError(f"WRONG AFFINITY MECHANISM {mechanism!r}: either CVD or SET")
     dev = device_for_rank(policy, rank, n_devices, planes)
@@ -112,7 +116,7 @@ def selected_device(default: Optional[int] = None) -> int:
 def main(argv: Optional[List[str]] = None) -> int:
     argv = list(sys.argv[1:] if argv is None else argv)
     if len(argv) < 3 or argv[0] not in POLICIES:
-        print("usage: tile_mapping <compact|spread|compact_plan> <CVD|SET> cmd [args...]", file=sys.stderr)
+        print("usage: tile_mapping <compact|spread|compact_plan> <CVD|SET> cmd [args...]   (ZAM, ODS: aliases)", file=sys.stderr)
         return 2
     policy, mechanism, cmd = argv[0], argv[1], argv[2:]
     rank = local_rank()

@@ -25,8 +25,8 @@ esac
 mechanism="${1:-}"; shift || true
 export CUDA_DEVICE_ORDER=PCI_BUS_ID
 case "$mechanism" in
-  CVD) export CUDA_VISIBLE_DEVICES="$gpu"; export HPCP_DEVICE=0 ;;
-  SET) export HPCP_DEVICE="$gpu" ;;
+  CVD|ZAM) export CUDA_VISIBLE_DEVICES="$gpu"; export HPCP_DEVICE=0 ;;   # ZAM/ODS: the reference's spellings
+  SET|ODS) export HPCP_DEVICE="$gpu" ;;
   *) echo "WRONG AFFINITY MECHANISM EITHER CVD OR SET" >&2; exit 2 ;;
 esac
 exec "$@"

@@ -14,8 +14,9 @@ def test_environment_for_both_mechanisms():
     assert e == {"CUDA_DEVICE_ORDER": "PCI_BUS_ID", "CUDA_VISIBLE_DEVICES": "3", "HPCP_DEVICE": "0"}
     e = tm.environment_for("spread", "SET", 3, 8)
     assert e == {"CUDA_DEVICE_ORDER": "PCI_BUS_ID", "HPCP_DEVICE": "5"}
+    assert tm.environment_for("compact", "ZAM", 3, 8) == tm.environment_for("compact", "CVD", 3, 8)   # alias
     with pytest.raises(ValueError):
-        tm.environment_for("compact", "ZAM", 0, 8)
+        tm.environment_for("compact", "XYZ", 0, 8)
 
 
 def test_local_rank_sources():
@@ -31,6 +32,8 @@ def test_local_rank_sources():
     ("spread", "CVD", 1, "CUDA_VISIBLE_DEVICES", "4"),
     ("spread", "SET", 3, "HPCP_DEVICE", "5"),
     ("compact", "SET", 9, "HPCP_DEVICE", "1"),
+    ("compact", "ZAM", 2, "CUDA_VISIBLE_DEVICES", "2"),   # the reference's mechanism names are aliases
+    ("spread", "ODS", 3, "HPCP_DEVICE", "5"),
 ])
 def test_bash_wrapper(policy, mech, rank, var, val):
     env = dict(os.environ, LOCAL_RANK=str(rank), HPCP_NUM_DEVICES="8")
@@ -50,7 +53,7 @@ def test_bash_wrapper_compact_plan_uses_topology_binary(bin_dir):
 
 def test_bash_wrapper_rejects_bad_mechanism():
     env = dict(os.environ, LOCAL_RANK="0", HPCP_NUM_DEVICES="8")
-    p = subprocess.run([os.path.join(ROOT, "scripts", "tile_mapping.sh"), "compact", "ZAM", "true"], env=env,
+    p = subprocess.run([os.path.join(ROOT, "scripts", "tile_mapping.sh"), "compact", "XYZ", "true"], env=env,
                        capture_output=True, text=True)
     assert p.returncode != 0 and "WRONG AFFINITY MECHANISM" in p.stderr
 
