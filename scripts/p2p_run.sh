@@ -7,19 +7,25 @@ set -x
 here="$(cd "$(dirname "${BASH_SOURCE[0]}")/.." && pwd)"
 make -C "$here" -j bin/topology bin/peer2pear >/dev/null || exit 1
 cd "$here" || exit 1
-ngpu=$(nvidia-smi -L | grep -c '^GPU ')
-"$here/bin/topology" --matrix
+# HPCP_P2P_CPU=1: host-only plumbing run of the same sweep (ranks are threads, the transport is memcpy).
+if [ -n "${HPCP_P2P_CPU:-}" ]; then
+  ngpu=${HPCP_NUM_DEVICES:-4}; extra=(--cpu --bytes "${HPCP_P2P_BYTES:-1048576}" --iters 3)
+else
+  ngpu=$(nvidia-smi -L | grep -c '^GPU '); extra=()
+  "$here/bin/topology" --matrix
+fi
 
 for mode in compact spread compact_plan; do
   for transport in sendrecv put get memcpy; do
     for n in 2 "$ngpu"; do
       [ "$n" -ge 2 ] || continue
       "$here/bin/peer2pear" "peer2pear_$transport $n $mode" -n "$n" --mapping "$mode" --transport "$transport" \
-          ${HPCP_P2P_JSON:+--json "$HPCP_P2P_JSON"}
+          "${extra[@]}" ${HPCP_P2P_JSON:+--json "$HPCP_P2P_JSON"}
     done
   done
 done
 
+[ -n "${HPCP_P2P_CPU:-}" ] && exit 0
 # process-per-GPU flavour: rank -> GPU chosen by the wrapper, both mechanisms
 for mode in compact spread compact_plan; do
   for mech in CVD SET; do

@@ -67,3 +67,34 @@ def test_native_clis_host_only_plumbing(bin_dir):
     p = subprocess.run([os.path.join(bin_dir, "allreduce.int"), "--cpu", "-n", "4", "-p", "8"], capture_output=True,
                        text=True, timeout=60)
     assert p.returncode == 0 and " int host-threads" in p.stdout
+
+
+def test_openmp_sweep_script_end_to_end(bin_dir, tmp_path):
+    """scripts/run_omp.sh == the reference's run_omp.sh: env matrix x modes x groups -> log -> tables."""
+    root = os.path.dirname(bin_dir)
+    p = subprocess.run(["bash", os.path.join(root, "scripts", "run_omp.sh")], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=300, env=dict(os.environ, HPCP_OMP_ELEMS="200000"))
+    assert p.returncode == 0, p.stderr[-2000:]
+    for env in ("OMP_PROC_BIND=false", "OMP_PROC_BIND=spread OMP_PLACES=cores", "OMP_WAIT_POLICY=active"):
+        assert env in p.stdout
+    assert p.stdout.count("host_threads    nowait") == 3          # one table per environment
+    for group in ("C C", "C MD", "C DM", "MD DM", "HD DH"):
+        assert p.stdout.count("\n" + group + " ") == 3
+    logs = list(tmp_path.glob("tmp-omp-*/omp.log"))
+    assert len(logs) == 1 and logs[0].read_text().count("## ") == 30   # 3 envs x 2 modes x 5 groups
+
+
+def test_p2p_sweep_script_host_only(bin_dir):
+    """scripts/p2p_run.sh == the reference's p2p/run.sh (policy x transport x ranks); HPCP_P2P_CPU=1 runs the
+    same sweep with host threads so the script itself is testable without a GPU."""
+    import re
+
+    root = os.path.dirname(bin_dir)
+    p = subprocess.run(["bash", os.path.join(root, "scripts", "p2p_run.sh")], capture_output=True, text=True,
+                       timeout=300, env=dict(os.environ, HPCP_P2P_CPU="1", HPCP_NUM_DEVICES="4",
+                                             HPCP_P2P_BYTES="65536"))
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = re.findall(r"^peer2pear_(\w+) (\d) (\w+) (Uni|Bi)directional Bandwidth: [\d.e+-]+ GB/s$", p.stdout, re.M)
+    assert len(lines) == 3 * 4 * 2 * 2                      # policies x transports x rank counts x directions
+    assert {l[0] for l in lines} == {"sendrecv", "put", "get", "memcpy"}
+    assert {l[2] for l in lines} == {"compact", "spread", "compact_plan"}
