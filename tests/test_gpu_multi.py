@@ -69,7 +69,7 @@ def test_cli_peer2pear_fused_triad(bin_dir, engine):
 
 @needs2
 @pytest.mark.parametrize("args", [[], ["-a"], ["-a", "--coll", "twoshot"], ["--algo", "ring-unfused"],
-                                  ["--type", "int"], ["-a", "--type", "int"], ["-H", "-p", "16"], ["-S", "-p", "16"]])
+                                  ["--type", "int"], ["-a", "--type", "int"], ["-H", "-p", "16"], ["-S", "-p", "16"], ["-R", "-p", "16"]])
 def test_cli_allreduce(bin_dir, args):
     n = min(_ngpu(), 4)
     rc, out, err = _run([os.path.join(bin_dir, "allreduce"), "-n", str(n), "-p", "20", "--iters", "2"] + args)
