@@ -27,6 +27,9 @@ LIB_OBJS   := $(KERNEL_SRC:csrc/%.cu=$(BUILD)/%.o) $(COMMON_CPP:csrc/%.cpp=$(BUI
               $(CON_CPP:csrc/%.cpp=$(BUILD)/%.o) $(BUILD)/concurency/backend_cuda.o
 LIB        := $(BUILD)/libhpcp.a
 
+# Programs built straight from one source file depend on every header (cheap and never stale).
+HEADERS := $(shell find csrc -name '*.h' -o -name '*.hpp' -o -name '*.cuh')
+
 CLIS := bin/concurency bin/omp_con bin/peer2pear bin/topology bin/allreduce bin/interop_torchless \
         bin/interop_driver bin/native_selftest
 
@@ -34,52 +37,54 @@ CLIS := bin/concurency bin/omp_con bin/peer2pear bin/topology bin/allreduce bin/
 all: cli ext
 cli: $(CLIS)
 
+# -MMD: every object records the headers it includes (build/**/*.d), so editing a header rebuilds its users.
 $(BUILD)/%.o: csrc/%.cu
 	@mkdir -p $(dir $@)
-	$(NVCC) $(NVFLAGS) -c $< -o $@
+	$(NVCC) $(NVFLAGS) -MMD -MF $(@:.o=.d) -c $< -o $@
 
 $(BUILD)/%.o: csrc/%.cpp
 	@mkdir -p $(dir $@)
-	$(CXX) $(CXXFLAGS) -c $< -o $@
+	$(CXX) $(CXXFLAGS) -MMD -MP -c $< -o $@
+
+-include $(LIB_OBJS:.o=.d)
 
 $(LIB): $(LIB_OBJS)
 	ar rcs $@ $^
 
-bin/concurency: csrc/concurency/main.cpp $(LIB)
+bin/concurency: csrc/concurency/main.cpp $(LIB) $(HEADERS)
 	@mkdir -p bin
 	$(NVCC) $(NVFLAGS) $< $(LIB) -o $@ -lgomp
 
 omp_con: bin/omp_con
 bin/omp_con: csrc/concurency/main.cpp csrc/concurency/driver.cpp csrc/concurency/backend_cpu.cpp \
-             csrc/concurency/backend_nocuda.cpp
+             csrc/concurency/backend_nocuda.cpp $(HEADERS)
 	@mkdir -p bin
-	$(CXX) -O2 -std=c++17 -fopenmp -Wall -Wextra $^ -o $@
+	$(CXX) -O2 -std=c++17 -fopenmp -Wall -Wextra $(filter %.cpp,$^) -o $@
 
-bin/peer2pear: csrc/p2p/peer2pear.cu $(LIB)
+bin/peer2pear: csrc/p2p/peer2pear.cu $(LIB) $(HEADERS)
 	@mkdir -p bin
 	$(NVCC) $(NVFLAGS) $< $(LIB) -o $@ -lgomp
 
-bin/topology: csrc/p2p/topology.cpp csrc/p2p/topology_core.cpp
+bin/topology: csrc/p2p/topology.cpp csrc/p2p/topology_core.cpp $(HEADERS)
 	@mkdir -p bin
-	$(CXX) $(CXXFLAGS) -DHPCP_TOPOLOGY_WITH_CUDA $^ -o $@ -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
+	$(CXX) $(CXXFLAGS) -DHPCP_TOPOLOGY_WITH_CUDA $(filter %.cpp,$^) -o $@ -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
 
-bin/allreduce: csrc/miniapps/allreduce.cu $(LIB)
+bin/allreduce: csrc/miniapps/allreduce.cu $(LIB) $(HEADERS)
 	@mkdir -p bin
 	$(NVCC) $(NVFLAGS) $< $(LIB) -o $@ -lgomp
 	ln -sf allreduce bin/allreduce.float
 	ln -sf allreduce bin/allreduce.int
 
-bin/interop_torchless: csrc/interop/interop_runtime_streams.cu $(LIB)
+bin/interop_torchless: csrc/interop/interop_runtime_streams.cu $(LIB) $(HEADERS)
 	@mkdir -p bin
 	$(NVCC) $(NVFLAGS) $< $(LIB) -o $@ -lgomp
 
-bin/interop_driver: csrc/interop/interop_driver_runtime.cu $(LIB)
+bin/interop_driver: csrc/interop/interop_driver_runtime.cu $(LIB) $(HEADERS)
 	@mkdir -p bin
 	$(NVCC) $(NVFLAGS) $< $(LIB) -o $@ -lgomp
 
 # host-only unit tests of the native runtime (no GPU needed to run)
-bin/native_selftest: csrc/tests/native_selftest.cpp csrc/concurency/driver.cpp csrc/p2p/topology_core.cpp \
-                     $(wildcard csrc/common/*.h) csrc/miniapps/devices.hpp
+bin/native_selftest: csrc/tests/native_selftest.cpp csrc/concurency/driver.cpp csrc/p2p/topology_core.cpp $(HEADERS)
 	@mkdir -p bin
 	$(CXX) $(CXXFLAGS) csrc/tests/native_selftest.cpp csrc/concurency/driver.cpp csrc/p2p/topology_core.cpp \
 	    -o $@ -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
