@@ -11,7 +11,10 @@ rm -f cuda.log
 
 LCOMMANDS=("C C" "C M2D" "C D2M" "M2D D2M" "H2D D2H")
 EXTRA=("C D2P" "D2P P2D" "A H2D")          # new on B200: peer-GPU copies, stream-triad compute
-MODES=("out_of_order" "in_order" "host_threads" "nowait" "fused")
+MODES=(${HPCP_CUDA_MODES:-out_of_order in_order host_threads nowait fused})
+# HPCP_CUDA_ELEMS shrinks the copies (default: the reference's 1 GB); without a GPU the binary falls back to
+# its CPU backend, which only has host_threads / nowait (HPCP_CUDA_MODES="host_threads nowait").
+SIZE_ARGS=(${HPCP_CUDA_ELEMS:+--globalsize_default_memory $HPCP_CUDA_ELEMS})
 
 for envs in "HPCP_DEVICE=0" \
             "HPCP_DEVICE=0 CUDA_DEVICE_MAX_CONNECTIONS=1" \
@@ -22,7 +25,7 @@ do
     export $envs
     for mode in "${MODES[@]}"; do
         # shellcheck disable=SC2068,SC2086
-        "$here/bin/concurency" "$mode" ${LCOMMANDS[@]/#/--commands } ${EXTRA_GROUPS:+${EXTRA[@]/#/--commands }} --json cuda.jsonl
+        "$here/bin/concurency" "$mode" ${LCOMMANDS[@]/#/--commands } ${EXTRA_GROUPS:+${EXTRA[@]/#/--commands }} "${SIZE_ARGS[@]}" --json cuda.jsonl
     done
     ) |& tee -a cuda.log
 done

@@ -3,6 +3,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -98,3 +100,19 @@ def test_p2p_sweep_script_host_only(bin_dir):
     assert len(lines) == 3 * 4 * 2 * 2                      # policies x transports x rank counts x directions
     assert {l[0] for l in lines} == {"sendrecv", "put", "get", "memcpy"}
     assert {l[2] for l in lines} == {"compact", "spread", "compact_plan"}
+
+
+def test_cuda_sweep_script_with_cpu_fallback(bin_dir, tmp_path, gpu_count):
+    """scripts/run_cuda.sh == the reference's run_sycl.sh.  Without a GPU `bin/concurency` falls back to its CPU
+    backend, so the script (env matrix, logging, JSON rows, tables) is exercised here with the two host modes."""
+    if gpu_count:
+        pytest.skip("GPU present: the script is run on the device by the profiling calls")
+    root = os.path.dirname(bin_dir)
+    p = subprocess.run(["bash", os.path.join(root, "scripts", "run_cuda.sh")], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=600, env=dict(os.environ, HPCP_CUDA_ELEMS="200000",
+                                                        HPCP_CUDA_MODES="host_threads nowait"))
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert p.stdout.count("host_threads    nowait") == 4          # one table per environment of the matrix
+    assert "CUDA_DEVICE_MAX_CONNECTIONS=32" in p.stdout and "HPCP_FUSED_COPY_ENGINE=ldst" in p.stdout
+    rows = list(tmp_path.glob("tmp-cuda-*/cuda.jsonl"))
+    assert len(rows) == 1 and len(rows[0].read_text().splitlines()) == 4 * 2 * 5
