@@ -99,7 +99,7 @@ class CpuBackend final : public Backend {
     int n_queues = req.n_queues;
     // -1: one host thread per command (deferred tasks also need a team to run on).
     if (n_queues == -1) n_queues = req.mode == "serial" ? 1 : static_cast<int>(nc);
-    if (req.verbose) std::cout << "#n_queues used: " << n_queues << std::endl;
+    if (req.verbose) std::cout << "#n_host_threads used: " << n_queues << std::endl;
 
     std::vector<HostCommand> cmds(nc);
     for (size_t i = 0; i < nc; ++i) {
