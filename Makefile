@@ -33,9 +33,19 @@ HEADERS := $(shell find csrc -name '*.h' -o -name '*.hpp' -o -name '*.cuh')
 CLIS := bin/concurency bin/omp_con bin/peer2pear bin/topology bin/allreduce bin/interop_torchless \
         bin/interop_driver bin/native_selftest
 
-.PHONY: all cli ext omp_con sass sanitize test clean
+.PHONY: all cli aliases ext omp_con sass sanitize test clean
 all: cli ext
-cli: $(CLIS)
+cli: $(CLIS) aliases
+
+# Program names of the reference as links to the programs here; defaults follow the name (see each main()):
+#   <app>.<type> typed miniapps (CMakeLists.txt upstream), the three allreduce variants (allocation kind),
+#   peer2pear_i / peer2pear_w (Isend/Irecv vs -DUSE_WIN builds, p2p/run.sh:4-5), sycl_con (run_sycl.sh:6),
+#   omp_host_threads / omp_nowait (one build per mode upstream, run_omp.sh:6-7; the mode is argv[1] here).
+aliases: $(CLIS)
+	@for n in allreduce.float allreduce.int allreduce-mpi-sycl.float allreduce-mpi-sycl.int \
+	          allreduce-usm-mpi-omp-offload.float allreduce-map-mpi-omp-offload.float; do ln -sf allreduce bin/$$n; done
+	@ln -sf peer2pear bin/peer2pear_i; ln -sf peer2pear bin/peer2pear_w
+	@ln -sf concurency bin/sycl_con; ln -sf omp_con bin/omp_host_threads; ln -sf omp_con bin/omp_nowait
 
 # -MMD: every object records the headers it includes (build/**/*.d), so editing a header rebuilds its users.
 $(BUILD)/%.o: csrc/%.cu
@@ -72,8 +82,6 @@ bin/topology: csrc/p2p/topology.cpp csrc/p2p/topology_core.cpp $(HEADERS)
 bin/allreduce: csrc/miniapps/allreduce.cu $(LIB) $(HEADERS)
 	@mkdir -p bin
 	$(NVCC) $(NVFLAGS) $< $(LIB) -o $@ -lgomp
-	ln -sf allreduce bin/allreduce.float
-	ln -sf allreduce bin/allreduce.int
 
 bin/interop_torchless: csrc/interop/interop_runtime_streams.cu $(LIB) $(HEADERS)
 	@mkdir -p bin

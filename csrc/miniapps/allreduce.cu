@@ -303,7 +303,20 @@ int run_on_host_typed(const Config& cfg) {
   });
   std::cout << "Elapsed (max over ranks): " << elapsed_ms << " ms | "
             << (cfg.use_collective ? "collective" : "ring") << " " << elem_type_name(cfg.type)
-            << " host-threads P=" << P << " N=2^" << cfg.log2_elems << std::endl;
+            << " host-threads P=" << P << " N=2^" << cfg.log2_elems << " arrays=" << alloc_kind_name(cfg.kind)
+            << " (host vectors in this mode)" << std::endl;
+  if (!cfg.json_path.empty()) {  // same row shape as the GPU path; the algo name marks the plumbing run
+    if (FILE* f = std::fopen(cfg.json_path.c_str(), "a")) {
+      const size_t n = size_t{1} << cfg.log2_elems;
+      const double sent = cfg.use_collective ? 0.0 : static_cast<double>(P - 1) * n * sizeof(T);
+      std::fprintf(f,
+                   "{\"pattern\":\"allreduce\",\"algo\":\"%s\",\"type\":\"%s\",\"alloc\":\"host-vectors\","
+                   "\"ranks\":%d,\"elements\":%zu,\"ms\":%.6f,\"GBps_sent_per_rank\":%.3f,\"mismatches\":%llu}\n",
+                   cfg.use_collective ? "host-collective" : "host-ring", elem_type_name(cfg.type), P, n, elapsed_ms,
+                   elapsed_ms > 0 ? sent / (elapsed_ms * 1e6) : 0.0, total_bad);
+      std::fclose(f);
+    }
+  }
   return total_bad == 0 ? 0 : 1;
 }
 
@@ -321,6 +334,14 @@ int main(int argc, char** argv) {
       const std::string self = argv[0];
       const auto dot = self.rfind('.');
       if (dot != std::string::npos) (void)elem_type_from_name(self.substr(dot + 1), &cfg.type);
+      // Program-name personalities of the reference's three miniapps: their default allocation kinds.
+      //   allreduce-mpi-sycl.<type>             shared USM           (allreduce-mpi-sycl.cpp:104)      -> -S
+      //   allreduce-usm-mpi-omp-offload.<type>  omp_target_alloc     (allreduce-usm-mpi-omp-offload.cpp:93) -> -D
+      //   allreduce-map-mpi-omp-offload.<type>  host arrays + map clause                               -> -R
+      const std::string base = self.substr(self.find_last_of('/') + 1);
+      if (base.rfind("allreduce-mpi-sycl", 0) == 0) cfg.kind = AllocKind::kManaged;
+      if (base.rfind("allreduce-usm-", 0) == 0) cfg.kind = AllocKind::kDevice;
+      if (base.rfind("allreduce-map-", 0) == 0) cfg.kind = AllocKind::kMapped;
     }
     static const option long_opts[] = {{"type", required_argument, nullptr, 1},
                                        {"algo", required_argument, nullptr, 2},

@@ -87,6 +87,14 @@ void usage() {
 
 Config parse(int argc, char** argv) {
   Config c;
+  // Program-name personalities of the reference's two builds (p2p/run.sh:4-5): `peer2pear_i` is the two-sided
+  // Isend/Irecv build, `peer2pear_w` the one-sided -DUSE_WIN (Put + fence) build.
+  {
+    std::string self = argc > 0 ? argv[0] : "";
+    self = self.substr(self.find_last_of('/') + 1);
+    if (self == "peer2pear_i") c.transport = "sendrecv";
+    if (self == "peer2pear_w") c.transport = "put";
+  }
   bool have_label = false;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
@@ -403,6 +411,16 @@ int run_on_host(const Config& cfg) {
     if (mismatches != 0) {
       std::cout << label << " VERIFICATION FAILED: " << mismatches << " wrong words" << std::endl;
       rc = 1;
+    }
+    if (!cfg.json_path.empty()) {  // same row shape as the GPU path; engine "host" marks the plumbing run
+      std::ofstream f(cfg.json_path, std::ios::app);
+      const double uni_bw = static_cast<double>(bytes) * pairs / uni_ns;
+      f << "{\"pattern\":\"peer2pear\",\"label\":\"" << cfg.label << "\",\"transport\":\"" << cfg.transport
+        << "\",\"engine\":\"host\",\"fused_triad\":false,\"mapping\":\"" << cfg.mapping << "\",\"ranks\":" << P
+        << ",\"bytes\":" << bytes << ",\"uni_us\":" << uni_ns * 1e-3 << ",\"bi_us\":" << bi_ns * 1e-3
+        << ",\"uni_GBps\":" << uni_bw << ",\"bi_GBps\":" << 2.0 * static_cast<double>(bytes) * pairs / bi_ns
+        << ",\"uni_GBps_per_pair\":" << uni_bw / pairs << ",\"frac_of_900GBps_per_dir\":" << (uni_bw / pairs) / 900.0
+        << ",\"mismatches\":" << mismatches << "}\n";
     }
   }
   return rc;

@@ -116,3 +116,36 @@ def test_cuda_sweep_script_with_cpu_fallback(bin_dir, tmp_path, gpu_count):
     assert "CUDA_DEVICE_MAX_CONNECTIONS=32" in p.stdout and "HPCP_FUSED_COPY_ENGINE=ldst" in p.stdout
     rows = list(tmp_path.glob("tmp-cuda-*/cuda.jsonl"))
     assert len(rows) == 1 and len(rows[0].read_text().splitlines()) == 4 * 2 * 5
+
+
+def test_reference_program_names_and_json_report_pipeline(bin_dir, tmp_path):
+    """The reference's program names exist as links and set the matching defaults; the JSON rows of every
+    program feed utils.report (all host-only here)."""
+    rows = tmp_path / "rows.jsonl"
+
+    def run(exe, *args):
+        p = subprocess.run([os.path.join(bin_dir, exe), *args], capture_output=True, text=True, timeout=120)
+        assert p.returncode in (0, 1), p.stdout + p.stderr
+        return p.stdout
+
+    for exe, kind, typ in (("allreduce-mpi-sycl.float", "managed", "float"), ("allreduce-mpi-sycl.int", "managed", "int"),
+                           ("allreduce-usm-mpi-omp-offload.float", "device", "float"),
+                           ("allreduce-map-mpi-omp-offload.float", "mapped-host-malloc", "float")):
+        out = run(exe, "--cpu", "-n", "2", "-p", "8", "--json", str(rows))
+        assert out.count("Passed") == 2 and f"arrays={kind}" in out and f" {typ} host-threads" in out
+    assert "arrays=pinned-host" in run("allreduce-mpi-sycl.float", "--cpu", "-n", "2", "-p", "8", "-H")   # flags still win
+    run("peer2pear_i", "two-sided", "--cpu", "-n", "2", "--bytes", "65536", "--json", str(rows))
+    run("peer2pear_w", "one-sided", "--cpu", "-n", "2", "--bytes", "65536", "--json", str(rows))
+    assert "## nowait | C C |" in run("omp_nowait", "nowait", "--tripcount_C", "1000", "--commands", "C", "C",
+                                      "--json", str(rows))
+    assert "## host_threads | C C |" in run("omp_host_threads", "host_threads", "--tripcount_C", "1000",
+                                            "--commands", "C", "C", "--json", str(rows))
+    assert "Usage:" in run("sycl_con")
+    parsed = [json.loads(l) for l in rows.read_text().splitlines()]
+    assert [r["transport"] for r in parsed if r["pattern"] == "peer2pear"] == ["sendrecv", "put"]
+    assert [r["algo"] for r in parsed if r["pattern"] == "allreduce"] == ["host-ring"] * 4
+    from hpc_patterns_b200.utils import report
+
+    text = report.render(report.load_rows([str(rows)]))
+    assert "## peer2pear" in text and "## allreduce miniapp" in text and "## concurrency bench" in text
+    assert "| two-sided | sendrecv | host |" in text and "| one-sided | put | host |" in text

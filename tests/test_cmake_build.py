@@ -21,7 +21,9 @@ def test_cmake_configure_build_and_host_ctest(tmp_path):
                          timeout=1800)
     assert bld.returncode == 0, bld.stdout[-3000:] + bld.stderr[-3000:]
     for exe in ("concurency", "omp_con", "peer2pear", "topology", "allreduce.float", "allreduce.int",
-                "interop_torchless", "interop_driver", "native_selftest"):
+                "interop_torchless", "interop_driver", "native_selftest",
+                "allreduce-mpi-sycl.float", "allreduce-map-mpi-omp-offload.float", "peer2pear_i", "peer2pear_w",
+                "sycl_con", "omp_nowait", "omp_host_threads"):          # incl. the reference's program names
         assert (tmp_path / exe).exists(), exe
     listing = subprocess.run(["ctest", "-N"], cwd=tmp_path, capture_output=True, text=True).stdout
     for case in ("allreduce.float", "allreduce.int.collective", "peer2pear.put", "peer2pear.sendrecv"):
