@@ -9,6 +9,7 @@
   report       JSONL rows -> roofline tables
   interop      torch <-> native runtime interop demos
   build        compile the native library, CLIs and the extension in-tree
+The reference's program names are accepted too: sycl_con, omp_host_threads, omp_nowait, peer2pear_i, peer2pear_w.
 """
 from __future__ import annotations
 
@@ -21,6 +22,13 @@ def main(argv=None) -> int:
         print(__doc__)
         return 0 if argv else 2
     prog, rest = argv[0], argv[1:]
+    # the reference's program names
+    if prog in ("sycl_con", "omp_con", "omp_host_threads", "omp_nowait"):
+        rest = (["--backend", "cpu"] if prog.startswith("omp_") else []) + rest
+        prog = "concurency"
+    if prog in ("peer2pear_i", "peer2pear_w"):
+        rest = ["--transport", "sendrecv" if prog.endswith("_i") else "put"] + rest
+        prog = "peer2pear"
     if prog == "concurency":
         from .models.concurency import main as m
         return m(rest)
