@@ -24,6 +24,16 @@ else
   echo "2-SM UMMA variant FAILED or hung: see $OUT/next_2sm_pytest.txt"
 fi
 unset HPCP_EXPERIMENTAL
+# ncu of the validated GEMM kernel (CTA-pair multicast variant) for comparison with the 2-SM capture
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_put_kernel -c 1 -f -o $OUT/prof_gemm_put \
+  python -c "
+import torch
+from hpc_patterns_b200.ops.gemm import gemm_put
+a = torch.randn(8192, 4096, device='cuda').bfloat16(); b = torch.randn(8192, 4096, device='cuda').bfloat16()
+c = torch.empty(8192, 8192, device='cuda', dtype=torch.bfloat16)
+for _ in range(3): gemm_put(a, b, c, 0, out_dtype=torch.bfloat16)
+torch.cuda.synchronize()" > $OUT/next_ncu_gemm.log 2>&1
+ncu -i $OUT/prof_gemm_put.ncu-rep --page raw --csv > $OUT/prof_gemm_put.raw.csv 2>/dev/null
 timeout 900 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -6 | tee $OUT/next_pytest.txt
 timeout 200 python bench.py --gpus 1 | tee $OUT/next_bench_n1.json | cut -c1-300
 echo "== next-round check done"
