@@ -90,7 +90,7 @@ class CpuBackend final : public Backend {
     return "cpu-serial(no OpenMP)";
 #endif
   }
-  std::vector<std::string> modes() const override { return {"host_threads", "nowait"}; }
+  std::vector<std::string> modes() const override { return {"nowait", "host_threads"}; }  // order of the reference usage line (bench_omp.cpp:12)
   std::string memory_letters() const override { return "MDHS"; }
   std::string compute_letters() const override { return "CA"; }
 

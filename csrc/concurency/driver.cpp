@@ -135,7 +135,7 @@ Options parse_arguments(const std::vector<std::string>& args, const Backend& bac
     auto modes = backend.modes();
     modes.push_back("serial");
     if (std::find(modes.begin(), modes.end(), opt.mode) == modes.end())
-      throw UsageError("Need to specify: " + join(modes, " | "));
+      throw UsageError("Need to specify: (" + join(modes, " | ") + ")");
   }
 
   const std::string mem_letters = backend.memory_letters();

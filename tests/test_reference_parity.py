@@ -78,6 +78,12 @@ def test_usage_and_exit_status_match(ref_bins, bin_dir):
     assert ref.returncode == ours.returncode == 1
     for flag in ("--commands", "--repetitions", "--min_bandwidth", "--queues", "--enable_profiling"):
         assert flag in ref.stdout and flag in ours.stdout
+    for bad in (["bogus_mode", "--commands", "C", "C"], ["nowait", "--bogus"], ["nowait", "--commands", "C", "X"]):
+        r = subprocess.run([ref_bins["nowait"]] + bad, capture_output=True, text=True)
+        o = subprocess.run([os.path.join(bin_dir, "omp_con")] + bad, capture_output=True, text=True)
+        assert r.returncode == o.returncode == 1
+        assert r.stdout.splitlines()[0] == o.stdout.splitlines()[0]          # same ERROR line, then the usage text
+        assert r.stdout.splitlines()[0].startswith("ERROR: ")
     bad_ref = subprocess.run([ref_bins["nowait"], "nowait", "--commands", "C", "H2M"], capture_output=True, text=True)
     bad_ours = subprocess.run([os.path.join(bin_dir, "omp_con"), "nowait", "--commands", "C", "H2M"],
                               capture_output=True, text=True)
