@@ -26,6 +26,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 
@@ -150,18 +151,32 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
       "r"(cta)
       : "memory");
 }
-// Wait on a local barrier whose arrivals may come from the other CTA of the cluster.
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(ptx::smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (ok == 0);
+// The 2-SM kernel has not run on hardware yet: its waits are bounded so that a protocol error reports WHICH
+// barrier never completed (printf + trap -> the launch fails with an error) instead of hanging the GPU.
+enum { kWaitEmpty = 0, kWaitFull = 1, kWaitTmemEmpty = 2, kWaitTmemFull = 3 };
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity, bool cluster_scope, int what,
+                                                  int index) {
+  for (unsigned long long spins = 0;; ++spins) {
+    uint32_t ok;
+    if (cluster_scope)  // arrivals may come from the other CTA of the pair
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(ptx::smem_u32(bar)), "r"(parity)
+          : "memory");
+    else
+      ok = ptx::mbar_try_wait(bar, parity) ? 1u : 0u;
+    if (ok) return;
+    if (spins > (1ull << 26)) {  // every try_wait poll already blocks for a HW time slice: seconds in total
+      if ((threadIdx.x & 31) == 0)
+        printf("gemm_put_2sm: barrier timeout cta=%d rank=%d warp=%d what=%d index=%d parity=%u\n",
+               static_cast<int>(blockIdx.x), static_cast<int>(cluster_cta_rank()), static_cast<int>(threadIdx.x >> 5),
+               what, index, parity);
+      __trap();
+    }
+  }
 }
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -494,7 +509,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int m0 = m_blk * kBM;
       const int n0 = n_blk * kBN + crank * (kBN / 2);  // my half of the shared B tile
       for (int kb = 0; kb < num_kb; ++kb) {
-        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);  // slot released by the pair's MMA (multicast commit)
+        mbar_wait_or_trap(&empty_bar[stage], phase ^ 1, false, kWaitEmpty, stage);  // slot released by the pair's MMA
         if (lane == 0) {
           unsigned char* sa = smem + static_cast<size_t>(stage) * kStageBytes2;
           if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes2);
@@ -518,11 +533,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (int item = first_item; item < num_items; item += item_stride, ++local_tile) {
       const int acc = local_tile & 1;
       const uint32_t acc_phase = static_cast<uint32_t>(local_tile >> 1) & 1;
-      mbar_wait_cluster(&tmem_empty_bar[acc], acc_phase ^ 1);  // both epilogues drained this accumulator
+      mbar_wait_or_trap(&tmem_empty_bar[acc], acc_phase ^ 1, true, kWaitTmemEmpty, acc);  // both epilogues drained it
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kBN);
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait_cluster(&full_bar[stage], phase);  // both CTAs' TMA bytes landed
+        mbar_wait_or_trap(&full_bar[stage], phase, true, kWaitFull, stage);  // both CTAs' TMA bytes landed
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = ptx::smem_u32(smem + static_cast<size_t>(stage) * kStageBytes2);
@@ -553,7 +568,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t acc_phase = static_cast<uint32_t>(local_tile >> 1) & 1;
       int m_blk, n_blk;
       tile_coords(item * 2 + crank, g.tiles_m, g.tiles_n, &m_blk, &n_blk);
-      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      mbar_wait_or_trap(&tmem_full_bar[acc], acc_phase, false, kWaitTmemFull, acc);
       tc_fence_after();
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kBN) + (static_cast<uint32_t>(ew * 32) << 16);
       epilogue_store_tile(g, taddr, stage_buf, m_blk * kBM, n_blk * kBN, ew, lane);
