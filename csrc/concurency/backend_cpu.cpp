@@ -102,11 +102,16 @@ class CpuBackend final : public Backend {
     if (req.verbose) std::cout << "#n_host_threads used: " << n_queues << std::endl;
 
     std::vector<HostCommand> cmds(nc);
-    for (size_t i = 0; i < nc; ++i) {
-      cmds[i].name = req.commands[i];
-      cmds[i].n = require_param(req, "globalsize_" + req.commands[i]);
-      if (cmds[i].name == "C") cmds[i].tripcount = require_param(req, "tripcount_C");
-      cmds[i].allocate();
+    try {
+      for (size_t i = 0; i < nc; ++i) {
+        cmds[i].name = req.commands[i];
+        cmds[i].n = require_param(req, "globalsize_" + req.commands[i]);
+        if (cmds[i].name == "C") cmds[i].tripcount = require_param(req, "tripcount_C");
+        cmds[i].allocate();
+      }
+    } catch (...) {
+      for (auto& c : cmds) c.release();  // a failed allocation / missing parameter must not leak the earlier buffers
+      throw;
     }
 
     BenchResult res;
