@@ -22,6 +22,8 @@
 #include "api.h"
 
 #include <algorithm>
+#include <cstdlib>
+#include <initializer_list>
 #include <type_traits>
 
 #include "../common/cuda_check.h"
@@ -232,8 +234,9 @@ struct NvlsDev {
   uint32_t* status;
 };
 
-template <typename T>
-__global__ void __launch_bounds__(512) nvls_kernel(const __grid_constant__ NvlsDev a) {
+// U independent in-switch reductions in flight per thread; kMaxThreads bounds the block size (register budget).
+template <typename T, int U, int kMaxThreads>
+__global__ void __launch_bounds__(kMaxThreads) nvls_kernel(const __grid_constant__ NvlsDev a) {
   const size_t base = static_cast<size_t>(a.rank) * a.slice_vec;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   auto reduce_at = [&](size_t off) {
@@ -248,21 +251,31 @@ __global__ void __launch_bounds__(512) nvls_kernel(const __grid_constant__ NvlsD
     }
     return r;
   };
-  // Grid-stride with 4 independent in-switch reductions in flight per thread.  (A CTA-contiguous
+  // Grid-stride with U (default 4) independent in-switch reductions in flight per thread.  (A CTA-contiguous
   // 64 KiB-block variant with 8 in flight and 2 CTAs/SM was measured slower on 8xB200:
   // 0.345-0.371 ms vs 0.326 ms at 2^25 floats, no gain at 2^28 - see BASELINE.md 4.4.)
   size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  for (; i + 3 * stride < a.slice_vec; i += 4 * stride) {
-    float4 r[4];
+  for (; i + (U - 1) * stride < a.slice_vec; i += U * stride) {
+    float4 r[U];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) r[k] = reduce_at((base + i + k * stride) * 16);
+    for (int k = 0; k < U; ++k) r[k] = reduce_at((base + i + k * stride) * 16);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) ptx::multimem_st_f32x4(a.vc_mc + (base + i + k * stride) * 16, r[k]);
+    for (int k = 0; k < U; ++k) ptx::multimem_st_f32x4(a.vc_mc + (base + i + k * stride) * 16, r[k]);
   }
   for (; i < a.slice_vec; i += stride)
     ptx::multimem_st_f32x4(a.vc_mc + (base + i) * 16, reduce_at((base + i) * 16));
   grid_then_node_barrier(a.ticket, a.ticket_target, a.pads, a.rank, a.world, a.barrier_epoch,
                          a.timeout_ns, a.status);
+}
+
+// Integer environment knob restricted to a list of allowed values (anything else -> the default).
+int env_choice(const char* name, std::initializer_list<int> allowed, int fallback) {
+  const char* e = std::getenv(name);
+  if (e == nullptr) return fallback;
+  const int v = std::atoi(e);
+  for (int a : allowed)
+    if (a == v) return v;
+  return fallback;
 }
 
 int grid_for(size_t items, int threads, int cap) {
@@ -426,13 +439,32 @@ int launch_allreduce_nvls(const NvlsArgs& args, ElemType type, int ctas, int dev
   d.barrier_epoch = args.barrier_epoch;
   d.timeout_ns = args.timeout_ns;
   d.status = args.status;
+  // Tuning knobs for sweeps (defaults = the measured configuration: 4 in flight, 512 threads, one CTA per SM):
+  //   HPCP_NVLS_UNROLL=1|2|4|8   HPCP_NVLS_THREADS=256|512|1024   HPCP_NVLS_CTAS_PER_SM=k   (or --ctas / ctas>0)
+  static const int unroll = env_choice("HPCP_NVLS_UNROLL", {1, 2, 4, 8}, 4);
+  static const int threads = env_choice("HPCP_NVLS_THREADS", {256, 512, 1024}, 512);
+  static const int per_sm = env_choice("HPCP_NVLS_CTAS_PER_SM", {1, 2, 3, 4}, 1);
   const int sms = device_sm_count(device);
-  const int grid = grid_for(std::max<size_t>(d.slice_vec, 1), 512, ctas > 0 ? ctas : sms);
+  const int grid = grid_for(std::max<size_t>(d.slice_vec, 1), threads, ctas > 0 ? ctas : sms * per_sm);
   d.ticket_target = args.ticket_base + static_cast<uint32_t>(grid);
-  if (type == ElemType::kFloat)
-    nvls_kernel<float><<<grid, 512, 0, stream>>>(d);
-  else
-    nvls_kernel<int><<<grid, 512, 0, stream>>>(d);
+#define HPCP_NVLS(U, B)                                             \
+  do {                                                              \
+    if (type == ElemType::kFloat)                                   \
+      nvls_kernel<float, U, B><<<grid, threads, 0, stream>>>(d);    \
+    else                                                            \
+      nvls_kernel<int, U, B><<<grid, threads, 0, stream>>>(d);      \
+  } while (0)
+  if (threads > 512) {  // 1024-thread blocks: 64 registers per thread
+    if (unroll == 1) HPCP_NVLS(1, 1024);
+    else if (unroll == 2) HPCP_NVLS(2, 1024);
+    else HPCP_NVLS(4, 1024);
+  } else {
+    if (unroll == 1) HPCP_NVLS(1, 512);
+    else if (unroll == 2) HPCP_NVLS(2, 512);
+    else if (unroll == 8) HPCP_NVLS(8, 512);
+    else HPCP_NVLS(4, 512);
+  }
+#undef HPCP_NVLS
   HPCP_CUDA(cudaGetLastError());
   return grid;
 }
