@@ -48,6 +48,8 @@ def parse_args():
                          "R=3 balances HBM time against NVLink time like the reference's autotuner; R=1 puts all")
     ap.add_argument("--halo-ctas", type=int, default=int(os.environ.get("HPCP_BENCH_HALO_CTAS", "0")),
                     help="EXPERIMENTAL (TMA engine, compute-ratio > 1): dedicate this many CTAs to the halo tiles")
+    ap.add_argument("--l2-hint", type=int, default=int(os.environ.get("HPCP_BENCH_L2_HINT", "0")),
+                    help="EXPERIMENTAL (TMA engine): L2 evict_first policy on the streamed bulk loads / local store")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-extras", action="store_true", help="skip the unfused / stock comparison runs")
     return ap.parse_args()
@@ -92,6 +94,8 @@ def main() -> int:
         tune["stage_kb"] = args.stage_kb
     if args.halo_ctas:
         tune["halo_ctas"] = args.halo_ctas
+    if args.l2_hint:
+        tune["l2_hint"] = args.l2_hint
     ex = FusedTriadExchange(comm, device, args.bytes, s=3.0, engine=args.engine, tune=tune,
                             compute_ratio=args.compute_ratio)
     stream = torch.cuda.current_stream(device)

@@ -56,6 +56,7 @@ CopyTuning tuning_from(const py::dict& d) {
   if (d.contains("vec_bytes")) t.vec_bytes = d["vec_bytes"].cast<int>();
   if (d.contains("blocked")) t.blocked = d["blocked"].cast<int>();
   if (d.contains("halo_ctas")) t.halo_ctas = d["halo_ctas"].cast<int>();
+  if (d.contains("l2_hint")) t.l2_hint = d["l2_hint"].cast<int>();
   return t;
 }
 

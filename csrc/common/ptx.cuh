@@ -172,6 +172,25 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint3
                "r"(smem_u32(smem_src)), "r"(bytes)
                : "memory");
 }
+// Same two copies with an L2 cache-policy operand (createpolicy ... evict_first: streamed once, never re-read).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
+                                              uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_hint(void* gdst, const void* smem_src, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+               "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy)
+               : "memory");
+}
 // shared -> global with an f32 add performed at the destination ("put + accumulate").
 __device__ __forceinline__ void bulk_s2g_add_f32(void* gdst, const void* smem_src,
                                                  uint32_t bytes) {

@@ -33,6 +33,8 @@ struct CopyTuning {
   int stages = 0;    // Tma: number of smem stages; 0 -> 8
   int vec_bytes = 0; // LdSt: 16 (LDG/STG.128) or 32 (sm_100 LDG/STG.256); 0 -> 16
   int blocked = 0;   // LdSt: 1 = each CTA owns one contiguous region instead of a grid-stride
+  int l2_hint = 0;   // triad_put, TMA engine, EXPERIMENTAL: 1 = L2 evict_first policy on the bulk loads of b, c and
+                     // the local bulk store of a (streamed once); the peer store keeps the default policy
   int halo_ctas = 0; // triad_put halo mode, TMA engine, EXPERIMENTAL: > 0 dedicates that many CTAs to the
                      // halo (NVLink-bound) tiles and the rest to the interior instead of interleaving
 };

@@ -155,7 +155,8 @@ constexpr int kMathWarps = 4;
 constexpr int kTmaThreads = 32 * (1 + kMathWarps);
 
 // Dynamic smem: [stages][2][tile_bytes] (b tile, c tile) | full[stages] | computed[stages]
-template <bool kPut>
+// kHint (EXPERIMENTAL, opt-in): L2 evict_first policy on the streamed bulk loads and the local bulk store.
+template <bool kPut, bool kHint = false>
 __global__ void __launch_bounds__(kTmaThreads)
     triad_put_tma_kernel(float* __restrict__ a_local, float* __restrict__ a_peer,
                          const float* __restrict__ b, const float* __restrict__ c, float s,
@@ -218,13 +219,19 @@ __global__ void __launch_bounds__(kTmaThreads)
   const int warp = threadIdx.x >> 5;
   if (warp == 0) {
     if (threadIdx.x == 0) {
+      const uint64_t policy = kHint ? ptx::l2_policy_evict_first() : 0;
       auto issue_load = [&](size_t j) {
         const int st = static_cast<int>(j % stages);
         const uint32_t len = tile_len(j);
         unsigned char* sb = smem + st * stage_stride;
         ptx::mbar_arrive_expect_tx(&full[st], 2 * len);
-        ptx::bulk_g2s(sb, bb + tile_off(j), len, &full[st]);
-        ptx::bulk_g2s(sb + tile_bytes, cb + tile_off(j), len, &full[st]);
+        if (kHint) {
+          ptx::bulk_g2s_hint(sb, bb + tile_off(j), len, &full[st], policy);
+          ptx::bulk_g2s_hint(sb + tile_bytes, cb + tile_off(j), len, &full[st], policy);
+        } else {
+          ptx::bulk_g2s(sb, bb + tile_off(j), len, &full[st]);
+          ptx::bulk_g2s(sb + tile_bytes, cb + tile_off(j), len, &full[st]);
+        }
       };
       const size_t lookahead = static_cast<size_t>(stages - 1);
       for (size_t j = 0; j < lookahead && j < n; ++j) issue_load(j);
@@ -232,7 +239,10 @@ __global__ void __launch_bounds__(kTmaThreads)
         const int st = static_cast<int>(j % stages);
         ptx::mbar_wait(&computed[st], static_cast<uint32_t>((j / stages) & 1));
         const unsigned char* sa = smem + st * stage_stride;  // `a` overwrote the b tile
-        ptx::bulk_s2g(alb + tile_off(j), sa, tile_len(j));
+        if (kHint)
+          ptx::bulk_s2g_hint(alb + tile_off(j), sa, tile_len(j), policy);
+        else
+          ptx::bulk_s2g(alb + tile_off(j), sa, tile_len(j));
         if (kPut && tile_is_halo(j)) ptx::bulk_s2g(apb + tile_off(j), sa, tile_len(j));
         ptx::bulk_commit();
         const size_t nxt = j + lookahead;
@@ -371,7 +381,19 @@ int launch_triad_put(const TriadPutArgs& args, CopyEngine engine, const CopyTuni
     const int per_sm = std::max(1, static_cast<int>((227 * 1024) / smem));
     const int cap = tune.ctas > 0 ? tune.ctas : sms * per_sm;
     ctas = static_cast<int>(std::min<size_t>(tiles, static_cast<size_t>(cap)));
-    if (put) {
+    if (tune.l2_hint != 0) {  // experimental variant with L2 cache-policy operands
+      if (put) {
+        HPCP_ENABLE_SMEM((triad_put_tma_kernel<true, true>), smem);
+        triad_put_tma_kernel<true, true><<<ctas, kTmaThreads, smem, stream>>>(
+            args.a_local, args.a_peer, args.b, args.c, args.s, n_bytes, tile_bytes, stages, put_bytes, ratio,
+            tune.halo_ctas, sync, arrive_flag, arrive_epoch);
+      } else {
+        HPCP_ENABLE_SMEM((triad_put_tma_kernel<false, true>), smem);
+        triad_put_tma_kernel<false, true><<<ctas, kTmaThreads, smem, stream>>>(
+            args.a_local, args.a_peer, args.b, args.c, args.s, n_bytes, tile_bytes, stages, put_bytes, ratio,
+            tune.halo_ctas, sync, arrive_flag, arrive_epoch);
+      }
+    } else if (put) {
       HPCP_ENABLE_SMEM(triad_put_tma_kernel<true>, smem);
       triad_put_tma_kernel<true><<<ctas, kTmaThreads, smem, stream>>>(
           args.a_local, args.a_peer, args.b, args.c, args.s, n_bytes, tile_bytes, stages, put_bytes, ratio,

@@ -23,6 +23,13 @@ torch.cuda.synchronize()" > $OUT/next_ncu.log 2>&1
 else
   echo "2-SM UMMA variant FAILED or hung: see $OUT/next_2sm_pytest.txt"
 fi
+# L2 cache-policy variant of the flagship (opt-in): exactness, then N=1 timing next to the default
+if timeout 120 python -m pytest tests/test_gpu_kernels.py -k "l2_hint" -x -q --timeout 60 2>&1 | tail -2 | tee $OUT/next_l2hint_pytest.txt | grep -q passed; then
+  for r in 1 3; do
+    timeout 200 python bench.py --gpus 1 --compute-ratio $r --no-extras --l2-hint 1 | tee $OUT/next_bench_n1_r${r}_l2hint.json | cut -c1-200
+    timeout 200 python bench.py --gpus 1 --compute-ratio $r --no-extras | tee $OUT/next_bench_n1_r${r}_default.json | cut -c1-200
+  done
+fi
 unset HPCP_EXPERIMENTAL
 # ncu of the validated GEMM kernel (CTA-pair multicast variant) for comparison with the 2-SM capture
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_put_kernel -c 1 -f -o $OUT/prof_gemm_put \

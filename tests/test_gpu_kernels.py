@@ -421,6 +421,23 @@ def test_gemm_put_2sm_umma(native, dev, m, n, k):
 
 
 @pytest.mark.skipif(not __import__("os").environ.get("HPCP_EXPERIMENTAL"), reason="experimental path, opt-in")
+@pytest.mark.parametrize("ratio", [1, 3])
+def test_triad_put_tma_l2_hint(native, dev, ratio):
+    """EXPERIMENTAL (not yet run): L2 evict_first cache-policy operands on the TMA engine's streamed copies."""
+    n_put = (64 * 16384) // 4
+    n = n_put * ratio
+    b = torch.randn(n, device=dev)
+    c = torch.randn(n, device=dev)
+    a = torch.zeros(n, device=dev)
+    peer = torch.full((n_put + 64,), -7.0, device=dev)
+    native.triad_put(a.data_ptr(), peer.data_ptr(), b.data_ptr(), c.data_ptr(), 2.0, n, "tma",
+                     {"l2_hint": 1}, {}, 0, 0, 0, _stream(), n_put)
+    torch.cuda.synchronize()
+    assert torch.allclose(a, torch.addcmul(b, c, torch.tensor(2.0, device=dev)), rtol=1e-6, atol=1e-6)
+    assert torch.equal(peer[:n_put], a[:n_put]) and bool((peer[n_put:] == -7.0).all())
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("HPCP_EXPERIMENTAL"), reason="experimental path, opt-in")
 @pytest.mark.parametrize("halo_ctas", [8, 48, 147])
 def test_triad_put_halo_split_scheduling(native, dev, halo_ctas):
     """EXPERIMENTAL: dedicated halo CTAs instead of interleaved halo/interior tiles (TMA engine)."""
