@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <fstream>
 #include <functional>
 #include <iomanip>
@@ -445,7 +446,11 @@ class FakeBackend final : public Backend {
       const auto eq = item.find('=');
       if (eq == std::string::npos) continue;
       const std::string k = item.substr(0, eq);
-      const double v = std::stod(item.substr(eq + 1));
+      const std::string text = item.substr(eq + 1);
+      char* end = nullptr;
+      const double v = std::strtod(text.c_str(), &end);  // strtod: subnormal values are values, not errors
+      if (text.empty() || end == nullptr || *end != '\0')
+        throw std::invalid_argument("fake backend: bad number in '" + item + "' (expected name=value,...)");
       if (k == "overlap")
         overlap_ = v;
       else

@@ -76,3 +76,28 @@ def test_verdict_rule_and_monotonicity(native, max_speedup, speedup, extra):
     # the bandwidth floor dominates and only applies when bytes moved
     assert native.concurency_judge(max_speedup, speedup, 1.0, 5.0, 100).startswith("FAILURE: Minimun Bandwish")
     assert native.concurency_judge(max_speedup, speedup, 1.0, 5.0, 0) == native.concurency_judge(max_speedup, speedup, 1.0, -1.0, 0)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.floats(1e-2, 1.0), st.floats(2e-6, 2e-4), st.floats(2e-6, 2e-4), st.floats(0.0, 1.0),
+       st.sampled_from(["in_order", "out_of_order", "nowait", "fused"]))
+def test_autotune_balances_linear_commands_and_verdict_follows_overlap(native, c_coef, md_coef, dm_coef, overlap, mode):
+    """With a backend whose command times are exactly linear in the tuned parameter, the reference's autotuner
+    (main.cpp:219-258: scale every parameter by fastest-copy-time / own-time) makes all commands equally long,
+    so the theoretical speedup is the number of commands and the verdict only depends on the overlap.
+    (Times are integer microseconds like upstream's; the coefficient ranges keep the baseline runs >= 400 us so
+    that the quantisation error of the linear model stays below the 1 % tolerance.)"""
+    import re
+
+    spec = f"fake:C={c_coef},MD={md_coef},DM={dm_coef},overlap={overlap}"
+    rc, out, err = native.concurency_main([mode, "--commands", "C", "M2D", "D2M"], spec)
+    assert "# Performing Autotuning to Balance Commands Times" in out, out + err
+    times = [int(t) for t in re.findall(r"Minimum Time Command \d \( *\w+\): (\d+)us", out)]
+    assert len(times) == 3 and max(times) - min(times) <= max(2, 0.01 * max(times)), out
+    max_speedup = float(re.search(r"Maximum Theoretical Speedup: ([\d.e+-]+)x", out).group(1))
+    speedup = float(re.search(r"Speedup Relative to Serial: ([\d.e+-]+)x", out).group(1))
+    assert abs(max_speedup - 3.0) < 0.05
+    # serial = 3t, concurrent = t + (1 - overlap) * 2t
+    assert abs(speedup - 3.0 / (1.0 + 2.0 * (1.0 - overlap))) < 0.05
+    ok = "SUCCESS: Close from Theoretical Speedup" in out
+    assert ok == (not max_speedup >= 1.3 * speedup) and rc == (0 if ok else 1)
