@@ -1,0 +1,406 @@
+// UMMA building blocks shared by the tensor-core kernels of the suite (gemm_put.cu, gemm_collective.cu):
+// tile geometry, shared-memory / instruction descriptors, TMA tensor loads, tcgen05.mma / commit / ld wrappers
+// (cta_group::1 and cta_group::2 forms), the grouped tile rasterisation and the host-side tensor-map encoder.
+// Everything device-side is __forceinline__, so including this header does not change a kernel's SASS.
+#pragma once
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+
+#include <cstdio>
+#include <mutex>
+#include <string>
+
+#include "../common/cuda_check.h"
+#include "../common/ptx.cuh"
+
+namespace hpcp {
+namespace umma {
+
+constexpr int kBM = 128, kBN = 256, kBK = 64, kUmmaK = 16;
+constexpr int kThreads = 256;
+constexpr int kEpiWarps = 4;
+constexpr int kTmemCols = 512;                          // 2 accumulators x 256 columns
+constexpr uint32_t kABytes = kBM * kBK * 2;             // 16 KiB
+constexpr uint32_t kBBytes = kBN * kBK * 2;             // 32 KiB
+constexpr int kStageRowWords = 36;                      // 32 payload floats + 4 pad (keeps float4 alignment)
+constexpr uint32_t kEpiWarpBytes = 32 * kStageRowWords * 4;  // 4608 B per epilogue warp
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);  // start address
+  d |= static_cast<uint64_t>(1) << 16;                      // LBO (unused for swizzled K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;              // SBO: 8 rows x 128 B
+  d |= static_cast<uint64_t>(1) << 46;                      // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                      // SWIZZLE_128B
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);  // D=f32, A=B=bf16, K-major both
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3}], [%4];" ::"r"(ptx::smem_u32(smem_dst)),
+      "l"(map), "r"(x), "r"(y), "r"(ptx::smem_u32(bar))
+      : "memory");
+}
+// Multicast variant: the box lands at the same smem offset in every CTA of `cta_mask`, and each of
+// those CTAs' mbarrier (same offset) receives the complete_tx.
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* map, int x, int y,
+                                                      uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(ptx::smem_u32(smem_dst)),
+      "l"(map), "r"(x), "r"(y), "r"(ptx::smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+// tcgen05.commit that arrives on the barrier at this offset in every CTA of `cta_mask`.
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          ptx::smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   ptx::smem_u32(bar))
+               : "memory");
+}
+// ---- cta_group::2 ("2-SM UMMA") forms: a CTA pair executes ONE M=256 MMA; each CTA holds its own 128 rows
+// of A and HALF of the B tile, the tensor cores of the two SMs exchange the B halves themselves.
+// Issued by both CTAs; the transaction bytes are counted on the LEADER's barrier (same offset in CTA 0 of
+// the pair, address obtained with mapa).
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, int x, int y,
+                                                uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .b32 lb;\n\t"
+      "mapa.shared::cluster.u32 lb, %4, 0;\n\t"
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3}], [lb];\n\t}" ::"r"(ptx::smem_u32(smem_dst)),
+      "l"(map), "r"(x), "r"(y), "r"(ptx::smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          ptx::smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+// Arrive on the barrier at the same offset in CTA `cta` of the cluster.
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(ptx::smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+// The 2-SM kernel has not run on hardware yet: its waits are bounded so that a protocol error reports WHICH
+// barrier never completed (printf + trap -> the launch fails with an error) instead of hanging the GPU.
+enum { kWaitEmpty = 0, kWaitFull = 1, kWaitTmemEmpty = 2, kWaitTmemFull = 3 };
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity, bool cluster_scope, int what,
+                                                  int index) {
+  for (unsigned long long spins = 0;; ++spins) {
+    uint32_t ok;
+    if (cluster_scope)  // arrivals may come from the other CTA of the pair
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(ptx::smem_u32(bar)), "r"(parity)
+          : "memory");
+    else
+      ok = ptx::mbar_try_wait(bar, parity) ? 1u : 0u;
+    if (ok) return;
+    if (spins > (1ull << 26)) {  // every try_wait poll already blocks for a HW time slice: seconds in total
+      if ((threadIdx.x & 31) == 0)
+        printf("gemm_put_2sm: barrier timeout cta=%d rank=%d warp=%d what=%d index=%d parity=%u\n",
+               static_cast<int>(blockIdx.x), static_cast<int>(cluster_cta_rank()), static_cast<int>(threadIdx.x >> 5),
+               what, index, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// Tile rasterisation: groups of kGroupM tile-rows, m fastest inside a group, so the ~148 tiles that
+// are in flight at any time cover a near-square block of C (8 x ~18 tiles): fewer distinct A/B
+// panels per k-step than row-major order -> less HBM traffic once A and B exceed the 126 MB L2.
+constexpr int kGroupM = 8;
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int* m_blk, int* n_blk) {
+  const int group_size = kGroupM * tiles_n;
+  const int group = tile / group_size;
+  const int first_m = group * kGroupM;
+  const int gm = tiles_m - first_m < kGroupM ? tiles_m - first_m : kGroupM;
+  const int in_group = tile - group * group_size;
+  *m_blk = first_m + in_group % gm;
+  *n_blk = in_group / gm;
+}
+
+// ---------------------------------------------------------------- persistent GEMM main loop ----
+// The warp-specialised persistent tile loop every GEMM kernel of the suite runs (256 threads, one CTA per SM):
+//   warp 0      TMA producer  : A[128x64] + B[256x64] per stage, kStagesT-deep smem ring, full/empty mbarriers
+//   warp 1      MMA issuer    : one elected thread, tcgen05.mma.cta_group::1 (M128 N256 K16); tcgen05.commit
+//                               frees the smem stage / publishes the accumulator
+//   warp 2      TMEM allocator: 512 columns = two 128x256 fp32 accumulators (epilogue of tile i overlaps the
+//                               main loop of tile i+1)
+//   warp 3      policy.aux_warp(): idle for a plain GEMM, the gather engine of all-gather -> GEMM
+//   warps 4..7  epilogue      : policy.epilogue() per accumulator (tcgen05.ld -> stores / reductions / puts)
+// kCluster == 2: clusters of two CTAs working on vertically adjacent tiles (same n_blk).  Both need the same B
+// tile, so each CTA fetches half of it (128 rows) and TMA-multicasts it into both CTAs' shared memory:
+// L2->SM operand traffic drops from 48 to 32 KiB per CTA per k-block.  A stage may only be refilled when BOTH
+// CTAs' MMAs have consumed it: the empty barriers count 2 arrivals and every tcgen05.commit is multicast.
+//
+// What differs between the kernels is the Policy:
+//   void coords(int tile, int* m_blk, int* n_blk) const    tile index -> tile coordinates (rasterisation)
+//   void a_rows_ready(int m_blk) const                      producer warp, before the first A load of a tile
+//   void epilogue(uint32_t taddr, float* stage_buf, int m0, int n0, int ew, int lane) const
+//   void aux_warp(int lane, unsigned char* aux_smem) const  warp 3, runs concurrently with the tile loop
+//   void finish() const                                     all threads, after the loop and the TMEM release
+//   static constexpr bool kHasAuxWarp                       false: warp 3 idles (the branch is compiled out)
+// aux_smem points behind the epilogue staging buffers; its size is whatever the launcher added to
+// gemm_smem_bytes<kStagesT>(aux_bytes).
+template <int kStagesT>
+constexpr size_t gemm_smem_bytes(uint32_t aux_bytes) {
+  return static_cast<size_t>(kStagesT) * (kABytes + kBBytes) + kEpiWarps * kEpiWarpBytes + aux_bytes + 1024;
+}
+
+template <int kCluster, int kStagesT, class Policy>
+__device__ __forceinline__ void gemm_persistent(const CUtensorMap& map_a, const CUtensorMap& map_b, int tiles_m,
+                                                int tiles_n, int k, const Policy& policy) {
+  constexpr uint32_t kStageBytesT = kABytes + kBBytes;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kStagesT];
+  __shared__ __align__(8) uint64_t empty_bar[kStagesT];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* epi_smem = smem + static_cast<size_t>(kStagesT) * kStageBytesT;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = k / kBK;
+  const int crank = kCluster > 1 ? static_cast<int>(cluster_cta_rank()) : 0;
+  // Work items are tile pairs in cluster mode: pair p -> tiles 2p, 2p+1 (consecutive tiles of the
+  // grouped rasterisation share n_blk when the group height is even).
+  const int first_item = static_cast<int>(blockIdx.x) / kCluster;
+  const int item_stride = static_cast<int>(gridDim.x) / kCluster;
+  const int num_items = num_tiles / kCluster;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < kStagesT; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], kCluster);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], kEpiWarps);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     ptx::smem_u32(&tmem_base_s)),
+                 "r"(static_cast<uint32_t>(kTmemCols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (kCluster > 1) cluster_sync_all();  // the peer's barriers exist before anything remote touches them
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    // The whole warp walks the loop (convergent barriers at kernel end); lane 0 issues the TMA.
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = first_item; item < num_items; item += item_stride) {
+      const int tile = item * kCluster + crank;
+      int m_blk, n_blk;
+      policy.coords(tile, &m_blk, &n_blk);
+      const int m0 = m_blk * kBM;
+      const int n0 = n_blk * kBN;
+      policy.a_rows_ready(m_blk);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);  // slot released by the MMA warp(s)
+        if (lane == 0) {
+          unsigned char* sa = smem + static_cast<size_t>(stage) * kStageBytesT;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytesT);
+          tma_load_2d(sa, &map_a, kb * kBK, m0, &full_bar[stage]);
+          if (kCluster > 1)  // my half of the shared B tile, delivered to both CTAs of the pair
+            tma_load_2d_multicast(sa + kABytes + crank * (kBBytes / 2), &map_b, kb * kBK,
+                                  n0 + crank * (kBN / 2), &full_bar[stage], static_cast<uint16_t>(0x3));
+          else
+            tma_load_2d(sa + kABytes, &map_b, kb * kBK, n0, &full_bar[stage]);
+        }
+        __syncwarp();
+        if (++stage == kStagesT) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc(kBM, kBN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int local_tile = 0;
+    for (int item = first_item; item < num_items; item += item_stride, ++local_tile) {
+      const int acc = local_tile & 1;
+      const uint32_t acc_phase = static_cast<uint32_t>(local_tile >> 1) & 1;
+      ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kBN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);  // TMA bytes landed
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = ptx::smem_u32(smem + static_cast<size_t>(stage) * kStageBytesT);
+          const uint64_t desc_a = make_smem_desc(sa);
+          const uint64_t desc_b = make_smem_desc(sa + kABytes);
+#pragma unroll
+          for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
+            const uint64_t adv = static_cast<uint64_t>((kk * kUmmaK * 2) >> 4);
+            umma_bf16(tmem_d, desc_a + adv, desc_b + adv, idesc, (kb | kk) != 0 ? 1u : 0u);
+          }
+          if (kCluster > 1)
+            umma_commit_multicast(&empty_bar[stage], static_cast<uint16_t>(0x3));  // frees the slot in both CTAs
+          else
+            umma_commit(&empty_bar[stage]);                            // frees the smem slot
+          if (kb == num_kb - 1) umma_commit(&tmem_full_bar[acc]);      // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == kStagesT) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (Policy::kHasAuxWarp && warp == 3) {
+    policy.aux_warp(lane, epi_smem + static_cast<size_t>(kEpiWarps) * kEpiWarpBytes);
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;            // 0..3 == warp % 4 -> TMEM lane group
+    float* stage_buf = reinterpret_cast<float*>(epi_smem + static_cast<size_t>(ew) * kEpiWarpBytes);
+    int local_tile = 0;
+    for (int item = first_item; item < num_items; item += item_stride, ++local_tile) {
+      const int tile = item * kCluster + crank;
+      const int acc = local_tile & 1;
+      const uint32_t acc_phase = static_cast<uint32_t>(local_tile >> 1) & 1;
+      int m_blk, n_blk;
+      policy.coords(tile, &m_blk, &n_blk);
+      const int m0 = m_blk * kBM;
+      const int n0 = n_blk * kBN;
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kBN) + (static_cast<uint32_t>(ew * 32) << 16);
+      policy.epilogue(taddr, stage_buf, m0, n0, ew, lane);
+      tc_fence_before();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);  // accumulator may be overwritten
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(kTmemCols))
+                 : "memory");
+  // A CTA of a pair must not retire while its partner can still multicast into it.
+  if (kCluster > 1) cluster_sync_all();
+  policy.finish();
+}
+
+inline PFN_cuTensorMapEncodeTiled gemm_tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+    (void)cudaGetLastError();
+  });
+  HPCP_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available");
+  return fn;
+}
+
+// 2-D bf16 [rows, k] K-major tensor with a [box_rows x 64] SWIZZLE_128B box.
+inline CUtensorMap make_kmajor_map(const void* base, int rows, int k, int box_rows) {
+  CUtensorMap map;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(k) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t elem_strides[2] = {1, 1};
+  const CUresult r = gemm_tensor_map_encoder()(
+      &map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, elem_strides,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  HPCP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string(r));
+  return map;
+}
+
+}  // namespace umma
+}  // namespace hpcp
