@@ -349,6 +349,88 @@ PYBIND11_MODULE(_C, m) {
       py::arg("stream") = 0, py::arg("cluster") = 0,
       "tcgen05 GEMM C = A . B^T (bf16 in, fp32 out) whose epilogue stores to c_local and/or the peer-mapped c_peer.");
 
+  m.def(
+      "gemm_reduce_scatter",
+      [](uintptr_t a, uintptr_t b, const std::vector<uintptr_t>& shards, const std::vector<uintptr_t>& done_flags,
+         uint32_t done_epoch, uintptr_t ticket, uint32_t ticket_base, int rank, int m_, int n, int k, int ctas,
+         int device, uintptr_t stream, int cluster) {
+        GemmRsArgs args;
+        if (shards.empty() || shards.size() > static_cast<size_t>(kApiMaxRanks))
+          throw std::invalid_argument("gemm_reduce_scatter: 1..16 shard pointers");
+        if (!done_flags.empty() && done_flags.size() != shards.size())
+          throw std::invalid_argument("gemm_reduce_scatter: done_flags must be empty or one per rank");
+        args.a = as_ptr<const void>(a);
+        args.b = as_ptr<const void>(b);
+        args.world = static_cast<int>(shards.size());
+        for (int q = 0; q < args.world; ++q) {
+          args.shard[q] = as_ptr<float>(shards[q]);
+          args.done_flag[q] = done_flags.empty() ? nullptr : as_ptr<uint32_t>(done_flags[q]);
+        }
+        args.done_epoch = done_epoch;
+        args.ticket = as_ptr<uint32_t>(ticket);
+        args.ticket_base = ticket_base;
+        args.rank = rank;
+        args.m = m_;
+        args.n = n;
+        args.k = k;
+        return launch_gemm_reduce_scatter(args, ctas, device, as_stream(stream), cluster);
+      },
+      py::arg("a"), py::arg("b"), py::arg("shards"), py::arg("done_flags") = std::vector<uintptr_t>(),
+      py::arg("done_epoch") = 0, py::arg("ticket") = 0, py::arg("ticket_base") = 0, py::arg("rank") = 0, py::arg("m"),
+      py::arg("n"), py::arg("k"), py::arg("ctas") = 0, py::arg("device") = 0, py::arg("stream") = 0,
+      py::arg("cluster") = 0,
+      "tcgen05 GEMM whose epilogue adds every tile into the owner's fp32 shard over NVLink (GEMM -> reduce-scatter).");
+  m.def("allgather_gemm_chunks_per_block", &allgather_gemm_chunks_per_block, py::arg("k"), py::arg("chunk_bytes") = 0);
+  m.def(
+      "allgather_gemm",
+      [](uintptr_t a_full, const std::vector<uintptr_t>& a_src, uintptr_t b, uintptr_t c, bool out_bf16,
+         uintptr_t ready, uint32_t ready_base, int chunk_bytes, const std::vector<uintptr_t>& done_flags,
+         uint32_t done_epoch, uintptr_t ticket, uint32_t ticket_base, uint64_t timeout_ns, uintptr_t status, int rank,
+         int m_, int n, int k, int ctas, int device, uintptr_t stream, int cluster) {
+        AgGemmArgs args;
+        if (a_src.empty() || a_src.size() > static_cast<size_t>(kApiMaxRanks))
+          throw std::invalid_argument("allgather_gemm: 1..16 row-block pointers");
+        if (!done_flags.empty() && done_flags.size() != a_src.size())
+          throw std::invalid_argument("allgather_gemm: done_flags must be empty or one per rank");
+        args.a_full = as_ptr<void>(a_full);
+        args.world = static_cast<int>(a_src.size());
+        for (int q = 0; q < args.world; ++q) {
+          args.a_src[q] = as_ptr<const void>(a_src[q]);
+          args.done_flag[q] = done_flags.empty() ? nullptr : as_ptr<uint32_t>(done_flags[q]);
+        }
+        args.b = as_ptr<const void>(b);
+        args.c = as_ptr<void>(c);
+        args.out_bf16 = out_bf16;
+        args.ready = as_ptr<uint32_t>(ready);
+        args.ready_base = ready_base;
+        args.chunk_bytes = chunk_bytes;
+        args.done_epoch = done_epoch;
+        args.ticket = as_ptr<uint32_t>(ticket);
+        args.ticket_base = ticket_base;
+        args.timeout_ns = timeout_ns;
+        args.status = as_ptr<uint32_t>(status);
+        args.rank = rank;
+        args.m = m_;
+        args.n = n;
+        args.k = k;
+        return launch_allgather_gemm(args, ctas, device, as_stream(stream), cluster);
+      },
+      py::arg("a_full"), py::arg("a_src"), py::arg("b"), py::arg("c"), py::arg("out_bf16") = false, py::arg("ready") = 0,
+      py::arg("ready_base") = 0, py::arg("chunk_bytes") = 0, py::arg("done_flags") = std::vector<uintptr_t>(),
+      py::arg("done_epoch") = 0, py::arg("ticket") = 0, py::arg("ticket_base") = 0, py::arg("timeout_ns") = 0,
+      py::arg("status") = 0, py::arg("rank") = 0, py::arg("m"), py::arg("n"), py::arg("k"), py::arg("ctas") = 0,
+      py::arg("device") = 0, py::arg("stream") = 0, py::arg("cluster") = 0,
+      "tcgen05 GEMM over row-sharded A: one gather thread per CTA pulls the peers' rows (TMA bulk, NVLink) while "
+      "the tiles of the rows that are already here are computed (all-gather -> GEMM).");
+  m.def(
+      "wait_flags",
+      [](uintptr_t flags, int count, uint32_t epoch, uint64_t timeout_ns, uintptr_t status, uintptr_t stream) {
+        launch_wait_flags(as_ptr<const uint32_t>(flags), count, epoch, timeout_ns, as_ptr<uint32_t>(status),
+                          as_stream(stream));
+      },
+      py::arg("flags"), py::arg("count"), py::arg("epoch"), py::arg("timeout_ns") = 0, py::arg("status") = 0,
+      py::arg("stream") = 0);
+
   // ------------------------------------------------------------ allreduce ----
   m.def("init3", [](uintptr_t va, uintptr_t vb, uintptr_t vc, size_t n, double a, double b, double c,
                     const std::string& dtype, uintptr_t stream) {

@@ -40,6 +40,9 @@ __device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
 __device__ __forceinline__ void red_release_sys_add(uint32_t* p, uint32_t v) {
   asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t atom_acq_rel_gpu_add(uint32_t* p, uint32_t v) {
   uint32_t old;
   asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;"
@@ -85,6 +88,13 @@ __device__ __forceinline__ uint4 ld_weak_v4(const uint4* p) {
 __device__ __forceinline__ void st_stream_v4(uint4* p, const uint4& v) {
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
                "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+// 16-byte floating-point reduction into (peer) memory: REDG.E.ADD.F32x4, performed at the owning GPU's L2.
+__device__ __forceinline__ void red_add_f32x4_sys(float* p, const float4& v) {
+  asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
                : "memory");
 }
 

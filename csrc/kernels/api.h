@@ -149,6 +149,56 @@ int launch_gemm_put(const void* a_bf16, const void* b_bf16, void* c_local, void*
                     int k, bool out_bf16, const SyncOps& sync, int ctas, int device, cudaStream_t stream,
                     int cluster = 0);
 
+// ------------------------------------- tensor-core GEMM fused with a collective ----
+// GEMM -> reduce-scatter (tensor-parallel row-parallel layer): C_r = A_r[M,K_r] . B_r[N,K_r]^T is this rank's
+// partial sum; the epilogue ADDS every tile into the fp32 shard [M/world, N] of the rank that owns those rows
+// (red.global.add.v4.f32 over NVLink), then the last CTA publishes done_epoch on every rank's done_flag.
+// The owner zeroes its shard before the step and reads it after all `world` flags arrived (launch_wait_flags).
+// fp32 atomics: the summation order is not fixed.  M % (128*world) == N % 256 == K % 64 == 0.
+struct GemmRsArgs {
+  const void* a = nullptr;                          // bf16 [M, K_r], K-major
+  const void* b = nullptr;                          // bf16 [N, K_r], K-major
+  float* shard[kApiMaxRanks] = {nullptr};           // peer-mapped: every rank's fp32 [M/world, N]
+  uint32_t* done_flag[kApiMaxRanks] = {nullptr};    // word on rank q written by THIS rank (may be null)
+  uint32_t done_epoch = 0;
+  uint32_t* ticket = nullptr;                       // rank-local CTA ticket counter (needed iff any done_flag)
+  uint32_t ticket_base = 0;
+  int rank = 0, world = 1;
+  int m = 0, n = 0, k = 0;
+};
+int launch_gemm_reduce_scatter(const GemmRsArgs& args, int ctas, int device, cudaStream_t stream, int cluster = 0);
+
+// All-gather -> GEMM (column-parallel layer on row-sharded activations): C[M,N] = A[M,K] . B_r[N,K]^T where rank q
+// holds rows [q*M/world, (q+1)*M/world) of A.  One gather thread per CTA pulls the peers' row blocks over NVLink
+// with TMA bulk copies into a_full and counts arrivals per 128-row block in `ready`; a tile's loads wait for its
+// block, the local block needs no wait.  `ready` counts up forever: a launch adds
+// allgather_gemm_chunks_per_block(k, chunk_bytes) to the counter of every remote block, ready_base is the value
+// before the launch.  The peers' blocks must be final before the launch (barrier) and done_flag tells them when
+// this rank has finished reading.
+struct AgGemmArgs {
+  void* a_full = nullptr;                           // local bf16 [M, K]; this rank's rows already in place
+  const void* a_src[kApiMaxRanks] = {nullptr};      // peer-mapped: rank q's row block [M/world, K]
+  const void* b = nullptr;                          // bf16 [N, K]
+  void* c = nullptr;                                // fp32 (or bf16 when out_bf16) [M, N]
+  bool out_bf16 = false;
+  uint32_t* ready = nullptr;                        // local [M/128] arrival counters
+  uint32_t ready_base = 0;
+  int chunk_bytes = 0;                              // gather granularity; 0 -> 4096
+  uint32_t* done_flag[kApiMaxRanks] = {nullptr};
+  uint32_t done_epoch = 0;
+  uint32_t* ticket = nullptr;
+  uint32_t ticket_base = 0;
+  uint64_t timeout_ns = 0;
+  uint32_t* status = nullptr;
+  int rank = 0, world = 1;
+  int m = 0, n = 0, k = 0;
+};
+uint32_t allgather_gemm_chunks_per_block(int k, int chunk_bytes);
+int launch_allgather_gemm(const AgGemmArgs& args, int ctas, int device, cudaStream_t stream, int cluster = 0);
+// Waits until `count` (<= 32) consecutive words all reached `epoch` (the receiving side of the two kernels above).
+void launch_wait_flags(const uint32_t* flags, int count, uint32_t epoch, uint64_t timeout_ns, uint32_t* status,
+                       cudaStream_t stream);
+
 // ------------------------------------------------------ allreduce miniapp ----
 enum class ElemType : int { kFloat = 0, kInt = 1 };
 

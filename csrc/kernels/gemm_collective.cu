@@ -1,0 +1,399 @@
+// K-gemm-rs and K-ag-gemm: the two tensor-parallel "GEMM next to a collective" steps as ONE kernel each.
+//
+//   GEMM -> reduce-scatter   every rank holds a K-slice: C_r = A_r[M,K_r] . B_r[N,K_r]^T is a partial sum of the
+//   (K-gemm-rs)              whole C; rank q owns rows [q*M/P, (q+1)*M/P) of the sum.  The epilogue of a tile
+//                            does not store: it ADDS the accumulator into the owner's fp32 shard over NVLink
+//                            (red.global.add.v4.f32, 128-byte row segments), tile by tile while the tensor cores
+//                            work on the next tile.  When a rank's last tile is out it publishes its arrival
+//                            epoch on every owner.  Stock pattern: cuBLAS GEMM, then ncclReduceScatter.
+//
+//   all-gather -> GEMM       every rank holds a row block A_r[M/P,K] and needs C = A[M,K] . B_r[N,K]^T.  Warp 3
+//   (K-ag-gemm)              of every CTA (idle in a plain GEMM) is a gather engine: TMA bulk copies pull 4 KiB
+//                            pieces of the peers' row blocks over NVLink through a small smem ring into the
+//                            local gathered A and count arrivals per 128-row block; the TMA producer of a tile
+//                            waits for its block's count, so the GEMM starts on the local block at t = 0 and
+//                            the transfer of block i+1 hides behind the math of block i.  Stock pattern:
+//                            ncclAllGather, then cuBLAS GEMM.
+//
+// Both kernels are policies of the suite's persistent tcgen05 tile loop (umma.cuh: gemm_persistent — TMA ring,
+// tcgen05.mma into double-buffered TMEM accumulators, tcgen05.ld epilogue, optional CTA pairs with TMA multicast
+// of the B tile).  Nothing in the reference is GEMM-shaped; its one collective is the ring
+// allreduce (allreduce-mpi-sycl.cpp:43-67), whose fused form here is K-ring.  These two kernels are what that
+// "compute step followed by a collective" idea looks like when the compute step runs on the tensor cores.
+//
+// Tiles are walked shard by shard starting with the neighbour (rank+1 for the reduce-scatter, the local block
+// first and then rank+1, rank+2, ... for the all-gather), so at any moment the P ranks talk to P different peers
+// and every NVLink carries traffic.
+#include "api.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <string>
+
+#include "../common/cuda_check.h"
+#include "../common/signal.cuh"
+#include "umma.cuh"
+
+namespace hpcp {
+
+namespace {
+
+using namespace umma;
+
+constexpr int kStages = 4;
+// Shared memory left next to four 48 KiB GEMM stages and the epilogue staging: the gather thread's ring.
+constexpr uint32_t kGatherSmemBytes = 14 * 1024 + 512;
+constexpr int kMaxGatherBufs = 8;
+
+// ------------------------------------------------------------------ GEMM -> reduce-scatter ----
+struct RsDev {
+  float* shard[kApiMaxRanks];         // peer-mapped: owner q's fp32 [M/P, N]
+  uint32_t* done_flag[kApiMaxRanks];  // word on rank q that this rank publishes at the end (may be null)
+  uint32_t done_epoch;
+  uint32_t* ticket;
+  uint32_t ticket_base;
+  int rank, world;
+  int n, k;
+  int tiles_m, tiles_n;
+  int shard_tiles_m;  // tiles_m / world
+};
+
+// Shard-major rasterisation: P groups of (M/P x N) tiles; group i of rank r is the shard of rank (r+first+i) % P,
+// the grouped order of umma.cuh inside a shard.
+__device__ __forceinline__ void shard_coords(int tile, int rank, int world, int first, int shard_tiles_m, int tiles_n,
+                                             int* m_blk, int* n_blk) {
+  const int per_shard = shard_tiles_m * tiles_n;
+  const int i = tile / per_shard;
+  const int owner = (rank + first + i) % world;
+  int mb;
+  tile_coords(tile - i * per_shard, shard_tiles_m, tiles_n, &mb, n_blk);
+  *m_blk = owner * shard_tiles_m + mb;
+}
+
+// Last CTA of the grid publishes `epoch` on every rank's flag (all threads call it).
+__device__ __forceinline__ void last_cta_publish_all(uint32_t* ticket, uint32_t tickets_target,
+                                                     uint32_t* const* flags, int world, uint32_t epoch) {
+  const bool last = last_cta_publish(ticket, tickets_target, nullptr, 0);  // barrier + fences + ticket
+  if (threadIdx.x == 0 && last)
+    for (int q = 0; q < world; ++q)
+      if (flags[q] != nullptr) ptx::st_release_sys(flags[q], epoch);
+}
+
+struct ReduceScatterPolicy {
+  static constexpr bool kHasAuxWarp = false;
+  const RsDev& g;
+  __device__ __forceinline__ void coords(int tile, int* m_blk, int* n_blk) const {
+    shard_coords(tile, g.rank, g.world, 1, g.shard_tiles_m, g.tiles_n, m_blk, n_blk);
+  }
+  __device__ __forceinline__ void a_rows_ready(int) const {}
+  __device__ __forceinline__ void epilogue(uint32_t taddr, float* stage_buf, int m0, int n0, int ew, int lane) const {
+    const int owner = (m0 / kBM) / g.shard_tiles_m;
+    const int row0 = m0 - owner * g.shard_tiles_m * kBM + ew * 32;  // first of this warp's rows inside the shard
+    float* base = g.shard[owner] + static_cast<size_t>(row0) * g.n + n0;
+    const size_t ld = static_cast<size_t>(g.n);
+    epilogue_fp32_segments(taddr, stage_buf, lane, [&](int row, int col, const float4& v) {
+      ptx::red_add_f32x4_sys(base + row * ld + col, v);
+    });
+  }
+  __device__ __forceinline__ void aux_warp(int, unsigned char*) const {}
+  __device__ __forceinline__ void finish() const {
+    if (g.ticket != nullptr)
+      last_cta_publish_all(g.ticket, g.ticket_base + gridDim.x, g.done_flag, g.world, g.done_epoch);
+  }
+};
+
+template <int kCluster>
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm_reduce_scatter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                               const __grid_constant__ RsDev g) {
+  gemm_persistent<kCluster, kStages>(map_a, map_b, g.tiles_m, g.tiles_n, g.k, ReduceScatterPolicy{g});
+}
+
+// ------------------------------------------------------------------ all-gather -> GEMM ----
+struct AgDev {
+  unsigned char* a_full;                      // local bf16 [M, K]
+  const unsigned char* a_src[kApiMaxRanks];   // peer-mapped: rank q's row block [M/P, K]
+  void* c_local;                              // fp32 or bf16 [M, N]
+  void* c_peer;                               // unused (kept for the shared epilogue): always null
+  int out_bf16;
+  uint32_t* ready;                            // local [M/128] arrival counters (monotonic)
+  uint32_t ready_target;                      // value a peer block's counter reaches when it is complete
+  uint32_t chunk_bytes;                       // gather granularity, divides the 128-row block size
+  uint32_t chunks_per_block;
+  int gather_bufs;                            // depth of the gather ring (2..kMaxGatherBufs)
+  uint32_t* done_flag[kApiMaxRanks];
+  uint32_t done_epoch;
+  uint32_t* ticket;
+  uint32_t ticket_base;
+  uint64_t timeout_ns;
+  uint32_t* status;
+  int rank, world;
+  int n, k;
+  int tiles_m, tiles_n;
+  int shard_tiles_m;
+};
+
+struct AllGatherPolicy {
+  static constexpr bool kHasAuxWarp = true;
+  const AgDev& g;
+  __device__ __forceinline__ void coords(int tile, int* m_blk, int* n_blk) const {
+    shard_coords(tile, g.rank, g.world, 0, g.shard_tiles_m, g.tiles_n, m_blk, n_blk);  // local block first
+  }
+  // Producer warp, before the first A load of a tile: the rows of a peer block must have landed.  The acquire
+  // pairs with the gather warps' release increments; the proxy fence orders it before this thread's TMA loads.
+  __device__ __forceinline__ void a_rows_ready(int m_blk) const {
+    if (m_blk / g.shard_tiles_m != g.rank) {
+      if ((threadIdx.x & 31) == 0) {
+        (void)wait_epoch(&g.ready[m_blk], g.ready_target, g.timeout_ns, g.status);
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
+      __syncwarp();
+    }
+  }
+  __device__ __forceinline__ void epilogue(uint32_t taddr, float* stage_buf, int m0, int n0, int ew, int lane) const {
+    epilogue_store_tile(g, taddr, stage_buf, m0, n0, ew, lane);
+  }
+  // Gather engine: one thread per CTA streams its share of the peers' row blocks, peer (rank+1) first — the
+  // order in which the tile loop needs them.  Piece c of the (P-1) * M/P * K * 2 remote bytes belongs to CTA
+  // c % gridDim.x, so the pieces of a block are spread over all SMs and the block completes as early as possible.
+  __device__ __forceinline__ void aux_warp(int lane, unsigned char* aux_smem) const {
+    if (lane == 0 && g.world > 1) gather(aux_smem);
+    __syncwarp();
+  }
+  __device__ __forceinline__ void gather(unsigned char* aux_smem) const {
+    const int bufs = g.gather_bufs;
+    uint64_t* full = reinterpret_cast<uint64_t*>(aux_smem + static_cast<size_t>(bufs) * g.chunk_bytes);
+    for (int s = 0; s < bufs; ++s) ptx::mbar_init(&full[s], 1);
+    ptx::fence_mbar_init();
+    const size_t block_bytes = static_cast<size_t>(kBM) * g.k * 2;
+    const size_t per_peer = static_cast<size_t>(g.shard_tiles_m) * g.chunks_per_block;
+    const size_t total = static_cast<size_t>(g.world - 1) * per_peer;
+    const size_t n = total > blockIdx.x ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    struct Piece {
+      const unsigned char* src;
+      unsigned char* dst;
+      uint32_t* counter;
+    };
+    auto piece = [&](size_t j) {
+      const size_t c = static_cast<size_t>(blockIdx.x) + j * gridDim.x;
+      const int i = static_cast<int>(c / per_peer);          // i-th peer after me
+      const size_t in_peer = c - i * per_peer;
+      const int peer = (g.rank + 1 + i) % g.world;
+      const size_t blk = in_peer / g.chunks_per_block;       // 128-row block inside the peer's rows
+      const size_t off = blk * block_bytes + (in_peer - blk * g.chunks_per_block) * g.chunk_bytes;
+      const size_t m_blk = static_cast<size_t>(peer) * g.shard_tiles_m + blk;
+      return Piece{g.a_src[peer] + off, g.a_full + static_cast<size_t>(peer) * g.shard_tiles_m * block_bytes + off,
+                   g.ready + m_blk};
+    };
+    auto issue_load = [&](size_t j) {
+      const int st = static_cast<int>(j % bufs);
+      ptx::mbar_arrive_expect_tx(&full[st], g.chunk_bytes);
+      ptx::bulk_g2s(aux_smem + static_cast<size_t>(st) * g.chunk_bytes, piece(j).src, g.chunk_bytes, &full[st]);
+    };
+    // Stores are retired in order: once store j-1 is complete its piece is counted and its buffer is reused.
+    auto retire = [&](size_t j) {
+      asm volatile("fence.proxy.async;" ::: "memory");
+      ptx::red_release_gpu_add(piece(j).counter, 1u);
+    };
+    const size_t lookahead = static_cast<size_t>(bufs - 1);
+    for (size_t j = 0; j < lookahead && j < n; ++j) issue_load(j);
+    for (size_t j = 0; j < n; ++j) {
+      const int st = static_cast<int>(j % bufs);
+      ptx::mbar_wait(&full[st], static_cast<uint32_t>((j / bufs) & 1));
+      ptx::bulk_s2g(piece(j).dst, aux_smem + static_cast<size_t>(st) * g.chunk_bytes, g.chunk_bytes);
+      ptx::bulk_commit();
+      if (j > 0) {
+        ptx::bulk_wait<1>();  // every store but the newest is complete (written, not just read)
+        retire(j - 1);
+      }
+      if (j + lookahead < n) issue_load(j + lookahead);  // into the buffer store j-1 has just left
+    }
+    if (n > 0) {
+      ptx::bulk_wait<0>();
+      retire(n - 1);
+    }
+  }
+  // The arrival epoch tells every peer that this rank no longer reads its row block.
+  __device__ __forceinline__ void finish() const {
+    if (g.ticket != nullptr)
+      last_cta_publish_all(g.ticket, g.ticket_base + gridDim.x, g.done_flag, g.world, g.done_epoch);
+  }
+};
+
+template <int kCluster>
+__global__ void __launch_bounds__(kThreads, 1)
+    allgather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                          const __grid_constant__ AgDev g) {
+  gemm_persistent<kCluster, kStages>(map_a, map_b, g.tiles_m, g.tiles_n, g.k, AllGatherPolicy{g});
+}
+
+// ------------------------------------------------------------------ wait for P flags ----
+__global__ void __launch_bounds__(32) wait_flags_kernel(const uint32_t* flags, int count, uint32_t epoch,
+                                                        uint64_t timeout_ns, uint32_t* status) {
+  if (static_cast<int>(threadIdx.x) < count) (void)wait_epoch(flags + threadIdx.x, epoch, timeout_ns, status);
+}
+
+// Shapes both kernels accept: whole 128x256x64 tiles, whole tiles per shard, and (for CTA pairs) an even number
+// of tile rows per raster group inside a shard.
+struct Shape {
+  int tiles_m, tiles_n, shard_tiles_m;
+  bool pairable;
+};
+Shape check_shape(const char* who, int m, int n, int k, int world) {
+  const std::string w(who);
+  HPCP_REQUIRE(world >= 1 && world <= kApiMaxRanks, w + ": world must be in [1,16]");
+  HPCP_REQUIRE(m > 0 && n > 0 && k > 0 && m % kBM == 0 && n % kBN == 0 && k % kBK == 0,
+               w + ": M, N, K must be multiples of 128, 256, 64");
+  HPCP_REQUIRE((m / kBM) % world == 0, w + ": M must be a multiple of 128 * world (whole tiles per shard)");
+  Shape s;
+  s.tiles_m = m / kBM;
+  s.tiles_n = n / kBN;
+  s.shard_tiles_m = s.tiles_m / world;
+  s.pairable = s.shard_tiles_m % 2 == 0 && (s.shard_tiles_m % kGroupM) % 2 == 0;
+  return s;
+}
+
+template <class Kernel, class Dev>
+void launch_pairs(Kernel kernel, int grid, size_t smem, cudaStream_t stream, const CUtensorMap& map_a,
+                  const CUtensorMap& map_b, const Dev& g) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  HPCP_CUDA(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, g));
+}
+
+}  // namespace
+
+void launch_wait_flags(const uint32_t* flags, int count, uint32_t epoch, uint64_t timeout_ns, uint32_t* status,
+                       cudaStream_t stream) {
+  HPCP_REQUIRE(count >= 0 && count <= 32, "wait_flags: at most 32 consecutive words");
+  if (count == 0) return;
+  wait_flags_kernel<<<1, 32, 0, stream>>>(flags, count, epoch, timeout_ns, status);
+  HPCP_CUDA(cudaGetLastError());
+}
+
+int launch_gemm_reduce_scatter(const GemmRsArgs& args, int ctas, int device, cudaStream_t stream, int cluster) {
+  const Shape s = check_shape("gemm_reduce_scatter", args.m, args.n, args.k, args.world);
+  HPCP_REQUIRE(args.rank >= 0 && args.rank < args.world, "gemm_reduce_scatter: bad rank");
+  HPCP_REQUIRE(cluster >= 0 && cluster <= 2, "gemm_reduce_scatter: cluster must be 0 (auto), 1 or 2");
+  HPCP_REQUIRE(cluster != 2 || s.pairable, "gemm_reduce_scatter: cluster=2 needs an even number of tile rows per shard");
+  HPCP_REQUIRE((reinterpret_cast<uintptr_t>(args.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(args.b) & 15) == 0,
+               "gemm_reduce_scatter: operands must be 16-byte aligned");
+  RsDev g{};
+  for (int q = 0; q < args.world; ++q) {
+    HPCP_REQUIRE(args.shard[q] != nullptr && (reinterpret_cast<uintptr_t>(args.shard[q]) & 15) == 0,
+                 "gemm_reduce_scatter: every rank's shard pointer is needed (16-byte aligned)");
+    g.shard[q] = args.shard[q];
+    g.done_flag[q] = args.done_flag[q];
+    HPCP_REQUIRE(args.done_flag[q] == nullptr || args.ticket != nullptr,
+                 "gemm_reduce_scatter: a signal needs a ticket counter");
+  }
+  g.done_epoch = args.done_epoch;
+  g.ticket = args.ticket;
+  g.ticket_base = args.ticket_base;
+  g.rank = args.rank;
+  g.world = args.world;
+  g.n = args.n;
+  g.k = args.k;
+  g.tiles_m = s.tiles_m;
+  g.tiles_n = s.tiles_n;
+  g.shard_tiles_m = s.shard_tiles_m;
+  const bool pairs = cluster != 1 && s.pairable;
+  const CUtensorMap map_a = make_kmajor_map(args.a, args.m, args.k, kBM);
+  const int tiles = s.tiles_m * s.tiles_n;
+  int grid = std::min(tiles, ctas > 0 ? ctas : device_sm_count(device));
+  constexpr size_t smem = gemm_smem_bytes<kStages>(0);
+  if (!pairs || grid < 2) {
+    const CUtensorMap map_b = make_kmajor_map(args.b, args.n, args.k, kBN);
+    HPCP_ENABLE_SMEM(gemm_reduce_scatter_kernel<1>, smem);
+    gemm_reduce_scatter_kernel<1><<<grid, kThreads, smem, stream>>>(map_a, map_b, g);
+    HPCP_CUDA(cudaGetLastError());
+    return grid;
+  }
+  grid &= ~1;
+  const CUtensorMap map_b = make_kmajor_map(args.b, args.n, args.k, kBN / 2);
+  HPCP_ENABLE_SMEM(gemm_reduce_scatter_kernel<2>, smem);
+  launch_pairs(gemm_reduce_scatter_kernel<2>, grid, smem, stream, map_a, map_b, g);
+  return grid;
+}
+
+uint32_t allgather_gemm_chunks_per_block(int k, int chunk_bytes) {
+  const int chunk = chunk_bytes > 0 ? chunk_bytes : 4096;
+  return static_cast<uint32_t>(static_cast<size_t>(kBM) * k * 2 / chunk);
+}
+
+int launch_allgather_gemm(const AgGemmArgs& args, int ctas, int device, cudaStream_t stream, int cluster) {
+  const Shape s = check_shape("allgather_gemm", args.m, args.n, args.k, args.world);
+  HPCP_REQUIRE(args.rank >= 0 && args.rank < args.world, "allgather_gemm: bad rank");
+  HPCP_REQUIRE(cluster >= 0 && cluster <= 2, "allgather_gemm: cluster must be 0 (auto), 1 or 2");
+  HPCP_REQUIRE(cluster != 2 || s.pairable, "allgather_gemm: cluster=2 needs an even number of tile rows per shard");
+  HPCP_REQUIRE(args.a_full != nullptr && args.b != nullptr && args.c != nullptr, "allgather_gemm: null operand");
+  HPCP_REQUIRE((reinterpret_cast<uintptr_t>(args.a_full) & 127) == 0 && (reinterpret_cast<uintptr_t>(args.b) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(args.c) & 15) == 0,
+               "allgather_gemm: a_full must be 128-byte aligned, b and c 16-byte aligned");
+  const int chunk = args.chunk_bytes > 0 ? args.chunk_bytes : 4096;
+  const size_t block_bytes = static_cast<size_t>(kBM) * args.k * 2;
+  HPCP_REQUIRE(chunk % 16 == 0 && chunk >= 512 && chunk <= 4096 && block_bytes % chunk == 0,
+               "allgather_gemm: chunk_bytes must be a multiple of 16 in [512, 4096] that divides 256*K");
+  HPCP_REQUIRE(args.world == 1 || args.ready != nullptr, "allgather_gemm: the arrival counters are needed");
+  AgDev g{};
+  for (int q = 0; q < args.world; ++q) {
+    HPCP_REQUIRE(q == args.rank || (args.a_src[q] != nullptr && (reinterpret_cast<uintptr_t>(args.a_src[q]) & 15) == 0),
+                 "allgather_gemm: every peer's row block pointer is needed (16-byte aligned)");
+    g.a_src[q] = static_cast<const unsigned char*>(args.a_src[q]);
+    g.done_flag[q] = args.done_flag[q];
+    HPCP_REQUIRE(args.done_flag[q] == nullptr || args.ticket != nullptr, "allgather_gemm: a signal needs a ticket counter");
+  }
+  g.a_full = static_cast<unsigned char*>(args.a_full);
+  g.c_local = args.c;
+  g.c_peer = nullptr;
+  g.out_bf16 = args.out_bf16 ? 1 : 0;
+  g.ready = args.ready;
+  g.chunk_bytes = static_cast<uint32_t>(chunk);
+  g.chunks_per_block = static_cast<uint32_t>(block_bytes / chunk);
+  g.gather_bufs = std::min<int>(kMaxGatherBufs, static_cast<int>((kGatherSmemBytes - 64) / chunk));
+  g.ready_target = args.ready_base + g.chunks_per_block;
+  g.done_epoch = args.done_epoch;
+  g.ticket = args.ticket;
+  g.ticket_base = args.ticket_base;
+  g.timeout_ns = args.timeout_ns;
+  g.status = args.status;
+  g.rank = args.rank;
+  g.world = args.world;
+  g.n = args.n;
+  g.k = args.k;
+  g.tiles_m = s.tiles_m;
+  g.tiles_n = s.tiles_n;
+  g.shard_tiles_m = s.shard_tiles_m;
+  const bool pairs = cluster != 1 && s.pairable;
+  const CUtensorMap map_a = make_kmajor_map(args.a_full, args.m, args.k, kBM);
+  const int tiles = s.tiles_m * s.tiles_n;
+  // Every CTA carries a share of the gather, so the whole grid must be resident: never more CTAs than SMs.
+  int grid = std::min(tiles, std::min(ctas > 0 ? ctas : device_sm_count(device), device_sm_count(device)));
+  constexpr size_t smem = gemm_smem_bytes<kStages>(kGatherSmemBytes);
+  static_assert(smem + 1024 <= 227 * 1024,  // + the static barriers, padded to the 1 KiB alignment of the ring
+                "GEMM stages + epilogue staging + gather ring must fit in 227 KiB");
+  if (!pairs || grid < 2) {
+    const CUtensorMap map_b = make_kmajor_map(args.b, args.n, args.k, kBN);
+    HPCP_ENABLE_SMEM(allgather_gemm_kernel<1>, smem);
+    allgather_gemm_kernel<1><<<grid, kThreads, smem, stream>>>(map_a, map_b, g);
+    HPCP_CUDA(cudaGetLastError());
+    return grid;
+  }
+  grid &= ~1;
+  const CUtensorMap map_b = make_kmajor_map(args.b, args.n, args.k, kBN / 2);
+  HPCP_ENABLE_SMEM(allgather_gemm_kernel<2>, smem);
+  launch_pairs(allgather_gemm_kernel<2>, grid, smem, stream, map_a, map_b, g);
+  return grid;
+}
+
+}  // namespace hpcp

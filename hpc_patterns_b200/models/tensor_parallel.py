@@ -1,0 +1,141 @@
+"""Tensor-parallel linear layers whose collective is fused into the GEMM kernel.
+
+Beyond the reference (which has no GEMM): the suite's "compute step followed by a
+collective as ONE kernel" family applied to the tensor cores.
+
+``RowParallelLinear``     every rank holds a K-slice of the weight; ``y = reduce_scatter(x_r @ W_r.T)``.
+                          One kernel: tcgen05 GEMM whose epilogue adds each tile into the owning rank's
+                          fp32 shard over NVLink (K-gemm-rs), then a wait for the P arrival epochs.
+``ColumnParallelLinear``  activations are row-sharded, the weight column-sharded:
+                          ``y = all_gather(x_r) @ W_r.T``.  One kernel: gather threads pull the peers'
+                          rows over NVLink while the GEMM already works on the rows that are here (K-ag-gemm).
+
+Both keep their operands in symmetric (peer-mapped) buffers, synchronise with the suite's signal pads
+(no NCCL, no host sync on the step) and carry a ``stock_forward`` that runs the same step the stock way —
+``torch.matmul`` (cuBLAS) + ``torch.distributed`` reduce_scatter / all_gather (NCCL) — as the baseline.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from .. import native
+from ..ops.gemm import allgather_gemm, gemm_reduce_scatter
+from ..parallel.comm import Comm
+from ..parallel.symmetric import SignalPads, SymmetricBuffer
+
+
+class _FusedLinearBase:
+    def __init__(self, comm: Comm, device: int, timeout_s: float):
+        self.C = native()
+        self.comm = comm
+        self.device = device
+        self.rank, self.world = comm.rank, comm.world
+        self.pads = SignalPads(comm, device, timeout_s=timeout_s)
+        self.epoch = 0
+        self.launches = 0
+
+    @property
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def check(self) -> None:
+        self.pads.check()
+
+
+class RowParallelLinear(_FusedLinearBase):
+    """``y_shard[M/P, N] = sum_r x_r[M, K_r] @ w_r[N, K_r].T`` restricted to this rank's rows."""
+
+    def __init__(self, comm: Comm, device: int, m: int, n: int, k_local: int, cluster: int = 0, ctas: int = 0,
+                 timeout_s: float = 30.0):
+        super().__init__(comm, device, timeout_s)
+        if m % (128 * self.world) or n % 256 or k_local % 64:
+            raise ValueError("M, N, K_local must be multiples of 128*world, 256, 64")
+        self.m, self.n, self.k = m, n, k_local
+        self.cluster, self.ctas = cluster, ctas
+        self.shard = SymmetricBuffer(comm, (m // self.world) * n * 4, device, zero=True)
+        self.y = self.shard.tensor(torch.float32).view(m // self.world, n)
+        self.w = torch.empty(n, k_local, device=f"cuda:{device}", dtype=torch.bfloat16)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x: bf16 ``[M, K_local]``.  Returns this rank's rows of the reduced output (a view of the symmetric shard,
+        valid until the next forward)."""
+        st = self._stream
+        self.epoch += 1
+        self.C.memset_async(self.shard.local_ptr, 0, self.shard.nbytes, st)
+        self.pads.device_barrier(st)  # every shard is zero before anybody adds into it
+        done = [self.pads.word(q, self.C.PAD_DONE + self.rank) for q in range(self.world)]
+        ctas = gemm_reduce_scatter(x, self.w, self.shard.ptrs, self.rank, done_flags=done, done_epoch=self.epoch,
+                                   ticket=self.pads.ticket_ptr, ticket_base=self.pads.ticket_issued & 0xFFFFFFFF,
+                                   ctas=self.ctas, stream=st, cluster=self.cluster)
+        self.pads.advance_tickets(ctas)
+        self.C.wait_flags(self.pads.word(self.rank, self.C.PAD_DONE), self.world, self.epoch, self.pads.timeout_ns,
+                          self.pads.status_ptr, st)
+        self.launches += 3
+        return self.y
+
+    def stock_forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """cuBLAS GEMM + NCCL reduce_scatter (fp32), the stock pattern."""
+        full = x.float() @ self.w.float().t() if x.device.type == "cpu" else torch.matmul(x, self.w.t()).float()
+        if self.world == 1:
+            return full
+        out = out if out is not None else torch.empty(self.m // self.world, self.n, device=x.device)
+        dist.reduce_scatter_tensor(out, full)
+        return out
+
+    def close(self) -> None:
+        self.shard.close()
+        self.pads.close()
+
+
+class ColumnParallelLinear(_FusedLinearBase):
+    """``y[M, N_local] = concat_r(x_r[M/P, K]) @ w[N_local, K].T``."""
+
+    def __init__(self, comm: Comm, device: int, m: int, n_local: int, k: int, out_dtype: torch.dtype = torch.float32,
+                 cluster: int = 0, ctas: int = 0, chunk_bytes: int = 0, timeout_s: float = 30.0):
+        super().__init__(comm, device, timeout_s)
+        if m % (128 * self.world) or n_local % 256 or k % 64:
+            raise ValueError("M, N_local, K must be multiples of 128*world, 256, 64")
+        self.m, self.n, self.k = m, n_local, k
+        self.cluster, self.ctas, self.chunk_bytes = cluster, ctas, chunk_bytes
+        self.a = SymmetricBuffer(comm, m * k * 2, device, zero=True)
+        self.a_full = self.a.tensor(torch.bfloat16).view(m, k)
+        rows = m // self.world
+        self.x_local = self.a_full[self.rank * rows:(self.rank + 1) * rows]  # write the activations here
+        self.w = torch.empty(n_local, k, device=f"cuda:{device}", dtype=torch.bfloat16)
+        self.y = torch.empty(m, n_local, device=f"cuda:{device}", dtype=out_dtype)
+        self.ready = torch.zeros(m // 128, device=f"cuda:{device}", dtype=torch.int32)
+        self.ready_base = 0
+        self._per_launch = self.C.allgather_gemm_chunks_per_block(k, chunk_bytes)
+        self._block_bytes = rows * k * 2
+
+    def forward(self, x_local: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x_local: this rank's bf16 rows ``[M/P, K]`` (or None when they were written into ``self.x_local``)."""
+        st = self._stream
+        if x_local is not None:
+            self.x_local.copy_(x_local)
+        # Every rank's rows are final, and nobody still reads the rows of the previous step.
+        self.pads.device_barrier(st)
+        src = [self.a.ptrs[q] + q * self._block_bytes for q in range(self.world)]
+        allgather_gemm(self.a_full, src, self.w, self.y, self.rank, ready=self.ready,
+                       ready_base=self.ready_base & 0xFFFFFFFF, chunk_bytes=self.chunk_bytes,
+                       timeout_ns=self.pads.timeout_ns, status=self.pads.status_ptr, ctas=self.ctas, stream=st,
+                       cluster=self.cluster)
+        if self.world > 1:
+            self.ready_base += self._per_launch
+        self.launches += 2
+        return self.y
+
+    def stock_forward(self, x_local: torch.Tensor) -> torch.Tensor:
+        """NCCL all_gather + cuBLAS GEMM, the stock pattern."""
+        if self.world == 1:
+            return torch.matmul(x_local, self.w.t())
+        full = torch.empty(self.m, self.k, device=x_local.device, dtype=x_local.dtype)
+        dist.all_gather_into_tensor(full, x_local.contiguous())
+        return torch.matmul(full, self.w.t())
+
+    def close(self) -> None:
+        self.a.close()
+        self.pads.close()

@@ -10,7 +10,7 @@ followed by a copy-engine peer copy.
 """
 from __future__ import annotations
 
-from typing import Optional
+from typing import Optional, Sequence
 
 import torch
 
@@ -47,3 +47,60 @@ def gemm_put(a: torch.Tensor, b: torch.Tensor, c_local: Optional[torch.Tensor] =
 def gemm_reference(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """Plain PyTorch fp32 reference of the op."""
     return a.float() @ b.float().t()
+
+
+def _check_operands(a: torch.Tensor, b: torch.Tensor) -> None:
+    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
+        raise TypeError("bf16 operands expected")
+    if a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[1]:
+        raise ValueError("expected A[M,K] and B[N,K]")
+
+
+def gemm_reduce_scatter(a: torch.Tensor, b: torch.Tensor, shards: Sequence[PtrLike], rank: int, *,
+                        done_flags: Sequence[int] = (), done_epoch: int = 0, ticket: int = 0, ticket_base: int = 0,
+                        ctas: int = 0, stream: Optional[int] = None, cluster: int = 0) -> int:
+    """K-gemm-rs (csrc/kernels/gemm_collective.cu): ``A[M,K_r] @ B[N,K_r].T`` is this rank's partial sum; the
+    epilogue adds every 128x256 tile into ``shards[owner]`` (fp32 ``[M/world, N]``, peer-mapped pointers or local
+    tensors, one per rank, zeroed by their owners) with ``red.global.add.v4.f32`` over NVLink.  When
+    ``done_flags`` (one word per rank) are given, the last CTA publishes ``done_epoch`` on all of them.
+    Returns the number of CTAs launched (ticket bookkeeping)."""
+    _check_operands(a, b)
+    world = len(shards)
+    m, k = a.shape
+    n = b.shape[0]
+    if m % (128 * world) or n % 256 or k % 64:
+        raise ValueError("M, N, K must be multiples of 128*world, 256, 64")
+    for s in shards:
+        if isinstance(s, torch.Tensor) and (s.dtype != torch.float32 or tuple(s.shape) != (m // world, n)):
+            raise ValueError("every shard must be fp32 [M/world, N]")
+    dev = a.device.index
+    return native().gemm_reduce_scatter(ptr(a), ptr(b), [ptr(s) for s in shards], [int(f) for f in done_flags],
+                                        done_epoch, ticket, ticket_base, rank, m, n, k, ctas, dev,
+                                        current_stream(dev) if stream is None else stream, cluster)
+
+
+def allgather_gemm(a_full: torch.Tensor, a_src: Sequence[PtrLike], b: torch.Tensor, c: torch.Tensor, rank: int, *,
+                   ready: PtrLike = 0, ready_base: int = 0, chunk_bytes: int = 0, done_flags: Sequence[int] = (),
+                   done_epoch: int = 0, ticket: int = 0, ticket_base: int = 0, timeout_ns: int = 0, status: int = 0,
+                   ctas: int = 0, stream: Optional[int] = None, cluster: int = 0) -> int:
+    """K-ag-gemm: ``C[M,N] = A[M,K] @ B[N,K].T`` where rank ``q`` holds rows ``[q*M/world, (q+1)*M/world)`` of A.
+    ``a_full`` is the local gathered A (this rank's rows already in place), ``a_src[q]`` the peer-mapped address of
+    rank q's row block.  One gather thread per CTA pulls the remote rows with TMA bulk copies while the tiles of the
+    rows that are already here run on the tensor cores; ``ready`` (int32 ``[M/128]``) counts arrivals per 128-row
+    block and counts up forever: pass the value before the launch as ``ready_base`` (it grows by
+    ``native().allgather_gemm_chunks_per_block(K, chunk_bytes)`` per launch).  Returns the CTAs launched."""
+    _check_operands(a_full, b)
+    world = len(a_src)
+    m, k = a_full.shape
+    n = b.shape[0]
+    if m % (128 * world) or n % 256 or k % 64:
+        raise ValueError("M, N, K must be multiples of 128*world, 256, 64")
+    if c.dtype not in (torch.float32, torch.bfloat16) or tuple(c.shape) != (m, n):
+        raise ValueError("c must be fp32 or bf16 [M, N]")
+    if world > 1 and isinstance(ready, torch.Tensor) and (ready.dtype != torch.int32 or ready.numel() < m // 128):
+        raise ValueError("ready must be int32 with one word per 128-row block")
+    dev = a_full.device.index
+    return native().allgather_gemm(ptr(a_full), [ptr(s) for s in a_src], ptr(b), ptr(c), c.dtype == torch.bfloat16,
+                                   ptr(ready), ready_base, chunk_bytes, [int(f) for f in done_flags], done_epoch,
+                                   ticket, ticket_base, timeout_ns, status, rank, m, n, k, ctas, dev,
+                                   current_stream(dev) if stream is None else stream, cluster)
