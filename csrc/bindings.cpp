@@ -21,6 +21,7 @@
 #include "concurency/bench.hpp"
 #include "concurency/driver.hpp"
 #include "kernels/api.h"
+#include "kernels/tile_order.h"
 #include "p2p/topology_core.hpp"
 
 namespace py = pybind11;
@@ -380,6 +381,23 @@ PYBIND11_MODULE(_C, m) {
       py::arg("n"), py::arg("k"), py::arg("ctas") = 0, py::arg("device") = 0, py::arg("stream") = 0,
       py::arg("cluster") = 0,
       "tcgen05 GEMM whose epilogue adds every tile into the owner's fp32 shard over NVLink (GEMM -> reduce-scatter).");
+  // Tile / gather orderings of the tensor-core kernels (kernels/tile_order.h), exposed for the CPU tests.
+  m.def("gemm_tile_coords", [](int tile, int tiles_m, int tiles_n) {
+    int mb = 0, nb = 0;
+    umma::tile_coords(tile, tiles_m, tiles_n, &mb, &nb);
+    return std::make_pair(mb, nb);
+  });
+  m.def("gemm_shard_coords", [](int tile, int rank, int world, int first, int shard_tiles_m, int tiles_n) {
+    int mb = 0, nb = 0;
+    umma::shard_coords(tile, rank, world, first, shard_tiles_m, tiles_n, &mb, &nb);
+    return std::make_pair(mb, nb);
+  });
+  m.def("gemm_gather_piece", [](size_t c, int rank, int world, int shard_tiles_m, uint32_t chunks_per_block,
+                                uint32_t chunk_bytes, size_t block_bytes) {
+    const umma::GatherPiece p = umma::gather_piece(c, rank, world, shard_tiles_m, chunks_per_block, chunk_bytes,
+                                                   block_bytes);
+    return py::make_tuple(p.peer, p.m_blk, p.src_off, p.dst_off);
+  });
   m.def("allgather_gemm_chunks_per_block", &allgather_gemm_chunks_per_block, py::arg("k"), py::arg("chunk_bytes") = 0);
   m.def(
       "allgather_gemm",

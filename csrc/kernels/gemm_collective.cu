@@ -58,18 +58,6 @@ struct RsDev {
   int shard_tiles_m;  // tiles_m / world
 };
 
-// Shard-major rasterisation: P groups of (M/P x N) tiles; group i of rank r is the shard of rank (r+first+i) % P,
-// the grouped order of umma.cuh inside a shard.
-__device__ __forceinline__ void shard_coords(int tile, int rank, int world, int first, int shard_tiles_m, int tiles_n,
-                                             int* m_blk, int* n_blk) {
-  const int per_shard = shard_tiles_m * tiles_n;
-  const int i = tile / per_shard;
-  const int owner = (rank + first + i) % world;
-  int mb;
-  tile_coords(tile - i * per_shard, shard_tiles_m, tiles_n, &mb, n_blk);
-  *m_blk = owner * shard_tiles_m + mb;
-}
-
 // Last CTA of the grid publishes `epoch` on every rank's flag (all threads call it).
 __device__ __forceinline__ void last_cta_publish_all(uint32_t* ticket, uint32_t tickets_target,
                                                      uint32_t* const* flags, int world, uint32_t epoch) {
@@ -166,41 +154,30 @@ struct AllGatherPolicy {
     for (int s = 0; s < bufs; ++s) ptx::mbar_init(&full[s], 1);
     ptx::fence_mbar_init();
     const size_t block_bytes = static_cast<size_t>(kBM) * g.k * 2;
-    const size_t per_peer = static_cast<size_t>(g.shard_tiles_m) * g.chunks_per_block;
-    const size_t total = static_cast<size_t>(g.world - 1) * per_peer;
+    const size_t total = static_cast<size_t>(g.world - 1) * g.shard_tiles_m * g.chunks_per_block;
     const size_t n = total > blockIdx.x ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    struct Piece {
-      const unsigned char* src;
-      unsigned char* dst;
-      uint32_t* counter;
-    };
-    auto piece = [&](size_t j) {
-      const size_t c = static_cast<size_t>(blockIdx.x) + j * gridDim.x;
-      const int i = static_cast<int>(c / per_peer);          // i-th peer after me
-      const size_t in_peer = c - i * per_peer;
-      const int peer = (g.rank + 1 + i) % g.world;
-      const size_t blk = in_peer / g.chunks_per_block;       // 128-row block inside the peer's rows
-      const size_t off = blk * block_bytes + (in_peer - blk * g.chunks_per_block) * g.chunk_bytes;
-      const size_t m_blk = static_cast<size_t>(peer) * g.shard_tiles_m + blk;
-      return Piece{g.a_src[peer] + off, g.a_full + static_cast<size_t>(peer) * g.shard_tiles_m * block_bytes + off,
-                   g.ready + m_blk};
+    auto piece = [&](size_t j) {  // my j-th piece (tile_order.h: peer rank+1 first, pieces dealt round-robin)
+      return gather_piece(static_cast<size_t>(blockIdx.x) + j * gridDim.x, g.rank, g.world, g.shard_tiles_m,
+                          g.chunks_per_block, g.chunk_bytes, block_bytes);
     };
     auto issue_load = [&](size_t j) {
       const int st = static_cast<int>(j % bufs);
       ptx::mbar_arrive_expect_tx(&full[st], g.chunk_bytes);
-      ptx::bulk_g2s(aux_smem + static_cast<size_t>(st) * g.chunk_bytes, piece(j).src, g.chunk_bytes, &full[st]);
+      const GatherPiece p = piece(j);
+      ptx::bulk_g2s(aux_smem + static_cast<size_t>(st) * g.chunk_bytes, g.a_src[p.peer] + p.src_off, g.chunk_bytes,
+                    &full[st]);
     };
     // Stores are retired in order: once store j-1 is complete its piece is counted and its buffer is reused.
     auto retire = [&](size_t j) {
       asm volatile("fence.proxy.async;" ::: "memory");
-      ptx::red_release_gpu_add(piece(j).counter, 1u);
+      ptx::red_release_gpu_add(g.ready + piece(j).m_blk, 1u);
     };
     const size_t lookahead = static_cast<size_t>(bufs - 1);
     for (size_t j = 0; j < lookahead && j < n; ++j) issue_load(j);
     for (size_t j = 0; j < n; ++j) {
       const int st = static_cast<int>(j % bufs);
       ptx::mbar_wait(&full[st], static_cast<uint32_t>((j / bufs) & 1));
-      ptx::bulk_s2g(piece(j).dst, aux_smem + static_cast<size_t>(st) * g.chunk_bytes, g.chunk_bytes);
+      ptx::bulk_s2g(g.a_full + piece(j).dst_off, aux_smem + static_cast<size_t>(st) * g.chunk_bytes, g.chunk_bytes);
       ptx::bulk_commit();
       if (j > 0) {
         ptx::bulk_wait<1>();  // every store but the newest is complete (written, not just read)

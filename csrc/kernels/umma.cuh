@@ -14,6 +14,7 @@
 
 #include "../common/cuda_check.h"
 #include "../common/ptx.cuh"
+#include "tile_order.h"
 
 namespace hpcp {
 namespace umma {
@@ -175,20 +176,6 @@ __device__ __forceinline__ void tc_fence_before() {
 }
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-
-// Tile rasterisation: groups of kGroupM tile-rows, m fastest inside a group, so the ~148 tiles that
-// are in flight at any time cover a near-square block of C (8 x ~18 tiles): fewer distinct A/B
-// panels per k-step than row-major order -> less HBM traffic once A and B exceed the 126 MB L2.
-constexpr int kGroupM = 8;
-__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int* m_blk, int* n_blk) {
-  const int group_size = kGroupM * tiles_n;
-  const int group = tile / group_size;
-  const int first_m = group * kGroupM;
-  const int gm = tiles_m - first_m < kGroupM ? tiles_m - first_m : kGroupM;
-  const int in_group = tile - group * group_size;
-  *m_blk = first_m + in_group % gm;
-  *n_blk = in_group / gm;
 }
 
 // Epilogue of one 128x256 accumulator (one epilogue warp = 32 accumulator rows): TMEM -> registers ->
