@@ -21,6 +21,7 @@
 #include "concurency/bench.hpp"
 #include "concurency/driver.hpp"
 #include "kernels/api.h"
+#include "kernels/ring_order.h"
 #include "kernels/tile_order.h"
 #include "p2p/topology_core.hpp"
 
@@ -463,14 +464,23 @@ PYBIND11_MODULE(_C, m) {
     launch_count_mismatch(as_ptr<const void>(v), n, expected, elem_from(dtype),
                           as_ptr<unsigned long long>(count), as_stream(stream));
   });
+  // Slot / flow-control rules of the fused ring (kernels/ring_order.h), exposed for the CPU protocol model.
+  m.def("ring_src_slot", &ring_src_slot);
+  m.def("ring_fwd_slot", &ring_fwd_slot);
+  m.def("ring_forwards", &ring_forwards);
+  m.def("ring_waits_for_ack", &ring_waits_for_ack);
+  m.def("ring_publishes_ack", &ring_publishes_ack);
   m.def("ring_num_chunks", &ring_num_chunks, py::arg("n"), py::arg("chunk_elems") = 0);
   m.def(
       "ring_allreduce",
       [](uintptr_t va, uintptr_t vc, uintptr_t slots_local, uintptr_t slots_right,
          uintptr_t arrived_local, uintptr_t arrived_right, int world, size_t n, size_t chunk_elems,
          uint32_t epoch_base, uint64_t timeout_ns, uintptr_t status, const std::string& dtype, int ctas,
-         int device, uintptr_t stream) {
+         int device, uintptr_t stream, int n_slots, uintptr_t ack_local, uintptr_t ack_left) {
         RingArgs a;
+        a.n_slots = n_slots;
+        a.ack_local = as_ptr<uint32_t>(ack_local);
+        a.ack_left = as_ptr<uint32_t>(ack_left);
         a.va = as_ptr<const void>(va);
         a.vc = as_ptr<void>(vc);
         a.slots_local = as_ptr<void>(slots_local);
@@ -489,7 +499,7 @@ PYBIND11_MODULE(_C, m) {
       py::arg("arrived_local"), py::arg("arrived_right"), py::arg("world"), py::arg("n"),
       py::arg("chunk_elems") = 0, py::arg("epoch_base") = 0, py::arg("timeout_ns") = 0,
       py::arg("status") = 0, py::arg("dtype") = "float", py::arg("ctas") = 0, py::arg("device") = 0,
-      py::arg("stream") = 0);
+      py::arg("stream") = 0, py::arg("n_slots") = 0, py::arg("ack_local") = 0, py::arg("ack_left") = 0);
   m.def(
       "allreduce_two_shot",
       [](const std::vector<uintptr_t>& va, const std::vector<uintptr_t>& vc,

@@ -229,6 +229,13 @@ struct RingArgs {
   uint32_t epoch_base = 0;        // arrival words count up: base + hop
   uint64_t timeout_ns = 0;
   uint32_t* status = nullptr;
+  // Receive-slot policy.  0 (default) = world-1 slots, no flow control.  2 = the reference's VA/VB double
+  // buffer: slots hold 2 * n elements, hop t lands in slot (t-1) % 2, and per-chunk ack words (n_chunks words,
+  // written by the right neighbour into ack_local; ack_left = the left neighbour's, peer-mapped) keep a sender
+  // from overwriting a chunk its neighbour has not consumed yet.  Ack epochs share epoch_base with the arrivals.
+  int n_slots = 0;
+  uint32_t* ack_local = nullptr;
+  uint32_t* ack_left = nullptr;
 };
 size_t ring_num_chunks(size_t n, size_t chunk_elems);
 void launch_ring_allreduce(const RingArgs& args, ElemType type, int ctas, int device,

@@ -13,8 +13,12 @@
 //   stores it into the right neighbour's slot t over NVLink (peer-mapped pointer)
 //   publishes (release) arrival word c  on the right neighbour.
 // Accumulate, send, receive and the step barrier are fused; steps pipeline
-// across the ring chunk by chunk.  Slots are (P-1) full blocks so no ack channel
-// is needed (896 MiB at P=8, N=2^25 floats — small against 180 GB of HBM3e).
+// across the ring chunk by chunk.  By default the receive slots are (P-1) full blocks, so
+// no ack channel is needed (896 MiB at P=8, N=2^25 floats — small against 180 GB of HBM3e).
+// n_slots = 2 is the reference's own VA/VB double buffer (allreduce-mpi-sycl.cpp:167-168,
+// 176-181): hop t lands in slot t % 2, and before a rank overwrites its neighbour's slot at
+// hop t >= 2 it waits for the neighbour's per-chunk ack of hop t-1 — the flow control that a
+// blocking MPI_Recv provides implicitly.  2 blocks instead of P-1 (256 MiB at P=8).
 //
 // The `-a` path (↔ MPI_Allreduce, :61-67) is a one-launch collective: two-shot
 // over peer mappings, or NVLS (multimem.ld_reduce / multimem.st) when a
@@ -28,6 +32,7 @@
 
 #include "../common/cuda_check.h"
 #include "../common/signal.cuh"
+#include "ring_order.h"
 
 namespace hpcp {
 
@@ -99,20 +104,33 @@ struct RingDev {
   uint32_t epoch_base;
   uint64_t timeout_ns;
   uint32_t* status;
+  // kAck only (appended so that the layout the default instantiation reads is unchanged):
+  uint32_t* ack_local;  // n_chunks words written by the right neighbour: "hop t of chunk c consumed"
+  uint32_t* ack_left;   // peer-mapped: the left neighbour's ack words
 };
 
-template <typename T>
+// kAck = false: P-1 receive slots, hop t lands in slot t-1.  kAck = true: two slots, hop t lands in slot
+// (t-1) % 2 and the sender waits for the receiver's ack of hop t-1 before it overwrites the slot at hop t+1.
+template <typename T, bool kAck = false>
 __global__ void __launch_bounds__(512) ring_allreduce_kernel(const __grid_constant__ RingDev a) {
   __shared__ int ok_s;
   for (int t = 0; t < a.world; ++t) {
-    const uint4* src = t == 0 ? a.va : a.slots_local + static_cast<size_t>(t - 1) * a.nvec;
-    uint4* fwd = t < a.world - 1 ? a.slots_right + static_cast<size_t>(t) * a.nvec : nullptr;
+    const uint4* src = t == 0 ? a.va : a.slots_local + static_cast<size_t>(ring_src_slot(t, kAck)) * a.nvec;
+    uint4* fwd = ring_forwards(t, a.world) ? a.slots_right + static_cast<size_t>(ring_fwd_slot(t, kAck)) * a.nvec
+                                           : nullptr;
     for (size_t c = blockIdx.x; c < a.n_chunks; c += gridDim.x) {
       if (t > 0) {
         if (threadIdx.x == 0)
           ok_s = wait_epoch(a.arrived_local + c, a.epoch_base + t, a.timeout_ns, a.status) ? 1 : 0;
         __syncthreads();
         if (!ok_s) return;  // peer hung: status word set, drain
+      }
+      if (kAck && ring_waits_for_ack(t, a.world)) {
+        // My hop-t forward overwrites what the right neighbour received at hop t-2 and reads at ITS hop t-1.
+        if (threadIdx.x == 0)
+          ok_s = wait_epoch(a.ack_local + c, a.epoch_base + t - 1, a.timeout_ns, a.status) ? 1 : 0;
+        __syncthreads();
+        if (!ok_s) return;
       }
       const size_t begin = c * a.chunk_vec;
       const size_t end = begin + a.chunk_vec < a.nvec ? begin + a.chunk_vec : a.nvec;
@@ -136,6 +154,10 @@ __global__ void __launch_bounds__(512) ring_allreduce_kernel(const __grid_consta
       }
       __syncthreads();  // whole chunk stored by this CTA (and ok_s consumed by everyone)
       if (fwd && threadIdx.x == 0) publish_epoch_light(a.arrived_right + c, a.epoch_base + t + 1);
+      // The slot chunk I have just read may be overwritten: tell the left neighbour (it only looks at hops
+      // 1 .. P-3, the ones followed by another write into the same slot).
+      if (kAck && ring_publishes_ack(t, a.world) && threadIdx.x == 0)
+        publish_epoch_light(a.ack_left + c, a.epoch_base + t);
     }
   }
 }
@@ -352,6 +374,12 @@ void launch_ring_allreduce(const RingArgs& args, ElemType type, int ctas, int de
   d.epoch_base = args.epoch_base;
   d.timeout_ns = args.timeout_ns;
   d.status = args.status;
+  const bool ack = args.n_slots == 2 && args.world > 3;  // with P <= 3 no slot is ever written twice
+  HPCP_REQUIRE(args.n_slots == 0 || args.n_slots == 2 || args.n_slots == args.world - 1,
+               "ring: n_slots must be 0 (= world-1, no flow control) or 2 (double buffer + acks)");
+  HPCP_REQUIRE(!ack || (args.ack_local != nullptr && args.ack_left != nullptr), "ring: n_slots=2 needs the ack words");
+  d.ack_local = args.ack_local;
+  d.ack_left = args.ack_left;
   // All CTAs may spin on arrival words: the grid must be co-resident (<= 4 CTAs of
   // 512 threads per SM).
   const int sms = device_sm_count(device);
@@ -375,10 +403,17 @@ void launch_ring_allreduce(const RingArgs& args, ElemType type, int ctas, int de
     }
     grid = best;
   }
-  if (type == ElemType::kFloat)
+  const bool two_slots = args.n_slots == 2;  // slot index t % 2 even when no ack is ever needed (P <= 3)
+  if (two_slots) {
+    if (type == ElemType::kFloat)
+      ring_allreduce_kernel<float, true><<<grid, 512, 0, stream>>>(d);
+    else
+      ring_allreduce_kernel<int, true><<<grid, 512, 0, stream>>>(d);
+  } else if (type == ElemType::kFloat) {
     ring_allreduce_kernel<float><<<grid, 512, 0, stream>>>(d);
-  else
+  } else {
     ring_allreduce_kernel<int><<<grid, 512, 0, stream>>>(d);
+  }
   HPCP_CUDA(cudaGetLastError());
 }
 

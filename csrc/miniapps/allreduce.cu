@@ -59,6 +59,7 @@ struct Config {
   size_t chunk_elems = 0;
   uint64_t timeout_ns = 30ull * 1000 * 1000 * 1000;
   std::string json_path;
+  int slots = 0;     // --slots 2: the reference's VA/VB double buffer with per-chunk acks (default: P-1 slots)
   bool cpu = false;  // --cpu: host-only plumbing run (threads as ranks, memcpy as send/recv)
 };
 
@@ -80,6 +81,8 @@ void print_help() {
                " --coll auto|nvls|twoshot   collective used with -a\n"
                " --iters N --warmup N  timed / untimed repetitions (min is reported)\n"
                " --ctas N --chunk N    kernel tuning (CTAs per rank, elements per ring chunk)\n"
+               " --slots 2             fused ring with two receive slots + per-chunk acks (the reference's VA/VB\n"
+               "                       double buffer) instead of P-1 slots without flow control\n"
                " --json FILE           append one JSON row\n"
                " --cpu                 host-only plumbing run: ranks are threads, send/recv are memcpy\n";
 }
@@ -89,6 +92,7 @@ struct Shared {
   NodeMemory* mem = nullptr;
   size_t n = 0;
   size_t n_chunks = 0;
+  size_t pad_extra = 0;  // words after the fixed pad: arrival words (+ ack words with --slots 2)
   SymmetricBuffer va, vb, vc, slots, pads;
   MulticastBuffer mc_va, mc_vc;
   bool nvls = false;
@@ -108,7 +112,7 @@ void rank_main(RankCtx& ctx, Shared& sh) {
   const int right = (me + 1) % P, left = (me - 1 + P) % P;
   const size_t esz = 4;
   uint32_t* my_pad = pad_of(sh, me);
-  uint32_t* status = my_pad + kPadWords + sh.n_chunks;
+  uint32_t* status = my_pad + kPadWords + sh.pad_extra;
   std::vector<uint32_t*> pad_list;
   for (int r = 0; r < P; ++r) pad_list.push_back(pad_of(sh, r));
 
@@ -178,6 +182,11 @@ void rank_main(RankCtx& ctx, Shared& sh) {
       a.epoch_base = ring_epoch;
       a.timeout_ns = cfg.timeout_ns;
       a.status = status;
+      a.n_slots = cfg.slots;
+      if (cfg.slots == 2) {  // ack words follow the arrival words on every pad
+        a.ack_local = my_pad + kPadWords + sh.n_chunks;
+        a.ack_left = pad_of(sh, left) + kPadWords + sh.n_chunks;
+      }
       ring_epoch += static_cast<uint32_t>(P);
       launch_ring_allreduce(a, cfg.type, cfg.ctas, dev, stream);
     } else {  // ring-unfused: the reference's step structure with separate kernels
@@ -352,6 +361,7 @@ int main(int argc, char** argv) {
                                        {"chunk", required_argument, nullptr, 7},
                                        {"json", required_argument, nullptr, 8},
                                        {"cpu", no_argument, nullptr, 9},
+                                       {"slots", required_argument, nullptr, 10},
                                        {"help", no_argument, nullptr, 'h'},
                                        {nullptr, 0, nullptr, 0}};
     int opt;
@@ -376,11 +386,13 @@ int main(int argc, char** argv) {
         case 7: cfg.chunk_elems = static_cast<size_t>(std::atoll(optarg)); break;
         case 8: cfg.json_path = optarg; break;
         case 9: cfg.cpu = true; break;
+        case 10: cfg.slots = std::atoi(optarg); break;
         default: print_help(); return 1;
       }
     }
     HPCP_REQUIRE(cfg.algo == "ring" || cfg.algo == "ring-unfused", "unknown --algo " + cfg.algo);
     HPCP_REQUIRE(cfg.log2_elems >= 4 && cfg.log2_elems <= 32, "-p must be in [4,32]");
+    HPCP_REQUIRE(cfg.slots == 0 || cfg.slots == 2, "--slots must be 2 (or omitted)");
 
     if (cfg.cpu) return run_on_host(cfg);
     const int ndev = visible_device_count();
@@ -408,7 +420,8 @@ int main(int argc, char** argv) {
       sh.n = (sh.n / (4 * P) + 1) * (4 * P);  // pad so that every rank owns an aligned slice
     const size_t bytes = sh.n * 4;
     sh.n_chunks = ring_num_chunks(sh.n, cfg.chunk_elems);
-    sh.pads = mem.alloc_pads(sh.n_chunks);
+    sh.pad_extra = sh.n_chunks * (cfg.slots == 2 ? 2 : 1);
+    sh.pads = mem.alloc_pads(sh.pad_extra);
 
     if (cfg.use_collective) {
       bool want_nvls = cfg.coll == "nvls";
@@ -433,7 +446,7 @@ int main(int argc, char** argv) {
     }
     if (!cfg.use_collective) {
       if (cfg.algo == "ring")
-        sh.slots = mem.alloc(bytes * static_cast<size_t>(P - 1), cfg.kind, /*zero=*/false);
+        sh.slots = mem.alloc(bytes * static_cast<size_t>(cfg.slots == 2 ? 2 : P - 1), cfg.kind, /*zero=*/false);
       else
         sh.vb = mem.alloc(bytes, cfg.kind);
     }

@@ -63,7 +63,10 @@ class AllreduceResult:
 
 class AllreduceMiniapp:
     def __init__(self, comm: Comm, device: int, log2_elems: int = 25, dtype: str = "float",
-                 algo: str = "ring", chunk_elems: int = 0, ctas: int = 0, timeout_s: float = 30.0):
+                 algo: str = "ring", chunk_elems: int = 0, ctas: int = 0, timeout_s: float = 30.0,
+                 slots: int = 0):
+        """``slots=2`` (fused ring only): two receive slots + per-chunk acks — the reference's VA/VB double
+        buffer — instead of ``world-1`` slots without flow control."""
         if algo not in ALGOS:
             raise ValueError(f"algo must be one of {ALGOS}")
         if dtype not in _TORCH_DTYPE:
@@ -78,8 +81,13 @@ class AllreduceMiniapp:
         self.n, self.nbytes = n, n * 4
         self.right, self.left = (self.rank + 1) % self.world, (self.rank - 1) % self.world
         torch.cuda.set_device(device)
+        if slots not in (0, 2):
+            raise ValueError("slots must be 0 (world-1 slots) or 2")
+        self.slots_policy = slots if algo == "ring" else 0
         self.n_chunks = self.C.ring_num_chunks(n, chunk_elems)
-        self.pads = SignalPads(comm, device, extra_words=self.n_chunks, timeout_s=timeout_s)
+        # arrival words, then (two-slot ring) ack words
+        self.pads = SignalPads(comm, device, extra_words=self.n_chunks * (2 if self.slots_policy == 2 else 1),
+                               timeout_s=timeout_s)
         self.ring_epoch = 0
         self.step_epoch = 0
         self.launches = 0
@@ -91,7 +99,8 @@ class AllreduceMiniapp:
             self.va = SymmetricBuffer(comm, self.nbytes, device)
             self.vc = SymmetricBuffer(comm, self.nbytes, device)
             if algo == "ring":
-                self.slots = SymmetricBuffer(comm, self.nbytes * max(self.world - 1, 1), device, zero=False)
+                n_slots = 2 if self.slots_policy == 2 else max(self.world - 1, 1)
+                self.slots = SymmetricBuffer(comm, self.nbytes * n_slots, device, zero=False)
             if algo in ("ring-unfused", "ring-nccl"):
                 self.vb = SymmetricBuffer(comm, self.nbytes, device)
 
@@ -133,7 +142,9 @@ class AllreduceMiniapp:
             C.ring_allreduce(va, vc, self.slots.local_ptr, self.slots.ptrs[self.right],
                              pads.chunk_word(me), pads.chunk_word(self.right), P, self.n,
                              self.chunk_elems, self.ring_epoch, pads.timeout_ns, pads.status_ptr,
-                             self.dtype, self.ctas, self.device, st)
+                             self.dtype, self.ctas, self.device, st, self.slots_policy,
+                             pads.chunk_word(me, self.n_chunks) if self.slots_policy == 2 else 0,
+                             pads.chunk_word(self.left, self.n_chunks) if self.slots_policy == 2 else 0)
             self.ring_epoch += P
             self.launches += 1
         elif self.algo == "twoshot":
@@ -250,6 +261,8 @@ def main(argv: Optional[List[str]] = None) -> int:
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--slots", type=int, default=0, choices=(0, 2),
+                    help="fused ring: 2 = two receive slots + per-chunk acks (VA/VB double buffer); default world-1 slots")
     args = ap.parse_args(argv)
     comm = Comm()
     from ..parallel.tile_mapping import selected_device
@@ -266,7 +279,7 @@ def main(argv: Optional[List[str]] = None) -> int:
                 print(f"# NVLS unavailable ({e}); using two-shot P2P", flush=True)
             algo = "twoshot"
     if app is None:
-        app = AllreduceMiniapp(comm, device, args.p, args.type, algo)
+        app = AllreduceMiniapp(comm, device, args.p, args.type, algo, slots=args.slots)
     res = app.run(args.iters, args.warmup)
     if comm.rank == 0:
         row = res.row()
