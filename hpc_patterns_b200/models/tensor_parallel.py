@@ -111,18 +111,31 @@ class ColumnParallelLinear(_FusedLinearBase):
         self._per_launch = self.C.allgather_gemm_chunks_per_block(k, chunk_bytes)
         self._block_bytes = rows * k * 2
 
+    def wait_readers(self) -> None:
+        """Enqueue a wait until every peer has finished pulling this rank's rows of the previous step.  Call it
+        before writing new activations into ``self.x_local`` (``forward(x_local)`` does)."""
+        if self.epoch > 0 and self.world > 1:
+            self.C.wait_flags(self.pads.word(self.rank, self.C.PAD_DONE), self.world, self.epoch,
+                              self.pads.timeout_ns, self.pads.status_ptr, self._stream)
+            self.launches += 1
+
     def forward(self, x_local: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """x_local: this rank's bf16 rows ``[M/P, K]`` (or None when they were written into ``self.x_local``)."""
+        """x_local: this rank's bf16 rows ``[M/P, K]`` (or None when they were written into ``self.x_local``
+        after ``wait_readers()``)."""
         st = self._stream
         if x_local is not None:
+            self.wait_readers()
             self.x_local.copy_(x_local)
-        # Every rank's rows are final, and nobody still reads the rows of the previous step.
-        self.pads.device_barrier(st)
+        self.pads.device_barrier(st)  # every rank's rows are final before anybody pulls them
+        self.epoch += 1
         src = [self.a.ptrs[q] + q * self._block_bytes for q in range(self.world)]
-        allgather_gemm(self.a_full, src, self.w, self.y, self.rank, ready=self.ready,
-                       ready_base=self.ready_base & 0xFFFFFFFF, chunk_bytes=self.chunk_bytes,
-                       timeout_ns=self.pads.timeout_ns, status=self.pads.status_ptr, ctas=self.ctas, stream=st,
-                       cluster=self.cluster)
+        done = [self.pads.word(q, self.C.PAD_DONE + self.rank) for q in range(self.world)]
+        ctas = allgather_gemm(self.a_full, src, self.w, self.y, self.rank, ready=self.ready,
+                              ready_base=self.ready_base & 0xFFFFFFFF, chunk_bytes=self.chunk_bytes,
+                              done_flags=done, done_epoch=self.epoch, ticket=self.pads.ticket_ptr,
+                              ticket_base=self.pads.ticket_issued & 0xFFFFFFFF, timeout_ns=self.pads.timeout_ns,
+                              status=self.pads.status_ptr, ctas=self.ctas, stream=st, cluster=self.cluster)
+        self.pads.advance_tickets(ctas)
         if self.world > 1:
             self.ready_base += self._per_launch
         self.launches += 2
