@@ -97,6 +97,13 @@ __global__ void __launch_bounds__(kThreads, 1)
   gemm_persistent<kCluster, kStages>(map_a, map_b, g.tiles_m, g.tiles_n, g.k, ReduceScatterPolicy{g});
 }
 
+// cluster = 3: the same policy on the 2-SM UMMA tile loop (tcgen05.mma.cta_group::2, one 256x256 tile per CTA pair).
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm_reduce_scatter_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                   const __grid_constant__ RsDev g) {
+  gemm_persistent_2sm(map_a, map_b, g.tiles_m, g.tiles_n, g.k, ReduceScatterPolicy{g});
+}
+
 // ------------------------------------------------------------------ all-gather -> GEMM ----
 struct AgDev {
   unsigned char* a_full;                      // local bf16 [M, K]
@@ -204,6 +211,12 @@ __global__ void __launch_bounds__(kThreads, 1)
   gemm_persistent<kCluster, kStages>(map_a, map_b, g.tiles_m, g.tiles_n, g.k, AllGatherPolicy{g});
 }
 
+__global__ void __launch_bounds__(kThreads, 1)
+    allgather_gemm_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                              const __grid_constant__ AgDev g) {
+  gemm_persistent_2sm(map_a, map_b, g.tiles_m, g.tiles_n, g.k, AllGatherPolicy{g});
+}
+
 // ------------------------------------------------------------------ wait for P flags ----
 __global__ void __launch_bounds__(32) wait_flags_kernel(const uint32_t* flags, int count, uint32_t epoch,
                                                         uint64_t timeout_ns, uint32_t* status) {
@@ -261,8 +274,8 @@ void launch_wait_flags(const uint32_t* flags, int count, uint32_t epoch, uint64_
 int launch_gemm_reduce_scatter(const GemmRsArgs& args, int ctas, int device, cudaStream_t stream, int cluster) {
   const Shape s = check_shape("gemm_reduce_scatter", args.m, args.n, args.k, args.world);
   HPCP_REQUIRE(args.rank >= 0 && args.rank < args.world, "gemm_reduce_scatter: bad rank");
-  HPCP_REQUIRE(cluster >= 0 && cluster <= 2, "gemm_reduce_scatter: cluster must be 0 (auto), 1 or 2");
-  HPCP_REQUIRE(cluster != 2 || s.pairable, "gemm_reduce_scatter: cluster=2 needs an even number of tile rows per shard");
+  HPCP_REQUIRE(cluster >= 0 && cluster <= 3, "gemm_reduce_scatter: cluster must be 0 (auto), 1, 2 or 3 (2-SM UMMA)");
+  HPCP_REQUIRE(cluster < 2 || s.pairable, "gemm_reduce_scatter: cluster=2/3 needs an even number of tile rows per shard");
   HPCP_REQUIRE((reinterpret_cast<uintptr_t>(args.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(args.b) & 15) == 0,
                "gemm_reduce_scatter: operands must be 16-byte aligned");
   RsDev g{};
@@ -296,8 +309,14 @@ int launch_gemm_reduce_scatter(const GemmRsArgs& args, int ctas, int device, cud
     HPCP_CUDA(cudaGetLastError());
     return grid;
   }
+  HPCP_REQUIRE(cluster != 3 || grid >= 2, "gemm_reduce_scatter: cluster=3 needs at least two CTAs");
   grid &= ~1;
   const CUtensorMap map_b = make_kmajor_map(args.b, args.n, args.k, kBN / 2);
+  if (cluster == 3) {
+    HPCP_ENABLE_SMEM(gemm_reduce_scatter_2sm_kernel, gemm_2sm_smem_bytes(0));
+    launch_pairs(gemm_reduce_scatter_2sm_kernel, grid, gemm_2sm_smem_bytes(0), stream, map_a, map_b, g);
+    return grid;
+  }
   HPCP_ENABLE_SMEM(gemm_reduce_scatter_kernel<2>, smem);
   launch_pairs(gemm_reduce_scatter_kernel<2>, grid, smem, stream, map_a, map_b, g);
   return grid;
@@ -311,8 +330,8 @@ uint32_t allgather_gemm_chunks_per_block(int k, int chunk_bytes) {
 int launch_allgather_gemm(const AgGemmArgs& args, int ctas, int device, cudaStream_t stream, int cluster) {
   const Shape s = check_shape("allgather_gemm", args.m, args.n, args.k, args.world);
   HPCP_REQUIRE(args.rank >= 0 && args.rank < args.world, "allgather_gemm: bad rank");
-  HPCP_REQUIRE(cluster >= 0 && cluster <= 2, "allgather_gemm: cluster must be 0 (auto), 1 or 2");
-  HPCP_REQUIRE(cluster != 2 || s.pairable, "allgather_gemm: cluster=2 needs an even number of tile rows per shard");
+  HPCP_REQUIRE(cluster >= 0 && cluster <= 3, "allgather_gemm: cluster must be 0 (auto), 1, 2 or 3 (2-SM UMMA)");
+  HPCP_REQUIRE(cluster < 2 || s.pairable, "allgather_gemm: cluster=2/3 needs an even number of tile rows per shard");
   HPCP_REQUIRE(args.a_full != nullptr && args.b != nullptr && args.c != nullptr, "allgather_gemm: null operand");
   HPCP_REQUIRE((reinterpret_cast<uintptr_t>(args.a_full) & 127) == 0 && (reinterpret_cast<uintptr_t>(args.b) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(args.c) & 15) == 0,
@@ -366,8 +385,16 @@ int launch_allgather_gemm(const AgGemmArgs& args, int ctas, int device, cudaStre
     HPCP_CUDA(cudaGetLastError());
     return grid;
   }
+  HPCP_REQUIRE(cluster != 3 || grid >= 2, "allgather_gemm: cluster=3 needs at least two CTAs");
   grid &= ~1;
   const CUtensorMap map_b = make_kmajor_map(args.b, args.n, args.k, kBN / 2);
+  if (cluster == 3) {
+    constexpr size_t smem2 = gemm_2sm_smem_bytes(kGatherSmemBytes);
+    static_assert(smem2 + 1024 <= 227 * 1024, "2-SM stages + epilogue staging + gather ring must fit in 227 KiB");
+    HPCP_ENABLE_SMEM(allgather_gemm_2sm_kernel, smem2);
+    launch_pairs(allgather_gemm_2sm_kernel, grid, smem2, stream, map_a, map_b, g);
+    return grid;
+  }
   HPCP_ENABLE_SMEM(allgather_gemm_kernel<2>, smem);
   launch_pairs(allgather_gemm_kernel<2>, grid, smem, stream, map_a, map_b, g);
   return grid;

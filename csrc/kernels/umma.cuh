@@ -443,6 +443,170 @@ __device__ __forceinline__ void gemm_persistent(const CUtensorMap& map_a, const 
   policy.finish();
 }
 
+// ---------------------------------------------------------------- 2-SM UMMA variant ----
+// The CTA pair of a cluster computes ONE 256x256 tile with tcgen05.mma.cta_group::2 (M=256, N=256, K=16):
+// CTA r owns rows [128r, 128r+128) of the tile (its A rows, its TMEM accumulator, its epilogue) and stages
+// only HALF of the B tile, so a pipeline stage is 32 KiB per CTA instead of 48 (6 stages instead of 4) and
+// each SM reads 8 instead of 12 KiB of operands from its shared memory per MMA.  Only the leader (rank 0)
+// issues MMAs and owns the pair-wide barriers:
+//   full[s]       (leader)  2 arrivals: leader's expect_tx(2 x 32 KiB) + the peer's remote arrive; the TMA
+//                           loads of BOTH CTAs complete_tx on it
+//   empty[s]      (each)    1 arrival: tcgen05.commit multicast to the pair
+//   tmem_full[a]  (each)    1 arrival: tcgen05.commit multicast to the pair
+//   tmem_empty[a] (leader)  2 x 4 arrivals: the epilogue warps of both CTAs
+constexpr int kStages2 = 6;
+constexpr uint32_t kStageBytes2 = kABytes + kBBytes / 2;  // 32 KiB per CTA
+constexpr size_t gemm_2sm_smem_bytes(uint32_t aux_bytes) {
+  return static_cast<size_t>(kStages2) * kStageBytes2 + kEpiWarps * kEpiWarpBytes + aux_bytes + 1024;
+}
+
+// Same Policy contract as gemm_persistent (coords() is called with tile = 2 * item + cluster rank: the two tiles of
+// an item must be vertically adjacent with the same n_blk, the leader's on top).
+template <class Policy>
+__device__ __forceinline__ void gemm_persistent_2sm(const CUtensorMap& map_a, const CUtensorMap& map_b, int tiles_m,
+                                                    int tiles_n, int k, const Policy& policy) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kStages2];
+  __shared__ __align__(8) uint64_t empty_bar[kStages2];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* epi_smem = smem + static_cast<size_t>(kStages2) * kStageBytes2;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = k / kBK;
+  const int crank = static_cast<int>(cluster_cta_rank());
+  const bool leader = crank == 0;
+  // Work items are 256x256 tiles = vertically adjacent pairs (2p, 2p+1) of the grouped rasterisation.
+  const int first_item = static_cast<int>(blockIdx.x) / 2;
+  const int item_stride = static_cast<int>(gridDim.x) / 2;
+  const int num_items = tiles_m * tiles_n / 2;
+
+  cluster_sync_all();  // both CTAs of the pair are resident before the pair-wide TMEM allocation
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < kStages2; ++s) {
+      ptx::mbar_init(&full_bar[s], 2);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], 2 * kEpiWarps);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {  // the same warp of both CTAs allocates collectively
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     ptx::smem_u32(&tmem_base_s)),
+                 "r"(static_cast<uint32_t>(kTmemCols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the partner's barriers and TMEM exist before anything remote touches them
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = first_item; item < num_items; item += item_stride) {
+      int m_blk, n_blk;
+      policy.coords(item * 2 + crank, &m_blk, &n_blk);
+      const int m0 = m_blk * kBM;
+      const int n0 = n_blk * kBN + crank * (kBN / 2);  // my half of the shared B tile
+      policy.a_rows_ready(m_blk);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait_or_trap(&empty_bar[stage], phase ^ 1, false, kWaitEmpty, stage);  // slot released by the pair's MMA
+        if (lane == 0) {
+          unsigned char* sa = smem + static_cast<size_t>(stage) * kStageBytes2;
+          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes2);
+          tma_load_2d_2sm(sa, &map_a, kb * kBK, m0, &full_bar[stage]);
+          tma_load_2d_2sm(sa + kABytes, &map_b, kb * kBK, n0, &full_bar[stage]);
+          if (!leader) mbar_arrive_cluster(&full_bar[stage], 0);
+        }
+        __syncwarp();
+        if (++stage == kStages2) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    const uint32_t idesc = make_idesc(2 * kBM, kBN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int local_tile = 0;
+    for (int item = first_item; item < num_items; item += item_stride, ++local_tile) {
+      const int acc = local_tile & 1;
+      const uint32_t acc_phase = static_cast<uint32_t>(local_tile >> 1) & 1;
+      mbar_wait_or_trap(&tmem_empty_bar[acc], acc_phase ^ 1, true, kWaitTmemEmpty, acc);  // both epilogues drained it
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kBN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait_or_trap(&full_bar[stage], phase, true, kWaitFull, stage);  // both CTAs' TMA bytes landed
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = ptx::smem_u32(smem + static_cast<size_t>(stage) * kStageBytes2);
+          const uint64_t desc_a = make_smem_desc(sa);
+          const uint64_t desc_b = make_smem_desc(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint64_t adv = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+            umma_bf16_2sm(tmem_d, desc_a + adv, desc_b + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage], static_cast<uint16_t>(0x3));  // frees the slot in both CTAs
+          if (kb == num_kb - 1) umma_commit_2sm(&tmem_full_bar[acc], static_cast<uint16_t>(0x3));
+        }
+        __syncwarp();
+        if (++stage == kStages2) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (Policy::kHasAuxWarp && warp == 3) {
+    policy.aux_warp(lane, epi_smem + static_cast<size_t>(kEpiWarps) * kEpiWarpBytes);
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int ew = warp - 4;
+    float* stage_buf = reinterpret_cast<float*>(epi_smem + static_cast<size_t>(ew) * kEpiWarpBytes);
+    int local_tile = 0;
+    for (int item = first_item; item < num_items; item += item_stride, ++local_tile) {
+      const int acc = local_tile & 1;
+      const uint32_t acc_phase = static_cast<uint32_t>(local_tile >> 1) & 1;
+      int m_blk, n_blk;
+      policy.coords(item * 2 + crank, &m_blk, &n_blk);
+      mbar_wait_or_trap(&tmem_full_bar[acc], acc_phase, false, kWaitTmemFull, acc);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * kBN) + (static_cast<uint32_t>(ew * 32) << 16);
+      policy.epilogue(taddr, stage_buf, m_blk * kBM, n_blk * kBN, ew, lane);
+      tc_fence_before();
+      if (lane == 0) {  // the leader's MMA warp may overwrite this accumulator in both CTAs
+        if (leader)
+          ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        else
+          mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA may free TMEM or retire while its partner can still touch it
+  if (warp == 2)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(kTmemCols))
+                 : "memory");
+  policy.finish();
+}
+
 inline PFN_cuTensorMapEncodeTiled gemm_tensor_map_encoder() {
   static PFN_cuTensorMapEncodeTiled fn = nullptr;
   static std::once_flag once;

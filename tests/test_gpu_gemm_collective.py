@@ -4,6 +4,8 @@ Written on a machine without a GPU and NOT RUN YET: opt-in (``HPCP_EXPERIMENTAL=
 cannot stop the regular suite; run them under ``timeout``.  One-GPU tests emulate P ranks with P launches on the
 same device ("virtual ranks": every rank's shard / row block is a separate buffer, peer pointers are plain local
 pointers), which exercises the whole tile order, ownership, gather and signalling logic without NVLink.
+``cluster=3`` cases run the same policies on the 2-SM UMMA tile loop (``tcgen05.mma.cta_group::2``), itself not yet
+validated: run ``-k "not 3]"``-style selections first if it fails (scripts/gpu_next_round.sh does).
 """
 import os
 import subprocess
@@ -38,7 +40,8 @@ def _dyadic(shape, dev, seed):
 
 @pytest.mark.parametrize("world,m,n,k,cluster", [(1, 256, 256, 64, 1), (2, 512, 512, 256, 1), (2, 1024, 512, 128, 2),
                                                  (4, 2048, 1024, 256, 0), (8, 2048, 768, 512, 0),
-                                                 (4, 8192, 2048, 256, 0)])
+                                                 (4, 8192, 2048, 256, 0), (2, 1024, 512, 128, 3),
+                                                 (4, 4096, 1024, 512, 3)])
 def test_gemm_reduce_scatter_virtual_ranks(native, dev, world, m, n, k, cluster):
     """Every virtual rank adds its partial product into the owners' shards; the shards must hold the exact sum
     (operands are small dyadic rationals, so fp32 addition is exact in any order)."""
@@ -71,7 +74,8 @@ def test_gemm_reduce_scatter_virtual_ranks(native, dev, world, m, n, k, cluster)
 
 @pytest.mark.parametrize("world,m,n,k,cluster,chunk", [(1, 256, 256, 64, 1, 0), (2, 512, 256, 128, 1, 0),
                                                        (2, 1024, 512, 256, 2, 2048), (4, 2048, 512, 512, 0, 0),
-                                                       (8, 2048, 256, 1024, 0, 1024), (4, 4096, 1024, 2048, 0, 4096)])
+                                                       (8, 2048, 256, 1024, 0, 1024), (4, 4096, 1024, 2048, 0, 4096),
+                                                       (2, 1024, 512, 256, 3, 0), (4, 4096, 512, 1024, 3, 2048)])
 @pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
 def test_allgather_gemm_virtual_ranks(native, dev, world, m, n, k, cluster, chunk, out_dtype):
     """Every virtual rank gathers the other ranks' row blocks while it multiplies; its C must equal the product
