@@ -355,8 +355,9 @@ PYBIND11_MODULE(_C, m) {
       "gemm_reduce_scatter",
       [](uintptr_t a, uintptr_t b, const std::vector<uintptr_t>& shards, const std::vector<uintptr_t>& done_flags,
          uint32_t done_epoch, uintptr_t ticket, uint32_t ticket_base, int rank, int m_, int n, int k, int ctas,
-         int device, uintptr_t stream, int cluster) {
+         int device, uintptr_t stream, int cluster, uintptr_t c_multicast) {
         GemmRsArgs args;
+        args.c_multicast = as_ptr<float>(c_multicast);
         if (shards.empty() || shards.size() > static_cast<size_t>(kApiMaxRanks))
           throw std::invalid_argument("gemm_reduce_scatter: 1..16 shard pointers");
         if (!done_flags.empty() && done_flags.size() != shards.size())
@@ -380,8 +381,9 @@ PYBIND11_MODULE(_C, m) {
       py::arg("a"), py::arg("b"), py::arg("shards"), py::arg("done_flags") = std::vector<uintptr_t>(),
       py::arg("done_epoch") = 0, py::arg("ticket") = 0, py::arg("ticket_base") = 0, py::arg("rank") = 0, py::arg("m"),
       py::arg("n"), py::arg("k"), py::arg("ctas") = 0, py::arg("device") = 0, py::arg("stream") = 0,
-      py::arg("cluster") = 0,
-      "tcgen05 GEMM whose epilogue adds every tile into the owner's fp32 shard over NVLink (GEMM -> reduce-scatter).");
+      py::arg("cluster") = 0, py::arg("c_multicast") = 0,
+      "tcgen05 GEMM whose epilogue adds every tile into the owner's fp32 shard over NVLink (GEMM -> reduce-scatter), "
+      "or, with c_multicast, into every rank's copy through the NVSwitch (GEMM -> all-reduce).");
   // Tile / gather orderings of the tensor-core kernels (kernels/tile_order.h), exposed for the CPU tests.
   m.def("gemm_tile_coords", [](int tile, int tiles_m, int tiles_n) {
     int mb = 0, nb = 0;

@@ -248,6 +248,13 @@ __device__ __forceinline__ void multimem_st_f32x4(void* mc_ptr, const float4& v)
                "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
+// In-switch reduction INTO memory: one 16-byte request, the switch adds it into every bound GPU's copy
+// (an all-reduce contribution that leaves the sender once).
+__device__ __forceinline__ void multimem_red_add_f32x4(void* mc_ptr, const float4& v) {
+  asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc_ptr), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ void multimem_st_b32(void* mc_ptr, uint32_t v) {
   asm volatile("multimem.st.relaxed.sys.global.b32 [%0], %1;" ::"l"(mc_ptr), "r"(v) : "memory");
 }

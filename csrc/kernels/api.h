@@ -159,6 +159,10 @@ struct GemmRsArgs {
   const void* a = nullptr;                          // bf16 [M, K_r], K-major
   const void* b = nullptr;                          // bf16 [N, K_r], K-major
   float* shard[kApiMaxRanks] = {nullptr};           // peer-mapped: every rank's fp32 [M/world, N]
+  // GEMM -> all-reduce through the switch instead: when set, `shard` is ignored and every tile is added with
+  // multimem.red.add.v4.f32 into this NVLS multicast mapping of a full fp32 [M, N] buffer that exists (zeroed) on
+  // every rank — each rank's partial product leaves its GPU exactly once and all ranks end up with the whole sum.
+  float* c_multicast = nullptr;
   uint32_t* done_flag[kApiMaxRanks] = {nullptr};    // word on rank q written by THIS rank (may be null)
   uint32_t done_epoch = 0;
   uint32_t* ticket = nullptr;                       // rank-local CTA ticket counter (needed iff any done_flag)

@@ -7,6 +7,11 @@
 //                            work on the next tile.  When a rank's last tile is out it publishes its arrival
 //                            epoch on every owner.  Stock pattern: cuBLAS GEMM, then ncclReduceScatter.
 //
+//   GEMM -> all-reduce       same partial products, but every rank wants the whole sum: the epilogue issues
+//   (K-gemm-ar, NVLS)        multimem.red.add.v4.f32 on the multicast mapping of C, the NVSwitch adds the segment
+//                            into all P copies.  M*N*4 bytes leave each GPU once (a ring reduce-scatter +
+//                            all-gather moves 2(P-1)/P of that and needs two passes).  Stock: cuBLAS + ncclAllReduce.
+//
 //   all-gather -> GEMM       every rank holds a row block A_r[M/P,K] and needs C = A[M,K] . B_r[N,K]^T.  Warp 3
 //   (K-ag-gemm)              of every CTA (idle in a plain GEMM) is a gather engine: TMA bulk copies pull 4 KiB
 //                            pieces of the peers' row blocks over NVLink through a small smem ring into the
@@ -48,6 +53,7 @@ constexpr int kMaxGatherBufs = 8;
 // ------------------------------------------------------------------ GEMM -> reduce-scatter ----
 struct RsDev {
   float* shard[kApiMaxRanks];         // peer-mapped: owner q's fp32 [M/P, N]
+  float* c_multicast;                 // all-reduce mode: NVLS multicast mapping of fp32 [M, N]; else null
   uint32_t* done_flag[kApiMaxRanks];  // word on rank q that this rank publishes at the end (may be null)
   uint32_t done_epoch;
   uint32_t* ticket;
@@ -89,6 +95,41 @@ struct ReduceScatterPolicy {
       last_cta_publish_all(g.ticket, g.ticket_base + gridDim.x, g.done_flag, g.world, g.done_epoch);
   }
 };
+
+// All-reduce flavour: every rank adds every tile of its partial product into the multicast mapping.  The walk
+// starts a 1/P-th of the tile list further for every rank (whole pairs), so the P ranks reduce into P different
+// regions of C at any moment instead of queueing on the same lines of the switch.
+struct AllReducePolicy {
+  static constexpr bool kHasAuxWarp = false;
+  const RsDev& g;
+  __device__ __forceinline__ void coords(int tile, int* m_blk, int* n_blk) const {
+    const int num_tiles = g.tiles_m * g.tiles_n;
+    const int rot = 2 * static_cast<int>(static_cast<long long>(num_tiles / 2) * g.rank / g.world);
+    int t = tile + rot;
+    if (t >= num_tiles) t -= num_tiles;
+    tile_coords(t, g.tiles_m, g.tiles_n, m_blk, n_blk);
+  }
+  __device__ __forceinline__ void a_rows_ready(int) const {}
+  __device__ __forceinline__ void epilogue(uint32_t taddr, float* stage_buf, int m0, int n0, int ew, int lane) const {
+    float* base = g.c_multicast + static_cast<size_t>(m0 + ew * 32) * g.n + n0;
+    const size_t ld = static_cast<size_t>(g.n);
+    epilogue_fp32_segments(taddr, stage_buf, lane, [&](int row, int col, const float4& v) {
+      ptx::multimem_red_add_f32x4(base + row * ld + col, v);
+    });
+  }
+  __device__ __forceinline__ void aux_warp(int, unsigned char*) const {}
+  __device__ __forceinline__ void finish() const {
+    if (g.ticket != nullptr)
+      last_cta_publish_all(g.ticket, g.ticket_base + gridDim.x, g.done_flag, g.world, g.done_epoch);
+  }
+};
+
+template <int kCluster>
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm_allreduce_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                          const __grid_constant__ RsDev g) {
+  gemm_persistent<kCluster, kStages>(map_a, map_b, g.tiles_m, g.tiles_n, g.k, AllReducePolicy{g});
+}
 
 template <int kCluster>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -279,8 +320,13 @@ int launch_gemm_reduce_scatter(const GemmRsArgs& args, int ctas, int device, cud
   HPCP_REQUIRE((reinterpret_cast<uintptr_t>(args.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(args.b) & 15) == 0,
                "gemm_reduce_scatter: operands must be 16-byte aligned");
   RsDev g{};
+  const bool all_reduce = args.c_multicast != nullptr;
+  HPCP_REQUIRE(!all_reduce || (reinterpret_cast<uintptr_t>(args.c_multicast) & 15) == 0,
+               "gemm_reduce_scatter: the multicast mapping must be 16-byte aligned");
+  HPCP_REQUIRE(!all_reduce || cluster != 3, "gemm_reduce_scatter: the all-reduce flavour has no 2-SM variant yet");
+  g.c_multicast = args.c_multicast;
   for (int q = 0; q < args.world; ++q) {
-    HPCP_REQUIRE(args.shard[q] != nullptr && (reinterpret_cast<uintptr_t>(args.shard[q]) & 15) == 0,
+    HPCP_REQUIRE(all_reduce || (args.shard[q] != nullptr && (reinterpret_cast<uintptr_t>(args.shard[q]) & 15) == 0),
                  "gemm_reduce_scatter: every rank's shard pointer is needed (16-byte aligned)");
     g.shard[q] = args.shard[q];
     g.done_flag[q] = args.done_flag[q];
@@ -297,15 +343,23 @@ int launch_gemm_reduce_scatter(const GemmRsArgs& args, int ctas, int device, cud
   g.tiles_m = s.tiles_m;
   g.tiles_n = s.tiles_n;
   g.shard_tiles_m = s.shard_tiles_m;
-  const bool pairs = cluster != 1 && s.pairable;
+  // Pairs of the all-reduce flavour walk the whole C in the grouped order: the usual whole-matrix condition.
+  const bool pairable = all_reduce ? (s.tiles_m % 2 == 0 && (s.tiles_m % kGroupM) % 2 == 0) : s.pairable;
+  HPCP_REQUIRE(cluster != 2 || pairable, "gemm_reduce_scatter: cluster=2 needs an even number of tile rows per group");
+  const bool pairs = cluster != 1 && pairable;
   const CUtensorMap map_a = make_kmajor_map(args.a, args.m, args.k, kBM);
   const int tiles = s.tiles_m * s.tiles_n;
   int grid = std::min(tiles, ctas > 0 ? ctas : device_sm_count(device));
   constexpr size_t smem = gemm_smem_bytes<kStages>(0);
   if (!pairs || grid < 2) {
     const CUtensorMap map_b = make_kmajor_map(args.b, args.n, args.k, kBN);
-    HPCP_ENABLE_SMEM(gemm_reduce_scatter_kernel<1>, smem);
-    gemm_reduce_scatter_kernel<1><<<grid, kThreads, smem, stream>>>(map_a, map_b, g);
+    if (all_reduce) {
+      HPCP_ENABLE_SMEM(gemm_allreduce_kernel<1>, smem);
+      gemm_allreduce_kernel<1><<<grid, kThreads, smem, stream>>>(map_a, map_b, g);
+    } else {
+      HPCP_ENABLE_SMEM(gemm_reduce_scatter_kernel<1>, smem);
+      gemm_reduce_scatter_kernel<1><<<grid, kThreads, smem, stream>>>(map_a, map_b, g);
+    }
     HPCP_CUDA(cudaGetLastError());
     return grid;
   }
@@ -315,6 +369,11 @@ int launch_gemm_reduce_scatter(const GemmRsArgs& args, int ctas, int device, cud
   if (cluster == 3) {
     HPCP_ENABLE_SMEM(gemm_reduce_scatter_2sm_kernel, gemm_2sm_smem_bytes(0));
     launch_pairs(gemm_reduce_scatter_2sm_kernel, grid, gemm_2sm_smem_bytes(0), stream, map_a, map_b, g);
+    return grid;
+  }
+  if (all_reduce) {
+    HPCP_ENABLE_SMEM(gemm_allreduce_kernel<2>, smem);
+    launch_pairs(gemm_allreduce_kernel<2>, grid, smem, stream, map_a, map_b, g);
     return grid;
   }
   HPCP_ENABLE_SMEM(gemm_reduce_scatter_kernel<2>, smem);

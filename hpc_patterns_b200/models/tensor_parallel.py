@@ -46,30 +46,51 @@ class _FusedLinearBase:
 
 
 class RowParallelLinear(_FusedLinearBase):
-    """``y_shard[M/P, N] = sum_r x_r[M, K_r] @ w_r[N, K_r].T`` restricted to this rank's rows."""
+    """``y = sum_r x_r[M, K_r] @ w_r[N, K_r].T``; ``reduce="scatter"``: every rank gets its ``[M/P, N]`` rows of the
+    sum (adds into the owners' shards over NVLink); ``reduce="all"``: every rank gets the whole ``[M, N]`` sum, added
+    into all copies by the NVSwitch (``multimem.red`` on the multicast mapping; needs NVLS, world >= 2)."""
 
     def __init__(self, comm: Comm, device: int, m: int, n: int, k_local: int, cluster: int = 0, ctas: int = 0,
-                 timeout_s: float = 30.0):
+                 timeout_s: float = 30.0, reduce: str = "scatter"):
         super().__init__(comm, device, timeout_s)
         if m % (128 * self.world) or n % 256 or k_local % 64:
             raise ValueError("M, N, K_local must be multiples of 128*world, 256, 64")
+        if reduce not in ("scatter", "all"):
+            raise ValueError("reduce must be 'scatter' or 'all'")
         self.m, self.n, self.k = m, n, k_local
-        self.cluster, self.ctas = cluster, ctas
+        self.cluster, self.ctas, self.reduce = cluster, ctas, reduce
+        self.w = torch.empty(n, k_local, device=f"cuda:{device}", dtype=torch.bfloat16)
+        self._symm = None
+        self._mc = 0
+        if reduce == "all":
+            import torch.distributed._symmetric_memory as symm
+
+            if self.world < 2:
+                raise RuntimeError("reduce='all' goes through the NVSwitch multicast mapping: needs >= 2 GPUs")
+            t = symm.empty(m * n, dtype=torch.float32, device=torch.device("cuda", device))
+            hdl = symm.rendezvous(t, dist.group.WORLD)
+            self._mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            if self._mc == 0:
+                raise RuntimeError("torch symmetric memory reports no multicast support on this system")
+            self._symm = (t, hdl)
+            self.shard = None
+            self.y = t.view(m, n)
+            return
         self.shard = SymmetricBuffer(comm, (m // self.world) * n * 4, device, zero=True)
         self.y = self.shard.tensor(torch.float32).view(m // self.world, n)
-        self.w = torch.empty(n, k_local, device=f"cuda:{device}", dtype=torch.bfloat16)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """x: bf16 ``[M, K_local]``.  Returns this rank's rows of the reduced output (a view of the symmetric shard,
         valid until the next forward)."""
         st = self._stream
         self.epoch += 1
-        self.C.memset_async(self.shard.local_ptr, 0, self.shard.nbytes, st)
-        self.pads.device_barrier(st)  # every shard is zero before anybody adds into it
+        self.C.memset_async(self.y.data_ptr(), 0, self.y.numel() * 4, st)
+        self.pads.device_barrier(st)  # every copy / shard is zero before anybody adds into it
         done = [self.pads.word(q, self.C.PAD_DONE + self.rank) for q in range(self.world)]
-        ctas = gemm_reduce_scatter(x, self.w, self.shard.ptrs, self.rank, done_flags=done, done_epoch=self.epoch,
+        shards = self.shard.ptrs if self.shard is not None else [0] * self.world
+        ctas = gemm_reduce_scatter(x, self.w, shards, self.rank, done_flags=done, done_epoch=self.epoch,
                                    ticket=self.pads.ticket_ptr, ticket_base=self.pads.ticket_issued & 0xFFFFFFFF,
-                                   ctas=self.ctas, stream=st, cluster=self.cluster)
+                                   ctas=self.ctas, stream=st, cluster=self.cluster, c_multicast=self._mc)
         self.pads.advance_tickets(ctas)
         self.C.wait_flags(self.pads.word(self.rank, self.C.PAD_DONE), self.world, self.epoch, self.pads.timeout_ns,
                           self.pads.status_ptr, st)
@@ -77,16 +98,21 @@ class RowParallelLinear(_FusedLinearBase):
         return self.y
 
     def stock_forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """cuBLAS GEMM + NCCL reduce_scatter (fp32), the stock pattern."""
+        """cuBLAS GEMM + NCCL reduce_scatter / all_reduce (fp32), the stock pattern."""
         full = x.float() @ self.w.float().t() if x.device.type == "cpu" else torch.matmul(x, self.w.t()).float()
         if self.world == 1:
+            return full
+        if self.reduce == "all":
+            dist.all_reduce(full)
             return full
         out = out if out is not None else torch.empty(self.m // self.world, self.n, device=x.device)
         dist.reduce_scatter_tensor(out, full)
         return out
 
     def close(self) -> None:
-        self.shard.close()
+        if self.shard is not None:
+            self.shard.close()
+        self._symm = None
         self.pads.close()
 
 

@@ -2,6 +2,7 @@
 """Tensor-parallel linear layers: fused kernels vs the stock pattern, N ranks (torchrun) or 1 GPU.
 
   row-parallel     y = reduce_scatter(x_r @ W_r.T)   K-gemm-rs  vs  cuBLAS matmul + NCCL reduce_scatter
+                   y = all_reduce(x_r @ W_r.T)       K-gemm-ar (multimem.red through the switch)  vs  + NCCL all_reduce
   column-parallel  y = all_gather(x_r) @ W_r.T       K-ag-gemm  vs  NCCL all_gather + cuBLAS matmul
 
 `--check` compares both fused layers with the stock result on exactly representable operands (exact equality),
@@ -84,6 +85,29 @@ def main() -> int:
                            "nvlink_GBps_per_gpu": round(args.m * args.n * 4 * (P - 1) / P / (t_fused * 1e6), 1)}
     row.close()
 
+    # ---- row-parallel with an all-reduce through the switch (NVLS) -------------------------------
+    if P > 1:
+        try:
+            ar = RowParallelLinear(comm, dev, args.m, args.n, k_local, cluster=args.cluster, reduce="all")
+        except RuntimeError as e:  # no multicast support on this system
+            ar = None
+            out["row_parallel_allreduce"] = {"unavailable": str(e)[:120]}
+        if ar is not None:
+            ar.w.copy_(dyadic((args.n, k_local), device, 200 + comm.rank))
+            if args.check:
+                y = ar.forward(x).clone()
+                ref = ar.stock_forward(x)
+                torch.cuda.synchronize(dev)
+                ar.check()
+                out["row_parallel_allreduce_exact"] = bool(comm.min(float(torch.equal(y, ref))) == 1.0)
+            t_fused = timed(lambda: ar.forward(x), comm, dev, args.steps)
+            t_stock = timed(lambda: ar.stock_forward(x), comm, dev, args.steps)
+            ar.check()
+            out["row_parallel_allreduce"] = {"fused_ms": round(t_fused, 4), "stock_ms": round(t_stock, 4),
+                                             "speedup": round(t_stock / t_fused, 3),
+                                             "nvlink_out_GBps_per_gpu": round(args.m * args.n * 4 / (t_fused * 1e6), 1)}
+            ar.close()
+
     # ---- column-parallel: rows of x are sharded and gathered, N is sharded -------------------------
     n_local = args.n // P
     col = ColumnParallelLinear(comm, dev, args.m, n_local, args.k, out_dtype=torch.bfloat16, cluster=args.cluster,
@@ -107,7 +131,8 @@ def main() -> int:
     col.close()
     if comm.rank == 0:
         print(json.dumps(out), flush=True)
-    ok = (not args.check) or (out["row_parallel_exact"] and out["column_parallel_exact"])
+    ok = (not args.check) or (out["row_parallel_exact"] and out["column_parallel_exact"] and
+                              out.get("row_parallel_allreduce_exact", True))
     comm.close()
     return 0 if ok else 1
 

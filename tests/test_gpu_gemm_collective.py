@@ -138,3 +138,4 @@ def test_tensor_parallel_layers_torchrun():
     p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout + p.stderr
     assert '"row_parallel_exact": true' in p.stdout and '"column_parallel_exact": true' in p.stdout
+    assert '"row_parallel_allreduce_exact": false' not in p.stdout      # absent when the box has no NVLS multicast
