@@ -384,6 +384,38 @@ PYBIND11_MODULE(_C, m) {
       py::arg("cluster") = 0, py::arg("c_multicast") = 0,
       "tcgen05 GEMM whose epilogue adds every tile into the owner's fp32 shard over NVLink (GEMM -> reduce-scatter), "
       "or, with c_multicast, into every rank's copy through the NVSwitch (GEMM -> all-reduce).");
+  m.def(
+      "gemm_all_to_all",
+      [](uintptr_t a, uintptr_t b, const std::vector<uintptr_t>& recv, bool out_bf16,
+         const std::vector<uintptr_t>& done_flags, uint32_t done_epoch, uintptr_t ticket, uint32_t ticket_base, int rank,
+         int m_, int n, int k, int ctas, int device, uintptr_t stream, int cluster) {
+        GemmA2aArgs args;
+        if (recv.empty() || recv.size() > static_cast<size_t>(kApiMaxRanks))
+          throw std::invalid_argument("gemm_all_to_all: 1..16 receive buffers");
+        if (!done_flags.empty() && done_flags.size() != recv.size())
+          throw std::invalid_argument("gemm_all_to_all: done_flags must be empty or one per rank");
+        args.a = as_ptr<const void>(a);
+        args.b = as_ptr<const void>(b);
+        args.world = static_cast<int>(recv.size());
+        for (int q = 0; q < args.world; ++q) {
+          args.recv[q] = as_ptr<void>(recv[q]);
+          args.done_flag[q] = done_flags.empty() ? nullptr : as_ptr<uint32_t>(done_flags[q]);
+        }
+        args.out_bf16 = out_bf16;
+        args.done_epoch = done_epoch;
+        args.ticket = as_ptr<uint32_t>(ticket);
+        args.ticket_base = ticket_base;
+        args.rank = rank;
+        args.m = m_;
+        args.n = n;
+        args.k = k;
+        return launch_gemm_all_to_all(args, ctas, device, as_stream(stream), cluster);
+      },
+      py::arg("a"), py::arg("b"), py::arg("recv"), py::arg("out_bf16") = false,
+      py::arg("done_flags") = std::vector<uintptr_t>(), py::arg("done_epoch") = 0, py::arg("ticket") = 0,
+      py::arg("ticket_base") = 0, py::arg("rank") = 0, py::arg("m"), py::arg("n"), py::arg("k"), py::arg("ctas") = 0,
+      py::arg("device") = 0, py::arg("stream") = 0, py::arg("cluster") = 0,
+      "tcgen05 GEMM whose epilogue stores row block q of the result into rank q's receive buffer (GEMM -> all-to-all).");
   // Tile / gather orderings of the tensor-core kernels (kernels/tile_order.h), exposed for the CPU tests.
   m.def("gemm_tile_coords", [](int tile, int tiles_m, int tiles_n) {
     int mb = 0, nb = 0;

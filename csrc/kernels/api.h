@@ -172,6 +172,22 @@ struct GemmRsArgs {
 };
 int launch_gemm_reduce_scatter(const GemmRsArgs& args, int ctas, int device, cudaStream_t stream, int cluster = 0);
 
+// GEMM -> all-to-all: C_r = A_r[M,K] . B_r[N,K]^T, row block q of C_r goes to rank q: every tile is stored (fp32 or
+// bf16) straight into slot `rank` of rank q's receive buffer [world, M/world, N]; done flags as above.
+struct GemmA2aArgs {
+  const void* a = nullptr;
+  const void* b = nullptr;
+  void* recv[kApiMaxRanks] = {nullptr};             // peer-mapped: every rank's receive buffer
+  bool out_bf16 = false;
+  uint32_t* done_flag[kApiMaxRanks] = {nullptr};
+  uint32_t done_epoch = 0;
+  uint32_t* ticket = nullptr;
+  uint32_t ticket_base = 0;
+  int rank = 0, world = 1;
+  int m = 0, n = 0, k = 0;
+};
+int launch_gemm_all_to_all(const GemmA2aArgs& args, int ctas, int device, cudaStream_t stream, int cluster = 0);
+
 // All-gather -> GEMM (column-parallel layer on row-sharded activations): C[M,N] = A[M,K] . B_r[N,K]^T where rank q
 // holds rows [q*M/world, (q+1)*M/world) of A.  One gather thread per CTA pulls the peers' row blocks over NVLink
 // with TMA bulk copies into a_full and counts arrivals per 128-row block in `ready`; a tile's loads wait for its

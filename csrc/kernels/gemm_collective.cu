@@ -12,6 +12,10 @@
 //                            into all P copies.  M*N*4 bytes leave each GPU once (a ring reduce-scatter +
 //                            all-gather moves 2(P-1)/P of that and needs two passes).  Stock: cuBLAS + ncclAllReduce.
 //
+//   GEMM -> all-to-all       row block q of C_r = A_r . B_r^T belongs to rank q (expert outputs going home, a
+//   (K-gemm-a2a)             Ulysses head/sequence swap): the epilogue stores every tile straight into slot r of
+//                            rank q's receive buffer [P, M/P, N] over NVLink.  Stock: cuBLAS + ncclAllToAll.
+//
 //   all-gather -> GEMM       every rank holds a row block A_r[M/P,K] and needs C = A[M,K] . B_r[N,K]^T.  Warp 3
 //   (K-ag-gemm)              of every CTA (idle in a plain GEMM) is a gather engine: TMA bulk copies pull 4 KiB
 //                            pieces of the peers' row blocks over NVLink through a small smem ring into the
@@ -136,6 +140,55 @@ __global__ void __launch_bounds__(kThreads, 1)
     gemm_reduce_scatter_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                                const __grid_constant__ RsDev g) {
   gemm_persistent<kCluster, kStages>(map_a, map_b, g.tiles_m, g.tiles_n, g.k, ReduceScatterPolicy{g});
+}
+
+// ------------------------------------------------------------------ GEMM -> all-to-all ----
+struct A2aDev {
+  unsigned char* recv[kApiMaxRanks];  // peer-mapped: rank q's receive buffer [P, M/P, N] (fp32 or bf16)
+  uint32_t* done_flag[kApiMaxRanks];
+  uint32_t done_epoch;
+  uint32_t* ticket;
+  uint32_t ticket_base;
+  int out_bf16;
+  int rank, world;
+  int n, k;
+  int tiles_m, tiles_n;
+  int shard_tiles_m;
+};
+
+struct AllToAllPolicy {
+  static constexpr bool kHasAuxWarp = false;
+  const A2aDev& g;
+  // What the shared store epilogue needs: one destination (the owner's slot for this rank), row length, type.
+  struct Out {
+    void* c_local;
+    void* c_peer;
+    int out_bf16;
+    int n;
+  };
+  __device__ __forceinline__ void coords(int tile, int* m_blk, int* n_blk) const {
+    shard_coords(tile, g.rank, g.world, 1, g.shard_tiles_m, g.tiles_n, m_blk, n_blk);  // the neighbour's rows first
+  }
+  __device__ __forceinline__ void a_rows_ready(int) const {}
+  __device__ __forceinline__ void epilogue(uint32_t taddr, float* stage_buf, int m0, int n0, int ew, int lane) const {
+    const int owner = (m0 / kBM) / g.shard_tiles_m;
+    const size_t shard_rows = static_cast<size_t>(g.shard_tiles_m) * kBM;
+    const size_t elem = g.out_bf16 ? 2 : 4;
+    const Out out{nullptr, g.recv[owner] + static_cast<size_t>(g.rank) * shard_rows * g.n * elem, g.out_bf16, g.n};
+    epilogue_store_tile(out, taddr, stage_buf, m0 - owner * static_cast<int>(shard_rows), n0, ew, lane);
+  }
+  __device__ __forceinline__ void aux_warp(int, unsigned char*) const {}
+  __device__ __forceinline__ void finish() const {
+    if (g.ticket != nullptr)
+      last_cta_publish_all(g.ticket, g.ticket_base + gridDim.x, g.done_flag, g.world, g.done_epoch);
+  }
+};
+
+template <int kCluster>
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm_all_to_all_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                           const __grid_constant__ A2aDev g) {
+  gemm_persistent<kCluster, kStages>(map_a, map_b, g.tiles_m, g.tiles_n, g.k, AllToAllPolicy{g});
 }
 
 // cluster = 3: the same policy on the 2-SM UMMA tile loop (tcgen05.mma.cta_group::2, one 256x256 tile per CTA pair).
@@ -378,6 +431,50 @@ int launch_gemm_reduce_scatter(const GemmRsArgs& args, int ctas, int device, cud
   }
   HPCP_ENABLE_SMEM(gemm_reduce_scatter_kernel<2>, smem);
   launch_pairs(gemm_reduce_scatter_kernel<2>, grid, smem, stream, map_a, map_b, g);
+  return grid;
+}
+
+int launch_gemm_all_to_all(const GemmA2aArgs& args, int ctas, int device, cudaStream_t stream, int cluster) {
+  const Shape s = check_shape("gemm_all_to_all", args.m, args.n, args.k, args.world);
+  HPCP_REQUIRE(args.rank >= 0 && args.rank < args.world, "gemm_all_to_all: bad rank");
+  HPCP_REQUIRE(cluster >= 0 && cluster <= 2, "gemm_all_to_all: cluster must be 0 (auto), 1 or 2");
+  HPCP_REQUIRE(cluster != 2 || s.pairable, "gemm_all_to_all: cluster=2 needs an even number of tile rows per shard");
+  HPCP_REQUIRE((reinterpret_cast<uintptr_t>(args.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(args.b) & 15) == 0,
+               "gemm_all_to_all: operands must be 16-byte aligned");
+  A2aDev g{};
+  for (int q = 0; q < args.world; ++q) {
+    HPCP_REQUIRE(args.recv[q] != nullptr && (reinterpret_cast<uintptr_t>(args.recv[q]) & 15) == 0,
+                 "gemm_all_to_all: every rank's receive buffer is needed (16-byte aligned)");
+    g.recv[q] = static_cast<unsigned char*>(args.recv[q]);
+    g.done_flag[q] = args.done_flag[q];
+    HPCP_REQUIRE(args.done_flag[q] == nullptr || args.ticket != nullptr, "gemm_all_to_all: a signal needs a ticket counter");
+  }
+  g.done_epoch = args.done_epoch;
+  g.ticket = args.ticket;
+  g.ticket_base = args.ticket_base;
+  g.out_bf16 = args.out_bf16 ? 1 : 0;
+  g.rank = args.rank;
+  g.world = args.world;
+  g.n = args.n;
+  g.k = args.k;
+  g.tiles_m = s.tiles_m;
+  g.tiles_n = s.tiles_n;
+  g.shard_tiles_m = s.shard_tiles_m;
+  const bool pairs = cluster != 1 && s.pairable;
+  const CUtensorMap map_a = make_kmajor_map(args.a, args.m, args.k, kBM);
+  int grid = std::min(s.tiles_m * s.tiles_n, ctas > 0 ? ctas : device_sm_count(device));
+  constexpr size_t smem = gemm_smem_bytes<kStages>(0);
+  if (!pairs || grid < 2) {
+    const CUtensorMap map_b = make_kmajor_map(args.b, args.n, args.k, kBN);
+    HPCP_ENABLE_SMEM(gemm_all_to_all_kernel<1>, smem);
+    gemm_all_to_all_kernel<1><<<grid, kThreads, smem, stream>>>(map_a, map_b, g);
+    HPCP_CUDA(cudaGetLastError());
+    return grid;
+  }
+  grid &= ~1;
+  const CUtensorMap map_b = make_kmajor_map(args.b, args.n, args.k, kBN / 2);
+  HPCP_ENABLE_SMEM(gemm_all_to_all_kernel<2>, smem);
+  launch_pairs(gemm_all_to_all_kernel<2>, grid, smem, stream, map_a, map_b, g);
   return grid;
 }
 

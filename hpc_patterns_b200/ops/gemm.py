@@ -82,6 +82,30 @@ def gemm_reduce_scatter(a: torch.Tensor, b: torch.Tensor, shards: Sequence[PtrLi
                                         current_stream(dev) if stream is None else stream, cluster, int(c_multicast))
 
 
+def gemm_all_to_all(a: torch.Tensor, b: torch.Tensor, recv: Sequence[PtrLike], rank: int, *,
+                    out_dtype: torch.dtype = torch.float32, done_flags: Sequence[int] = (), done_epoch: int = 0,
+                    ticket: int = 0, ticket_base: int = 0, ctas: int = 0, stream: Optional[int] = None,
+                    cluster: int = 0) -> int:
+    """K-gemm-a2a: ``C_r = A[M,K] @ B[N,K].T``; row block q of ``C_r`` (``M/world`` rows) is stored by the epilogue
+    into slot ``rank`` of ``recv[q]`` (``[world, M/world, N]`` of ``out_dtype``, peer-mapped pointers or local
+    tensors).  The all-to-all of expert outputs going home / a Ulysses swap, fused into the producing GEMM."""
+    _check_operands(a, b)
+    world = len(recv)
+    m, k = a.shape
+    n = b.shape[0]
+    if m % (128 * world) or n % 256 or k % 64:
+        raise ValueError("M, N, K must be multiples of 128*world, 256, 64")
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("out_dtype must be float32 or bfloat16")
+    for r in recv:
+        if isinstance(r, torch.Tensor) and (r.dtype != out_dtype or r.numel() != m * n):
+            raise ValueError("every receive buffer must be [world, M/world, N] of out_dtype")
+    dev = a.device.index
+    return native().gemm_all_to_all(ptr(a), ptr(b), [ptr(r) for r in recv], out_dtype == torch.bfloat16,
+                                    [int(f) for f in done_flags], done_epoch, ticket, ticket_base, rank, m, n, k, ctas,
+                                    dev, current_stream(dev) if stream is None else stream, cluster)
+
+
 def allgather_gemm(a_full: torch.Tensor, a_src: Sequence[PtrLike], b: torch.Tensor, c: torch.Tensor, rank: int, *,
                    ready: PtrLike = 0, ready_base: int = 0, chunk_bytes: int = 0, done_flags: Sequence[int] = (),
                    done_epoch: int = 0, ticket: int = 0, ticket_base: int = 0, timeout_ns: int = 0, status: int = 0,

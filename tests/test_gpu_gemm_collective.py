@@ -72,6 +72,26 @@ def test_gemm_reduce_scatter_virtual_ranks(native, dev, world, m, n, k, cluster)
             assert pads[q][native.PAD_DONE:native.PAD_DONE + world].tolist() == [epoch] * world
 
 
+@pytest.mark.parametrize("world,m,n,k,cluster", [(1, 128, 256, 64, 1), (2, 512, 256, 128, 1), (4, 2048, 512, 256, 0),
+                                                 (8, 2048, 768, 128, 2)])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_gemm_all_to_all_virtual_ranks(native, dev, world, m, n, k, cluster, out_dtype):
+    """recv[q][r] must hold row block q of rank r's product."""
+    from hpc_patterns_b200.ops.gemm import gemm_all_to_all, gemm_reference
+
+    rows = m // world
+    a = [_dyadic((m, k), dev, 20 + r) for r in range(world)]
+    b = [_dyadic((n, k), dev, 60 + r) for r in range(world)]
+    recv = [torch.full((world, rows, n), float("nan"), device=dev, dtype=out_dtype) for _ in range(world)]
+    for r in range(world):
+        gemm_all_to_all(a[r], b[r], recv, r, out_dtype=out_dtype, cluster=cluster)
+    torch.cuda.synchronize()
+    for r in range(world):
+        ref = gemm_reference(a[r], b[r]).to(out_dtype)
+        for q in range(world):
+            assert torch.equal(recv[q][r], ref[q * rows:(q + 1) * rows]), (q, r)
+
+
 @pytest.mark.parametrize("world,m,n,k,cluster,chunk", [(1, 256, 256, 64, 1, 0), (2, 512, 256, 128, 1, 0),
                                                        (2, 1024, 512, 256, 2, 2048), (4, 2048, 512, 512, 0, 0),
                                                        (8, 2048, 256, 1024, 0, 1024), (4, 4096, 1024, 2048, 0, 4096),
