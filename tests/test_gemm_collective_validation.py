@@ -1,0 +1,61 @@
+"""Argument validation of the fused collective GEMMs — runs without a GPU (every check fires before any CUDA call)."""
+import pytest
+import torch
+
+import hpc_patterns_b200
+from hpc_patterns_b200.ops.gemm import allgather_gemm, gemm_all_to_all, gemm_reduce_scatter
+
+
+def _bf16(*shape):
+    return torch.zeros(*shape, dtype=torch.bfloat16)
+
+
+def test_python_wrappers_reject_bad_operands():
+    with pytest.raises(TypeError):
+        gemm_reduce_scatter(torch.zeros(256, 64), _bf16(256, 64), [0, 0], 0)
+    with pytest.raises(ValueError, match="multiples"):
+        gemm_reduce_scatter(_bf16(128, 64), _bf16(256, 64), [0, 0], 0)          # M not a multiple of 128 * world
+    with pytest.raises(ValueError, match="shard"):
+        gemm_reduce_scatter(_bf16(256, 64), _bf16(256, 64), [torch.zeros(64, 256), torch.zeros(128, 256)], 0)
+    with pytest.raises(ValueError, match="c must be"):
+        allgather_gemm(_bf16(256, 64), [0, 0], _bf16(256, 64), torch.zeros(256, 128), 0)
+    with pytest.raises(ValueError, match="ready"):
+        allgather_gemm(_bf16(256, 64), [0, 0], _bf16(256, 64), torch.zeros(256, 256), 0,
+                       ready=torch.zeros(1, dtype=torch.int32))
+    with pytest.raises(ValueError, match="receive buffer"):
+        gemm_all_to_all(_bf16(256, 64), _bf16(256, 64), [torch.zeros(2, 128, 128), torch.zeros(2, 128, 256)], 0)
+    with pytest.raises(TypeError):
+        gemm_all_to_all(_bf16(256, 64), _bf16(256, 64), [0, 0], 0, out_dtype=torch.float16)
+
+
+def test_native_launchers_reject_bad_shapes_and_modes():
+    C = hpc_patterns_b200.native()
+    with pytest.raises(RuntimeError, match="multiple of 128 \\* world"):
+        C.gemm_reduce_scatter(16, 16, [16, 16, 16], m=256, n=256, k=64)
+    with pytest.raises(RuntimeError, match="cluster"):
+        C.gemm_reduce_scatter(16, 16, [16, 16], m=256, n=256, k=64, cluster=7)
+    with pytest.raises(RuntimeError, match="even number of tile rows"):
+        C.gemm_reduce_scatter(16, 16, [16, 16], m=256, n=256, k=64, cluster=2)   # one tile row per shard
+    with pytest.raises(RuntimeError, match="shard pointer"):
+        C.gemm_reduce_scatter(16, 16, [16, 0], m=256, n=256, k=64)
+    with pytest.raises(RuntimeError, match="ticket"):
+        C.gemm_reduce_scatter(16, 16, [16, 16], done_flags=[16, 16], m=256, n=256, k=64)
+    with pytest.raises(RuntimeError, match="chunk_bytes"):
+        C.allgather_gemm(128, [128, 128], 16, 16, ready=16, chunk_bytes=3000, m=256, n=256, k=64)
+    with pytest.raises(RuntimeError, match="arrival counters"):
+        C.allgather_gemm(128, [128, 128], 16, 16, m=256, n=256, k=64)
+    with pytest.raises(RuntimeError, match="row block pointer"):
+        C.allgather_gemm(128, [0, 0], 16, 16, ready=16, rank=0, m=256, n=256, k=64)
+    with pytest.raises(RuntimeError, match="receive buffer"):
+        C.gemm_all_to_all(16, 16, [16, 0], m=256, n=256, k=64)
+    with pytest.raises((RuntimeError, ValueError)):
+        C.gemm_all_to_all(16, 16, [], m=256, n=256, k=64)
+    assert C.allgather_gemm_chunks_per_block(64, 0) == 4 and C.allgather_gemm_chunks_per_block(8192, 2048) == 1024
+
+
+def test_ring_rejects_inconsistent_slot_policy():
+    C = hpc_patterns_b200.native()
+    with pytest.raises(RuntimeError, match="n_slots"):
+        C.ring_allreduce(16, 16, 16, 16, 16, 16, world=8, n=1024, n_slots=3)
+    with pytest.raises(RuntimeError, match="ack words"):
+        C.ring_allreduce(16, 16, 16, 16, 16, 16, world=8, n=1024, n_slots=2)
