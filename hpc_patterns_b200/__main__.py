@@ -3,6 +3,7 @@
   concurency   compute-while-copy overlap benchmark (native driver in-process)
   peer2pear    P2P bandwidth, process-per-GPU (run under torchrun for >1 GPU)
   allreduce    allreduce miniapp, process-per-GPU (run under torchrun)
+  tp           tensor-parallel linear layers with the collective fused into the GEMM, vs cuBLAS + NCCL (torchrun)
   topology     fabric planes / rank->GPU mapping (JSON)
   tile-mapping per-rank launcher: <policy> <CVD|SET> cmd...
   parse        concurrency log -> SUCCESS/FAILURE tables
@@ -37,6 +38,9 @@ def main(argv=None) -> int:
         return m(rest)
     if prog == "allreduce":
         from .models.allreduce import main as m
+        return m(rest)
+    if prog == "tp":
+        from .models.tensor_parallel import main as m
         return m(rest)
     if prog == "topology":
         from . import native
