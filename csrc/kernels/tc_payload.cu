@@ -28,6 +28,7 @@
 
 #include "../common/cuda_check.h"
 #include "../common/ptx.cuh"
+#include "umma.cuh"
 
 namespace hpcp {
 
@@ -42,86 +43,16 @@ constexpr int kThreads = 192;
 constexpr uint32_t kABytes = kTileM * kTileK * 2;  // 16 KiB
 constexpr uint32_t kBBytes = kTileN * kTileK * 2;  // 32 KiB
 
-// ---- descriptors (bit layouts: PTX ISA "tcgen05 matrix / instruction descriptor") ----
-// Shared-memory matrix descriptor, K-major, SWIZZLE_128B: 8-row x 128-byte atoms, atoms
-// stacked every 1024 bytes (stride byte offset); leading byte offset unused for swizzled
-// K-major (encoded 1); descriptor version 1 (Blackwell); layout type 2 = SWIZZLE_128B.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);        // start address  [0,14)
-  d |= static_cast<uint64_t>(1) << 16;                            // LBO            [16,30)
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;                    // SBO            [32,46)
-  d |= static_cast<uint64_t>(1) << 46;                            // version        [46,48)
-  d |= static_cast<uint64_t>(2) << 61;                            // SWIZZLE_128B   [61,64)
-  return d;
-}
-// Instruction descriptor for kind::f16: D = f32, A = B = bf16, both K-major, M x N tile.
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) |                      // c_format = F32
-         (1u << 7) | (1u << 10) |         // a_format = b_format = BF16
-         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
-}
-
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y,
-                                            uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%2, %3}], [%4];" ::"r"(ptx::smem_u32(smem_dst)),
-      "l"(map), "r"(x), "r"(y), "r"(ptx::smem_u32(bar))
-      : "memory");
-}
-
-// Same load, multicast to every CTA of the cluster named in `cta_mask`: the tile lands at the same
-// shared-memory offset in each destination CTA and each destination's mbarrier (same offset) gets
-// the complete_tx — one L2 read feeds both SMs of the pair.
-__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* map, int x, int y,
-                                                      uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(ptx::smem_u32(smem_dst)),
-      "l"(map), "r"(x), "r"(y), "r"(ptx::smem_u32(bar)), "h"(cta_mask)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_cta_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   ptx::smem_u32(bar))
-               : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
-        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
-        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
-        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
+// Descriptors, TMA tensor loads and tcgen05 wrappers: umma.cuh (shared with the GEMM kernels).
+using umma::cluster_cta_rank;
+using umma::cluster_sync_all;
+using umma::make_idesc;
+using umma::make_smem_desc;
+using umma::tma_load_2d;
+using umma::tma_load_2d_multicast;
+using umma::tmem_ld_32x32b_x32;
+using umma::umma_bf16;
+using umma::umma_commit;
 
 // Dynamic smem (1024-aligned): A tile | B tile ; static smem: barriers + TMEM base.
 // kCluster == 2: launched as thread-block clusters of two CTAs that share the B tile — each CTA
@@ -228,28 +159,13 @@ __global__ void tc_fill_operands_kernel(__nv_bfloat16* a, __nv_bfloat16* b) {
   }
 }
 
-PFN_cuTensorMapEncodeTiled tensor_map_encoder() {
-  static PFN_cuTensorMapEncodeTiled fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
-    (void)cudaGetLastError();
-  });
-  HPCP_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available (driver too old?)");
-  return fn;
-}
-
 CUtensorMap make_operand_map(const void* base, int rows, int box_rows) {
   CUtensorMap map;
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kTileK), static_cast<cuuint64_t>(rows)};
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kTileK) * 2};
   const cuuint32_t box[2] = {static_cast<cuuint32_t>(kTileK), static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t elem_strides[2] = {1, 1};
-  const CUresult r = tensor_map_encoder()(
+  const CUresult r = umma::gemm_tensor_map_encoder()(
       &map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
       elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
       CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

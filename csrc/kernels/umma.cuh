@@ -28,15 +28,21 @@ constexpr uint32_t kBBytes = kBN * kBK * 2;             // 32 KiB
 constexpr int kStageRowWords = 36;                      // 32 payload floats + 4 pad (keeps float4 alignment)
 constexpr uint32_t kEpiWarpBytes = 32 * kStageRowWords * 4;  // 4608 B per epilogue warp
 
+// ---- descriptors (bit layouts: PTX ISA "tcgen05 matrix / instruction descriptor") ----
+// Shared-memory matrix descriptor, K-major, SWIZZLE_128B: 8-row x 128-byte atoms, atoms stacked every 1024 bytes
+// (stride byte offset); leading byte offset unused for swizzled K-major (encoded 1); descriptor version 1
+// (Blackwell); layout type 2 = SWIZZLE_128B.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);  // start address
-  d |= static_cast<uint64_t>(1) << 16;                      // LBO (unused for swizzled K-major)
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;              // SBO: 8 rows x 128 B
-  d |= static_cast<uint64_t>(1) << 46;                      // descriptor version (Blackwell)
-  d |= static_cast<uint64_t>(2) << 61;                      // SWIZZLE_128B
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);  // start address  [0,14)
+  d |= static_cast<uint64_t>(1) << 16;                      // LBO            [16,30)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;              // SBO            [32,46): 8 rows x 128 B
+  d |= static_cast<uint64_t>(1) << 46;                      // version        [46,48)
+  d |= static_cast<uint64_t>(2) << 61;                      // SWIZZLE_128B   [61,64)
   return d;
 }
+// Instruction descriptor for kind::f16: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at
+// [17,23), M >> 4 at [24,29).
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);  // D=f32, A=B=bf16, K-major both
