@@ -355,9 +355,10 @@ PYBIND11_MODULE(_C, m) {
       "gemm_reduce_scatter",
       [](uintptr_t a, uintptr_t b, const std::vector<uintptr_t>& shards, const std::vector<uintptr_t>& done_flags,
          uint32_t done_epoch, uintptr_t ticket, uint32_t ticket_base, int rank, int m_, int n, int k, int ctas,
-         int device, uintptr_t stream, int cluster, uintptr_t c_multicast) {
+         int device, uintptr_t stream, int cluster, uintptr_t c_multicast, bool out_bf16) {
         GemmRsArgs args;
         args.c_multicast = as_ptr<float>(c_multicast);
+        args.out_bf16 = out_bf16;
         if (shards.empty() || shards.size() > static_cast<size_t>(kApiMaxRanks))
           throw std::invalid_argument("gemm_reduce_scatter: 1..16 shard pointers");
         if (!done_flags.empty() && done_flags.size() != shards.size())
@@ -366,7 +367,7 @@ PYBIND11_MODULE(_C, m) {
         args.b = as_ptr<const void>(b);
         args.world = static_cast<int>(shards.size());
         for (int q = 0; q < args.world; ++q) {
-          args.shard[q] = as_ptr<float>(shards[q]);
+          args.shard[q] = as_ptr<void>(shards[q]);
           args.done_flag[q] = done_flags.empty() ? nullptr : as_ptr<uint32_t>(done_flags[q]);
         }
         args.done_epoch = done_epoch;
@@ -381,7 +382,7 @@ PYBIND11_MODULE(_C, m) {
       py::arg("a"), py::arg("b"), py::arg("shards"), py::arg("done_flags") = std::vector<uintptr_t>(),
       py::arg("done_epoch") = 0, py::arg("ticket") = 0, py::arg("ticket_base") = 0, py::arg("rank") = 0, py::arg("m"),
       py::arg("n"), py::arg("k"), py::arg("ctas") = 0, py::arg("device") = 0, py::arg("stream") = 0,
-      py::arg("cluster") = 0, py::arg("c_multicast") = 0,
+      py::arg("cluster") = 0, py::arg("c_multicast") = 0, py::arg("out_bf16") = false,
       "tcgen05 GEMM whose epilogue adds every tile into the owner's fp32 shard over NVLink (GEMM -> reduce-scatter), "
       "or, with c_multicast, into every rank's copy through the NVSwitch (GEMM -> all-reduce).");
   m.def(

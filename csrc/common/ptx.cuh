@@ -98,6 +98,13 @@ __device__ __forceinline__ void red_add_f32x4_sys(float* p, const float4& v) {
                : "memory");
 }
 
+// Same for 8 packed bf16 (REDG.E.ADD.BF16x8): half the NVLink bytes, every addition rounds to bf16.
+__device__ __forceinline__ void red_add_bf16x8_sys(void* p, const uint4& v) {
+  asm volatile("red.relaxed.sys.global.add.noftz.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
 // --------------------------------------------- 256-bit ld / st (sm_100+) ----
 // One LDG.256 / STG.256 per thread: a warp covers 1 KiB contiguous per access.
 struct alignas(32) U32x8 {

@@ -158,7 +158,9 @@ int launch_gemm_put(const void* a_bf16, const void* b_bf16, void* c_local, void*
 struct GemmRsArgs {
   const void* a = nullptr;                          // bf16 [M, K_r], K-major
   const void* b = nullptr;                          // bf16 [N, K_r], K-major
-  float* shard[kApiMaxRanks] = {nullptr};           // peer-mapped: every rank's fp32 [M/world, N]
+  void* shard[kApiMaxRanks] = {nullptr};            // peer-mapped: every rank's [M/world, N], fp32 (bf16 if out_bf16)
+  // bf16 shards: REDG.E.ADD.BF16x8 — half the NVLink bytes, but each of the P additions rounds to bf16.
+  bool out_bf16 = false;
   // GEMM -> all-reduce through the switch instead: when set, `shard` is ignored and every tile is added with
   // multimem.red.add.v4.f32 into this NVLS multicast mapping of a full fp32 [M, N] buffer that exists (zeroed) on
   // every rank — each rank's partial product leaves its GPU exactly once and all ranks end up with the whole sum.

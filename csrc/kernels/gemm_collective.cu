@@ -56,7 +56,8 @@ constexpr int kMaxGatherBufs = 8;
 
 // ------------------------------------------------------------------ GEMM -> reduce-scatter ----
 struct RsDev {
-  float* shard[kApiMaxRanks];         // peer-mapped: owner q's fp32 [M/P, N]
+  unsigned char* shard[kApiMaxRanks]; // peer-mapped: owner q's [M/P, N], fp32 (or bf16 when out_bf16)
+  int out_bf16;
   float* c_multicast;                 // all-reduce mode: NVLS multicast mapping of fp32 [M, N]; else null
   uint32_t* done_flag[kApiMaxRanks];  // word on rank q that this rank publishes at the end (may be null)
   uint32_t done_epoch;
@@ -87,11 +88,19 @@ struct ReduceScatterPolicy {
   __device__ __forceinline__ void epilogue(uint32_t taddr, float* stage_buf, int m0, int n0, int ew, int lane) const {
     const int owner = (m0 / kBM) / g.shard_tiles_m;
     const int row0 = m0 - owner * g.shard_tiles_m * kBM + ew * 32;  // first of this warp's rows inside the shard
-    float* base = g.shard[owner] + static_cast<size_t>(row0) * g.n + n0;
-    const size_t ld = static_cast<size_t>(g.n);
-    epilogue_fp32_segments(taddr, stage_buf, lane, [&](int row, int col, const float4& v) {
-      ptx::red_add_f32x4_sys(base + row * ld + col, v);
-    });
+    const size_t elem = g.out_bf16 ? 2 : 4;
+    unsigned char* base = g.shard[owner] + (static_cast<size_t>(row0) * g.n + n0) * elem;
+    const size_t ld = static_cast<size_t>(g.n) * elem;
+    if (g.out_bf16)
+      epilogue_segments(true, taddr, stage_buf, lane, [&](int row, int col, int byte, const uint4& v) {
+        ptx::red_add_bf16x8_sys(base + row * ld + col * 2 + byte, v);
+      });
+    else
+      epilogue_segments(false, taddr, stage_buf, lane, [&](int row, int col, int byte, const uint4& v) {
+        ptx::red_add_f32x4_sys(reinterpret_cast<float*>(base + row * ld + col * 4 + byte),
+                               make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z),
+                                           __uint_as_float(v.w)));
+      });
   }
   __device__ __forceinline__ void aux_warp(int, unsigned char*) const {}
   __device__ __forceinline__ void finish() const {
@@ -117,8 +126,10 @@ struct AllReducePolicy {
   __device__ __forceinline__ void epilogue(uint32_t taddr, float* stage_buf, int m0, int n0, int ew, int lane) const {
     float* base = g.c_multicast + static_cast<size_t>(m0 + ew * 32) * g.n + n0;
     const size_t ld = static_cast<size_t>(g.n);
-    epilogue_fp32_segments(taddr, stage_buf, lane, [&](int row, int col, const float4& v) {
-      ptx::multimem_red_add_f32x4(base + row * ld + col, v);
+    epilogue_segments(false, taddr, stage_buf, lane, [&](int row, int col, int byte, const uint4& v) {
+      ptx::multimem_red_add_f32x4(base + row * ld + col + byte / 4,
+                                  make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z),
+                                              __uint_as_float(v.w)));
     });
   }
   __device__ __forceinline__ void aux_warp(int, unsigned char*) const {}
@@ -378,10 +389,12 @@ int launch_gemm_reduce_scatter(const GemmRsArgs& args, int ctas, int device, cud
                "gemm_reduce_scatter: the multicast mapping must be 16-byte aligned");
   HPCP_REQUIRE(!all_reduce || cluster != 3, "gemm_reduce_scatter: the all-reduce flavour has no 2-SM variant yet");
   g.c_multicast = args.c_multicast;
+  HPCP_REQUIRE(!all_reduce || !args.out_bf16, "gemm_reduce_scatter: the all-reduce flavour accumulates in fp32");
+  g.out_bf16 = args.out_bf16 ? 1 : 0;
   for (int q = 0; q < args.world; ++q) {
     HPCP_REQUIRE(all_reduce || (args.shard[q] != nullptr && (reinterpret_cast<uintptr_t>(args.shard[q]) & 15) == 0),
                  "gemm_reduce_scatter: every rank's shard pointer is needed (16-byte aligned)");
-    g.shard[q] = args.shard[q];
+    g.shard[q] = static_cast<unsigned char*>(args.shard[q]);
     g.done_flag[q] = args.done_flag[q];
     HPCP_REQUIRE(args.done_flag[q] == nullptr || args.ticket != nullptr,
                  "gemm_reduce_scatter: a signal needs a ticket counter");

@@ -184,8 +184,59 @@ __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
-// Epilogue of one 128x256 accumulator (one epilogue warp = 32 accumulator rows): TMEM -> registers ->
-// padded smem transpose -> full 128-byte row segments to c_local and/or the peer.
+// Epilogue walk of one 128x256 accumulator (one epilogue warp = 32 accumulator rows): TMEM -> registers -> padded
+// smem transpose -> 16-byte pieces of full 128-byte row segments.  One round moves a 128-byte segment per row: 32
+// fp32 columns, or 64 bf16 columns (two TMEM loads, converted before staging), so whatever emit() does with a piece
+// (store, peer store, reduction) always happens in full 128-byte segments: 8 consecutive lanes = one segment, 4 rows
+// per instruction.  emit(row, col, byte, v): 16 bytes `v` of accumulator row `row` (0..31 inside this warp's rows)
+// that start `byte` bytes into the round's segment, whose first column is `col`.
+template <class Emit>
+__device__ __forceinline__ void epilogue_segments(bool out_bf16, uint32_t taddr, float* stage_buf, int lane, Emit emit) {
+  const int cols_per_round = out_bf16 ? 64 : 32;
+  unsigned char* stage_row = reinterpret_cast<unsigned char*>(stage_buf) + lane * (kStageRowWords * 4);
+  for (int col = 0; col < kBN; col += cols_per_round) {
+    if (out_bf16) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + col + half * 32, r);
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 pk;
+          __nv_bfloat162 t;
+          t = __floats2bfloat162_rn(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+          pk.x = *reinterpret_cast<uint32_t*>(&t);
+          t = __floats2bfloat162_rn(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          pk.y = *reinterpret_cast<uint32_t*>(&t);
+          t = __floats2bfloat162_rn(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
+          pk.z = *reinterpret_cast<uint32_t*>(&t);
+          t = __floats2bfloat162_rn(__uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
+          pk.w = *reinterpret_cast<uint32_t*>(&t);
+          *reinterpret_cast<uint4*>(stage_row + half * 64 + j * 2) = pk;
+        }
+      }
+    } else {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(taddr + col, r);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<uint4*>(stage_row + j * 4) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = it * 4 + (lane >> 3);
+      const int c16 = lane & 7;
+      const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(stage_buf) +
+                                                      row * (kStageRowWords * 4) + c16 * 16);
+      emit(row, col, c16 * 16, v);
+    }
+    __syncwarp();
+  }
+}
+
+// The plain epilogue: the same walk with the stores written out (kept in this explicit form on purpose: it is the
+// code of the GPU-validated gemm_put kernels, and the lambda form above does not compile to byte-identical SASS).
 // G: any struct with c_local, c_peer (either may be null), out_bf16 and n (the row length of C).
 template <class G>
 __device__ __forceinline__ void epilogue_store_tile(const G& g, uint32_t taddr, float* stage_buf, int m0,
@@ -237,32 +288,6 @@ __device__ __forceinline__ void epilogue_store_tile(const G& g, uint32_t taddr, 
         ptx::st_stream_v4(reinterpret_cast<uint4*>(static_cast<unsigned char*>(g.c_peer) + off), v);
       if (g.c_local != nullptr)
         *reinterpret_cast<uint4*>(static_cast<unsigned char*>(g.c_local) + off) = v;
-    }
-    __syncwarp();
-  }
-}
-
-
-// fp32-only form of the same walk for epilogues that do something else than store: emit(row, col, v) receives
-// 16 bytes = 4 consecutive fp32 columns [col, col+4) of accumulator row `row` (0..31 inside this warp's 32 rows);
-// consecutive lanes hold consecutive 16-byte pieces, 8 lanes = one full 128-byte row segment.
-template <class Emit>
-__device__ __forceinline__ void epilogue_fp32_segments(uint32_t taddr, float* stage_buf, int lane, Emit emit) {
-  unsigned char* stage_row = reinterpret_cast<unsigned char*>(stage_buf) + lane * (kStageRowWords * 4);
-  for (int col = 0; col < kBN; col += 32) {
-    uint32_t r[32];
-    tmem_ld_32x32b_x32(taddr + col, r);
-#pragma unroll
-    for (int j = 0; j < 32; j += 4)
-      *reinterpret_cast<uint4*>(stage_row + j * 4) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-    __syncwarp();
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int row = it * 4 + (lane >> 3);
-      const int c16 = lane & 7;
-      const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(stage_buf) +
-                                                        row * (kStageRowWords * 4) + c16 * 16);
-      emit(row, col + c16 * 4, v);
     }
     __syncwarp();
   }

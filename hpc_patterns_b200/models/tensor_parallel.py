@@ -51,8 +51,14 @@ class RowParallelLinear(_FusedLinearBase):
     into all copies by the NVSwitch (``multimem.red`` on the multicast mapping; needs NVLS, world >= 2)."""
 
     def __init__(self, comm: Comm, device: int, m: int, n: int, k_local: int, cluster: int = 0, ctas: int = 0,
-                 timeout_s: float = 30.0, reduce: str = "scatter"):
+                 timeout_s: float = 30.0, reduce: str = "scatter", out_dtype: torch.dtype = torch.float32):
+        """``out_dtype=torch.bfloat16`` (reduce-scatter only): bf16 shards, half the NVLink bytes, every addition
+        rounds to bf16."""
         super().__init__(comm, device, timeout_s)
+        if out_dtype not in (torch.float32, torch.bfloat16) or (reduce == "all" and out_dtype != torch.float32):
+            raise ValueError("out_dtype: float32, or bfloat16 with reduce='scatter'")
+        self.out_dtype = out_dtype
+        self.y_elem = 2 if out_dtype == torch.bfloat16 else 4
         if m % (128 * self.world) or n % 256 or k_local % 64:
             raise ValueError("M, N, K_local must be multiples of 128*world, 256, 64")
         if reduce not in ("scatter", "all"):
@@ -80,21 +86,22 @@ class RowParallelLinear(_FusedLinearBase):
             self.shard = None
             self.y = t.view(m, n)
             return
-        self.shard = SymmetricBuffer(comm, (m // self.world) * n * 4, device, zero=True)
-        self.y = self.shard.tensor(torch.float32).view(m // self.world, n)
+        self.shard = SymmetricBuffer(comm, (m // self.world) * n * self.y_elem, device, zero=True)
+        self.y = self.shard.tensor(out_dtype).view(m // self.world, n)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """x: bf16 ``[M, K_local]``.  Returns this rank's rows of the reduced output (a view of the symmetric shard,
         valid until the next forward)."""
         st = self._stream
         self.epoch += 1
-        self.C.memset_async(self.y.data_ptr(), 0, self.y.numel() * 4, st)
+        self.C.memset_async(self.y.data_ptr(), 0, self.y.numel() * self.y_elem, st)
         self.pads.device_barrier(st)  # every copy / shard is zero before anybody adds into it
         done = [self.pads.word(q, self.C.PAD_DONE + self.rank) for q in range(self.world)]
         shards = self.shard.ptrs if self.shard is not None else [0] * self.world
         ctas = gemm_reduce_scatter(x, self.w, shards, self.rank, done_flags=done, done_epoch=self.epoch,
                                    ticket=self.pads.ticket_ptr, ticket_base=self.pads.ticket_issued & 0xFFFFFFFF,
-                                   ctas=self.ctas, stream=st, cluster=self.cluster, c_multicast=self._mc)
+                                   ctas=self.ctas, stream=st, cluster=self.cluster, c_multicast=self._mc,
+                                   out_dtype=self.out_dtype)
         self.pads.advance_tickets(ctas)
         self.C.wait_flags(self.pads.word(self.rank, self.C.PAD_DONE), self.world, self.epoch, self.pads.timeout_ns,
                           self.pads.status_ptr, st)

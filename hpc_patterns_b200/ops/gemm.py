@@ -58,28 +58,33 @@ def _check_operands(a: torch.Tensor, b: torch.Tensor) -> None:
 
 def gemm_reduce_scatter(a: torch.Tensor, b: torch.Tensor, shards: Sequence[PtrLike], rank: int, *,
                         done_flags: Sequence[int] = (), done_epoch: int = 0, ticket: int = 0, ticket_base: int = 0,
-                        ctas: int = 0, stream: Optional[int] = None, cluster: int = 0, c_multicast: int = 0) -> int:
+                        ctas: int = 0, stream: Optional[int] = None, cluster: int = 0, c_multicast: int = 0,
+                        out_dtype: torch.dtype = torch.float32) -> int:
     """K-gemm-rs (csrc/kernels/gemm_collective.cu): ``A[M,K_r] @ B[N,K_r].T`` is this rank's partial sum; the
     epilogue adds every 128x256 tile into ``shards[owner]`` (fp32 ``[M/world, N]``, peer-mapped pointers or local
     tensors, one per rank, zeroed by their owners) with ``red.global.add.v4.f32`` over NVLink.  When
     ``done_flags`` (one word per rank) are given, the last CTA publishes ``done_epoch`` on all of them.
     ``c_multicast`` (the NVLS multicast address of a zeroed fp32 ``[M, N]`` buffer that exists on every rank) turns
     the step into GEMM -> all-reduce: every tile is added into all copies by the switch (``multimem.red``);
-    ``shards`` then only tells the world size.  Returns the number of CTAs launched (ticket bookkeeping)."""
+    ``shards`` then only tells the world size.  ``out_dtype=torch.bfloat16``: bf16 shards, ``REDG.E.ADD.BF16x8`` —
+    half the NVLink bytes, every one of the P additions rounds to bf16.  Returns the CTAs launched."""
     _check_operands(a, b)
     world = len(shards)
     m, k = a.shape
     n = b.shape[0]
     if m % (128 * world) or n % 256 or k % 64:
         raise ValueError("M, N, K must be multiples of 128*world, 256, 64")
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError("out_dtype must be float32 or bfloat16")
     for s in shards:
-        if not c_multicast and isinstance(s, torch.Tensor) and (s.dtype != torch.float32 or
+        if not c_multicast and isinstance(s, torch.Tensor) and (s.dtype != out_dtype or
                                                                   tuple(s.shape) != (m // world, n)):
-            raise ValueError("every shard must be fp32 [M/world, N]")
+            raise ValueError("every shard must be [M/world, N] of out_dtype")
     dev = a.device.index
     return native().gemm_reduce_scatter(ptr(a), ptr(b), [ptr(s) for s in shards], [int(f) for f in done_flags],
                                         done_epoch, ticket, ticket_base, rank, m, n, k, ctas, dev,
-                                        current_stream(dev) if stream is None else stream, cluster, int(c_multicast))
+                                        current_stream(dev) if stream is None else stream, cluster, int(c_multicast),
+                                        out_dtype == torch.bfloat16)
 
 
 def gemm_all_to_all(a: torch.Tensor, b: torch.Tensor, recv: Sequence[PtrLike], rank: int, *,

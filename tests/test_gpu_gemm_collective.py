@@ -72,6 +72,23 @@ def test_gemm_reduce_scatter_virtual_ranks(native, dev, world, m, n, k, cluster)
             assert pads[q][native.PAD_DONE:native.PAD_DONE + world].tolist() == [epoch] * world
 
 
+@pytest.mark.parametrize("world,m,n,k,cluster", [(2, 512, 256, 64, 1), (4, 2048, 512, 64, 0)])
+def test_gemm_reduce_scatter_bf16_shards(native, dev, world, m, n, k, cluster):
+    """bf16 shards (REDG.E.ADD.BF16x8).  Ternary operands and K = 64: every partial sum and every running total is an
+    integer of magnitude <= 256, exactly representable in bf16, so the result is exact in any order."""
+    from hpc_patterns_b200.ops.gemm import gemm_reduce_scatter, gemm_reference
+
+    g = torch.Generator(device=dev).manual_seed(3)
+    a = [torch.randint(-1, 2, (m, k), device=dev, generator=g).to(torch.bfloat16) for _ in range(world)]
+    b = [torch.randint(-1, 2, (n, k), device=dev, generator=g).to(torch.bfloat16) for _ in range(world)]
+    shards = [torch.zeros(m // world, n, device=dev, dtype=torch.bfloat16) for _ in range(world)]
+    for r in range(world):
+        gemm_reduce_scatter(a[r], b[r], shards, r, cluster=cluster, out_dtype=torch.bfloat16)
+    torch.cuda.synchronize()
+    ref = sum(gemm_reference(a[r], b[r]) for r in range(world))
+    assert torch.equal(torch.cat(shards, 0).float(), ref)
+
+
 @pytest.mark.parametrize("world,m,n,k,cluster", [(1, 128, 256, 64, 1), (2, 512, 256, 128, 1), (4, 2048, 512, 256, 0),
                                                  (8, 2048, 768, 128, 2)])
 @pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
