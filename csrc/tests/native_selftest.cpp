@@ -8,11 +8,15 @@
 #include <iostream>
 #include <stdexcept>
 #include <string>
+#include <set>
+#include <utility>
 #include <vector>
 
 #include "../common/dtype_traits.h"
 #include "../common/rank_runtime.h"
 #include "../concurency/driver.hpp"
+#include "../kernels/ring_order.h"
+#include "../kernels/tile_order.h"
 #include "../miniapps/devices.hpp"
 #include "../p2p/topology_core.hpp"
 
@@ -140,7 +144,57 @@ void test_driver_pure_functions() {
 
 }  // namespace
 
+// The orderings the tensor-core kernels and the ring kernel run on the device (host + device headers).
+void test_kernel_orderings() {
+  using namespace hpcp;
+  using namespace hpcp::umma;
+  for (int tiles_m : {1, 2, 7, 8, 16, 64})
+    for (int tiles_n : {1, 3, 32}) {
+      std::set<std::pair<int, int>> seen;
+      for (int t = 0; t < tiles_m * tiles_n; ++t) {
+        int mb = -1, nb = -1;
+        tile_coords(t, tiles_m, tiles_n, &mb, &nb);
+        CHECK(mb >= 0 && mb < tiles_m && nb >= 0 && nb < tiles_n);
+        seen.insert({mb, nb});
+      }
+      CHECK(static_cast<int>(seen.size()) == tiles_m * tiles_n);  // a bijection
+    }
+  // Shard-major order: rank r starts with the shard of rank r + first; all ranks are on different shards at any time.
+  const int world = 8, shard_tiles_m = 4, tiles_n = 3, per_shard = shard_tiles_m * tiles_n;
+  for (int first : {0, 1})
+    for (int t = 0; t < world * per_shard; t += 5) {
+      std::set<int> owners;
+      for (int r = 0; r < world; ++r) {
+        int mb = 0, nb = 0;
+        shard_coords(t, r, world, first, shard_tiles_m, tiles_n, &mb, &nb);
+        CHECK(mb / shard_tiles_m == (r + first + t / per_shard) % world);
+        owners.insert(mb / shard_tiles_m);
+      }
+      CHECK(static_cast<int>(owners.size()) == world);
+    }
+  // Gather pieces of the all-gather -> GEMM kernel: every remote byte exactly once, counted on the block it lands in.
+  const uint32_t cpb = 8, chunk = 4096;
+  const size_t block_bytes = static_cast<size_t>(cpb) * chunk;
+  std::set<size_t> dst;
+  for (size_t c = 0; c < static_cast<size_t>(world - 1) * shard_tiles_m * cpb; ++c) {
+    const GatherPiece p = gather_piece(c, 3, world, shard_tiles_m, cpb, chunk, block_bytes);
+    CHECK(p.peer != 3 && p.m_blk == static_cast<int>(p.dst_off / block_bytes));
+    CHECK(p.dst_off == static_cast<size_t>(p.peer) * shard_tiles_m * block_bytes + p.src_off);
+    dst.insert(p.dst_off);
+  }
+  CHECK(dst.size() == static_cast<size_t>(world - 1) * shard_tiles_m * cpb);
+  // Ring slots and acks: every ack that is waited for is published, and nothing else.
+  for (int P = 1; P <= 9; ++P)
+    for (int t = 0; t < P; ++t) {
+      if (t + 1 < P) CHECK(ring_waits_for_ack(t + 1, P) == ring_publishes_ack(t, P) || t == 0);
+      CHECK(!ring_waits_for_ack(t, P) || (t >= 2 && ring_forwards(t, P)));
+      CHECK(ring_src_slot(t + 1, true) == ring_fwd_slot(t, true));   // what hop t forwards is what hop t+1 reads
+      CHECK(ring_src_slot(t + 1, false) == ring_fwd_slot(t, false));
+    }
+}
+
 int main() {
+  test_kernel_orderings();
   test_rank_runtime();
   test_devices_and_dtypes();
   test_topology();
