@@ -16,6 +16,7 @@ from typing import Dict, Iterable, List
 NVLINK_NOMINAL_GBPS = 900.0
 NVLINK_MEASURED_GBPS = 770.0      # peer copy per direction, profiling recipe
 HBM_FALLBACK_GBPS = 6650.0
+BF16_FALLBACK_TFLOPS = 1600.0   # cuBLAS bf16, profiling recipe fallback
 
 
 def measured_hbm_gbps(root: str = ".") -> float:
@@ -24,6 +25,14 @@ def measured_hbm_gbps(root: str = ".") -> float:
             return float(json.load(f)["hbm_gbs"])
     except (OSError, KeyError, ValueError):
         return HBM_FALLBACK_GBPS
+
+
+def measured_bf16_tflops(root: str = ".") -> float:
+    try:
+        with open(os.path.join(root, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops"])
+    except (OSError, KeyError, ValueError):
+        return BF16_FALLBACK_TFLOPS
 
 
 def load_rows(paths: Iterable[str]) -> List[Dict]:
@@ -76,6 +85,48 @@ def concurency_table(rows: List[Dict]) -> str:
     return "\n".join(out)
 
 
+def tensor_parallel_table(rows: List[Dict], root: str = ".") -> str:
+    """Rows of ``python -m hpc_patterns_b200 tp`` (one JSON object per run: ranks, m, n, k and one sub-object per
+    layer).  The roofline of a fused layer is the slower of its GEMM at the measured cuBLAS rate and its bytes over
+    NVLink at the measured 770 GB/s per direction."""
+    peak = measured_bf16_tflops(root)
+    out = ["| layer | ranks | M | N | K | fused ms | stock ms (cuBLAS + NCCL) | speed-up | TFLOP/s per GPU | roofline ms "
+           "(tensor / NVLink) | fraction |", "|---|---|---|---|---|---|---|---|---|---|---|"]
+    for r in rows:
+        if "row_parallel" not in r and "column_parallel" not in r:
+            continue
+        P, m, n, k = r["ranks"], r["m"], r["n"], r["k"]
+        layers = (("row_parallel", 2.0 * m * n * (k // P), m * n * 4 * (P - 1) / P),
+                  ("row_parallel_allreduce", 2.0 * m * n * (k // P), m * n * 4 if P > 1 else 0),
+                  ("column_parallel", 2.0 * m * (n // P) * k, m * k * 2 * (P - 1) / P))
+        for name, flops, link_bytes in layers:
+            d = r.get(name)
+            if not isinstance(d, dict) or "fused_ms" not in d:
+                continue
+            t_tensor = flops / (peak * 1e9)
+            t_link = link_bytes / (NVLINK_MEASURED_GBPS * 1e6)
+            roof = max(t_tensor, t_link)
+            out.append(f"| {name}{' (chunk ' + str(r['chunk']) + ')' if 'chunk' in r else ''} | {P} | {m} | {n} | {k} | "
+                       f"{d['fused_ms']:.4f} | {d['stock_ms']:.4f} | {d['speedup']:.2f} | "
+                       f"{flops / d['fused_ms'] / 1e9:.0f} | {t_tensor:.3f} / {t_link:.3f} | {roof / d['fused_ms']:.2f} |")
+    return "\n".join(out)
+
+
+def gemm_table(rows: List[Dict], root: str = ".") -> str:
+    """Rows of scripts/gemm_put_bench.py."""
+    peak = measured_bf16_tflops(root)
+    out = ["| M | N | K | ranks | ours TFLOP/s | 2-SM UMMA | cuBLAS | ours / measured peak | fused GEMM->put ms | stock ms |",
+           "|---|---|---|---|---|---|---|---|---|---|"]
+    for r in rows:
+        if "gemm_tflops" not in r:
+            continue
+        two = r.get("gemm_tflops_2sm")
+        out.append(f"| {r['m']} | {r['n']} | {r['k']} | {r.get('ranks', 1)} | {r['gemm_tflops']:.0f} | "
+                   f"{'%.0f' % two if two else '-'} | {r['cublas_tflops']:.0f} | {max(r['gemm_tflops'], two or 0) / peak:.2f} | "
+                   f"{r.get('fused_gemm_put_ms', float('nan')):.3f} | {r.get('stock_cublas_then_memcpy_ms', float('nan')):.3f} |")
+    return "\n".join(out)
+
+
 def render(rows: List[Dict]) -> str:
     parts = ["# Measured rows (device-timed, max over ranks)\n"]
     if any(r.get("pattern") == "peer2pear" for r in rows):
@@ -84,6 +135,10 @@ def render(rows: List[Dict]) -> str:
         parts += ["## allreduce miniapp\n", allreduce_table(rows), ""]
     if any(r.get("pattern") == "concurency" for r in rows):
         parts += ["## concurrency bench\n", concurency_table(rows), ""]
+    if any("row_parallel" in r or "column_parallel" in r for r in rows):
+        parts += ["## tensor-parallel layers (GEMM fused with its collective)\n", tensor_parallel_table(rows), ""]
+    if any("gemm_tflops" in r for r in rows):
+        parts += ["## tcgen05 GEMM (-> put)\n", gemm_table(rows), ""]
     return "\n".join(parts)
 
 

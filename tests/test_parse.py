@@ -101,3 +101,26 @@ def test_python_sweep_renders_tables_with_the_cpu_backend(native):
     total, per = cc.bench("nowait", ["C", "MD"], {"tripcount_C": 1000, "globalsize_C": 64,
                                                  "globalsize_MD": 100000}, backend="cpu", n_repetitions=2)
     assert total > 0 and per == []
+
+
+def test_report_renders_tensor_parallel_and_gemm_rows(tmp_path):
+    """Rows of `python -m hpc_patterns_b200 tp` and scripts/gemm_put_bench.py -> roofline tables."""
+    import json
+
+    from hpc_patterns_b200.utils import report
+
+    rows = [{"ranks": 8, "m": 8192, "n": 8192, "k": 28672, "chunk": 2048,
+             "row_parallel": {"fused_ms": 0.4, "stock_ms": 0.8, "speedup": 2.0},
+             "row_parallel_allreduce": {"unavailable": "no multicast"},
+             "column_parallel": {"fused_ms": 0.35, "stock_ms": 0.5, "speedup": 1.43}},
+            {"m": 8192, "n": 8192, "k": 4096, "ranks": 2, "gemm_tflops": 1486.0, "gemm_tflops_2sm": 1600.0,
+             "cublas_tflops": 1662.0, "fused_gemm_put_ms": 0.401, "stock_cublas_then_memcpy_ms": 0.514}]
+    p = tmp_path / "rows.jsonl"
+    p.write_text("\n".join(json.dumps(r) for r in rows))
+    text = report.render(report.load_rows([str(p)]))
+    assert "## tensor-parallel layers" in text and "## tcgen05 GEMM" in text
+    line = [ln for ln in text.splitlines() if ln.startswith("| row_parallel (chunk 2048)")][0]
+    cells = [c.strip() for c in line.split("|")]
+    assert cells[2:6] == ["8", "8192", "8192", "28672"] and cells[8] == "2.00"
+    assert "row_parallel_allreduce" not in text                      # unavailable rows are skipped
+    assert "| 8192 | 8192 | 4096 | 2 | 1486 | 1600 | 1662 |" in text
