@@ -120,7 +120,9 @@ def allgather_gemm(a_full: torch.Tensor, a_src: Sequence[PtrLike], b: torch.Tens
     rank q's row block.  One gather thread per CTA pulls the remote rows with TMA bulk copies while the tiles of the
     rows that are already here run on the tensor cores; ``ready`` (int32 ``[M/128]``) counts arrivals per 128-row
     block and counts up forever: pass the value before the launch as ``ready_base`` (it grows by
-    ``native().allgather_gemm_chunks_per_block(K, chunk_bytes)`` per launch).  Returns the CTAs launched."""
+    ``native().allgather_gemm_chunks_per_block(K, chunk_bytes)`` per launch).  The sources are arbitrary row-block
+    pointers, so an all-to-all followed by a GEMM (MoE dispatch -> expert GEMM) is the same call with
+    ``a_src[q]`` = slot ``rank`` of rank q's send buffer.  Returns the CTAs launched."""
     _check_operands(a_full, b)
     world = len(a_src)
     m, k = a_full.shape

@@ -148,6 +148,29 @@ def test_allgather_gemm_virtual_ranks(native, dev, world, m, n, k, cluster, chun
                 assert ready[r].tolist() == want
 
 
+def test_all_to_all_then_gemm_is_the_same_kernel(native, dev):
+    """Dispatch -> GEMM: rank r's A is slot r of every rank's send buffer [P, M/P, K] — allgather_gemm with
+    a_src[q] = send_q[r] (the sources are arbitrary row-block pointers)."""
+    from hpc_patterns_b200.ops.gemm import allgather_gemm, gemm_reference
+
+    world, m, n, k = 4, 2048, 256, 256
+    rows = m // world
+    send = [_dyadic((world, rows, k), dev, 30 + q) for q in range(world)]
+    b = [_dyadic((n, k), dev, 70 + r) for r in range(world)]
+    status = torch.zeros(world, dtype=torch.int32, device=dev)
+    for r in range(world):
+        a_full = torch.full((m, k), float("nan"), device=dev, dtype=torch.bfloat16)
+        a_full[r * rows:(r + 1) * rows] = send[r][r]                       # my own contribution is local
+        ready = torch.zeros(m // 128, dtype=torch.int32, device=dev)
+        c = torch.zeros(m, n, device=dev)
+        allgather_gemm(a_full, [send[q][r] for q in range(world)], b[r], c, r, ready=ready, timeout_ns=int(5e9),
+                       status=status.data_ptr() + 4 * r)
+        torch.cuda.synchronize()
+        a_ref = torch.cat([send[q][r] for q in range(world)], 0)
+        assert torch.equal(a_full, a_ref) and torch.equal(c, gemm_reference(a_ref, b[r]))
+    assert status.tolist() == [0] * world
+
+
 def test_allgather_gemm_reports_a_missing_block(native, dev):
     """A block that never arrives must end in a timeout status, not in a hang: ready_base is set one launch too
     high, so the counters can never reach the target."""
