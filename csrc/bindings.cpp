@@ -440,8 +440,9 @@ PYBIND11_MODULE(_C, m) {
       [](uintptr_t a_full, const std::vector<uintptr_t>& a_src, uintptr_t b, uintptr_t c, bool out_bf16,
          uintptr_t ready, uint32_t ready_base, int chunk_bytes, const std::vector<uintptr_t>& done_flags,
          uint32_t done_epoch, uintptr_t ticket, uint32_t ticket_base, uint64_t timeout_ns, uintptr_t status, int rank,
-         int m_, int n, int k, int ctas, int device, uintptr_t stream, int cluster) {
+         int m_, int n, int k, int ctas, int device, uintptr_t stream, int cluster, int activation) {
         AgGemmArgs args;
+        args.activation = activation;
         if (a_src.empty() || a_src.size() > static_cast<size_t>(kApiMaxRanks))
           throw std::invalid_argument("allgather_gemm: 1..16 row-block pointers");
         if (!done_flags.empty() && done_flags.size() != a_src.size())
@@ -473,7 +474,7 @@ PYBIND11_MODULE(_C, m) {
       py::arg("ready_base") = 0, py::arg("chunk_bytes") = 0, py::arg("done_flags") = std::vector<uintptr_t>(),
       py::arg("done_epoch") = 0, py::arg("ticket") = 0, py::arg("ticket_base") = 0, py::arg("timeout_ns") = 0,
       py::arg("status") = 0, py::arg("rank") = 0, py::arg("m"), py::arg("n"), py::arg("k"), py::arg("ctas") = 0,
-      py::arg("device") = 0, py::arg("stream") = 0, py::arg("cluster") = 0,
+      py::arg("device") = 0, py::arg("stream") = 0, py::arg("cluster") = 0, py::arg("activation") = 0,
       "tcgen05 GEMM over row-sharded A: one gather thread per CTA pulls the peers' rows (TMA bulk, NVLink) while "
       "the tiles of the rows that are already here are computed (all-gather -> GEMM).");
   m.def(

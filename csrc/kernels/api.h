@@ -203,6 +203,7 @@ struct AgGemmArgs {
   const void* b = nullptr;                          // bf16 [N, K]
   void* c = nullptr;                                // fp32 (or bf16 when out_bf16) [M, N]
   bool out_bf16 = false;
+  int activation = 0;                               // fused into the epilogue: 0 none, 1 relu, 2 gelu (tanh form), 3 silu
   uint32_t* ready = nullptr;                        // local [M/128] arrival counters
   uint32_t ready_base = 0;
   int chunk_bytes = 0;                              // gather granularity; 0 -> 4096

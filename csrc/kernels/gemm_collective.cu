@@ -216,6 +216,7 @@ struct AgDev {
   void* c_local;                              // fp32 or bf16 [M, N]
   void* c_peer;                               // unused (kept for the shared epilogue): always null
   int out_bf16;
+  int activation;                             // 0 none, 1 relu, 2 gelu (tanh form), 3 silu — applied to C before it is stored
   uint32_t* ready;                            // local [M/128] arrival counters (monotonic)
   uint32_t ready_target;                      // value a peer block's counter reaches when it is complete
   uint32_t chunk_bytes;                       // gather granularity, divides the 128-row block size
@@ -251,7 +252,28 @@ struct AllGatherPolicy {
     }
   }
   __device__ __forceinline__ void epilogue(uint32_t taddr, float* stage_buf, int m0, int n0, int ew, int lane) const {
-    epilogue_store_tile(g, taddr, stage_buf, m0, n0, ew, lane);
+    if (g.activation == 0) {
+      epilogue_store_tile(g, taddr, stage_buf, m0, n0, ew, lane);
+      return;
+    }
+    // Fused activation (the layer's nonlinearity never costs a pass over C in HBM).
+    const size_t elem = g.out_bf16 ? 2 : 4;
+    unsigned char* base = static_cast<unsigned char*>(g.c_local) + (static_cast<size_t>(m0 + ew * 32) * g.n + n0) * elem;
+    const size_t ld = static_cast<size_t>(g.n) * elem;
+    auto store = [&](int row, int col, int byte, const uint4& v) {
+      *reinterpret_cast<uint4*>(base + row * ld + col * elem + byte) = v;
+    };
+    if (g.activation == 1)
+      epilogue_segments(g.out_bf16 != 0, taddr, stage_buf, lane, store, [](float x) { return fmaxf(x, 0.0f); });
+    else if (g.activation == 2)
+      epilogue_segments(g.out_bf16 != 0, taddr, stage_buf, lane, store, [](float x) {
+        float t;  // gelu, tanh form: 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.7978845608f * (x + 0.044715f * x * x * x)));
+        return 0.5f * x * (1.0f + t);
+      });
+    else
+      epilogue_segments(g.out_bf16 != 0, taddr, stage_buf, lane, store,
+                        [](float x) { return __fdividef(x, 1.0f + __expf(-x)); });  // silu
   }
   // Gather engine: one thread per CTA streams its share of the peers' row blocks, peer (rank+1) first — the
   // order in which the tile loop needs them.  Piece c of the (P-1) * M/P * K * 2 remote bytes belongs to CTA
@@ -522,6 +544,8 @@ int launch_allgather_gemm(const AgGemmArgs& args, int ctas, int device, cudaStre
   g.c_local = args.c;
   g.c_peer = nullptr;
   g.out_bf16 = args.out_bf16 ? 1 : 0;
+  HPCP_REQUIRE(args.activation >= 0 && args.activation <= 3, "allgather_gemm: activation must be 0..3");
+  g.activation = args.activation;
   g.ready = args.ready;
   g.chunk_bytes = static_cast<uint32_t>(chunk);
   g.chunks_per_block = static_cast<uint32_t>(block_bytes / chunk);

@@ -190,8 +190,13 @@ __device__ __forceinline__ void tc_fence_after() {
 // (store, peer store, reduction) always happens in full 128-byte segments: 8 consecutive lanes = one segment, 4 rows
 // per instruction.  emit(row, col, byte, v): 16 bytes `v` of accumulator row `row` (0..31 inside this warp's rows)
 // that start `byte` bytes into the round's segment, whose first column is `col`.
-template <class Emit>
-__device__ __forceinline__ void epilogue_segments(bool out_bf16, uint32_t taddr, float* stage_buf, int lane, Emit emit) {
+// pre(x): applied to every fp32 accumulator value before it is converted / staged (a fused activation).
+struct EpilogueIdentity {
+  __device__ __forceinline__ float operator()(float x) const { return x; }
+};
+template <class Emit, class Pre = EpilogueIdentity>
+__device__ __forceinline__ void epilogue_segments(bool out_bf16, uint32_t taddr, float* stage_buf, int lane, Emit emit,
+                                                  Pre pre = Pre{}) {
   const int cols_per_round = out_bf16 ? 64 : 32;
   unsigned char* stage_row = reinterpret_cast<unsigned char*>(stage_buf) + lane * (kStageRowWords * 4);
   for (int col = 0; col < kBN; col += cols_per_round) {
@@ -200,6 +205,8 @@ __device__ __forceinline__ void epilogue_segments(bool out_bf16, uint32_t taddr,
       for (int half = 0; half < 2; ++half) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + col + half * 32, r);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(pre(__uint_as_float(r[j])));
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           uint4 pk;
@@ -218,6 +225,8 @@ __device__ __forceinline__ void epilogue_segments(bool out_bf16, uint32_t taddr,
     } else {
       uint32_t r[32];
       tmem_ld_32x32b_x32(taddr + col, r);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(pre(__uint_as_float(r[j])));
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
         *reinterpret_cast<uint4*>(stage_row + j * 4) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);

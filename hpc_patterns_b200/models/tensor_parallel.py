@@ -27,6 +27,19 @@ from ..parallel.comm import Comm
 from ..parallel.symmetric import SignalPads, SymmetricBuffer
 
 
+def apply_activation(y: torch.Tensor, activation: str) -> torch.Tensor:
+    """Plain PyTorch form of the epilogue activations (gelu in its tanh form, like the kernel)."""
+    if activation == "none":
+        return y
+    if activation == "relu":
+        return torch.relu(y)
+    if activation == "gelu":
+        return torch.nn.functional.gelu(y, approximate="tanh")
+    if activation == "silu":
+        return torch.nn.functional.silu(y)
+    raise ValueError(f"unknown activation {activation!r}")
+
+
 class _FusedLinearBase:
     def __init__(self, comm: Comm, device: int, timeout_s: float):
         self.C = native()
@@ -131,10 +144,13 @@ class ColumnParallelLinear(_FusedLinearBase):
     """``y[M, N_local] = concat_r(x_r[M/P, K]) @ w[N_local, K].T``."""
 
     def __init__(self, comm: Comm, device: int, m: int, n_local: int, k: int, out_dtype: torch.dtype = torch.float32,
-                 cluster: int = 0, ctas: int = 0, chunk_bytes: int = 0, timeout_s: float = 30.0):
+                 cluster: int = 0, ctas: int = 0, chunk_bytes: int = 0, timeout_s: float = 30.0,
+                 activation: str = "none"):
+        """``activation`` (none | relu | gelu | silu) is fused into the GEMM's epilogue."""
         super().__init__(comm, device, timeout_s)
         if m % (128 * self.world) or n_local % 256 or k % 64:
             raise ValueError("M, N_local, K must be multiples of 128*world, 256, 64")
+        self.activation = activation
         self.m, self.n, self.k = m, n_local, k
         self.cluster, self.ctas, self.chunk_bytes = cluster, ctas, chunk_bytes
         self.a = SymmetricBuffer(comm, m * k * 2, device, zero=True)
@@ -171,7 +187,8 @@ class ColumnParallelLinear(_FusedLinearBase):
                               ready_base=self.ready_base & 0xFFFFFFFF, chunk_bytes=self.chunk_bytes,
                               done_flags=done, done_epoch=self.epoch, ticket=self.pads.ticket_ptr,
                               ticket_base=self.pads.ticket_issued & 0xFFFFFFFF, timeout_ns=self.pads.timeout_ns,
-                              status=self.pads.status_ptr, ctas=self.ctas, stream=st, cluster=self.cluster)
+                              status=self.pads.status_ptr, ctas=self.ctas, stream=st, cluster=self.cluster,
+                              activation=self.activation)
         self.pads.advance_tickets(ctas)
         if self.world > 1:
             self.ready_base += self._per_launch
@@ -179,16 +196,55 @@ class ColumnParallelLinear(_FusedLinearBase):
         return self.y
 
     def stock_forward(self, x_local: torch.Tensor) -> torch.Tensor:
-        """NCCL all_gather + cuBLAS GEMM, the stock pattern."""
-        if self.world == 1:
-            return torch.matmul(x_local, self.w.t())
-        full = torch.empty(self.m, self.k, device=x_local.device, dtype=x_local.dtype)
-        dist.all_gather_into_tensor(full, x_local.contiguous())
-        return torch.matmul(full, self.w.t())
+        """NCCL all_gather + cuBLAS GEMM (+ a separate activation kernel), the stock pattern."""
+        full = x_local
+        if self.world > 1:
+            full = torch.empty(self.m, self.k, device=x_local.device, dtype=x_local.dtype)
+            dist.all_gather_into_tensor(full, x_local.contiguous())
+        return apply_activation(torch.matmul(full, self.w.t()), self.activation)
 
     def close(self) -> None:
         self.a.close()
         self.pads.close()
+
+
+class ParallelMLP:
+    """A sequence-parallel transformer MLP block on the two fused layers:
+
+        x_rows [M/P, H]  --all-gather -> GEMM (+ activation in the epilogue)-->  h [M, F/P]
+                         --GEMM -> reduce-scatter-->                             y_rows [M/P, H]
+
+    Two kernels (plus the barrier / wait launches of the layers), no NCCL, the hidden activations h never leave the
+    GPU that produced them.  ``stock_forward`` is the same block through all_gather + cuBLAS + activation kernel +
+    cuBLAS + reduce_scatter."""
+
+    def __init__(self, comm: Comm, device: int, tokens: int, hidden: int, ffn: int, activation: str = "gelu",
+                 cluster: int = 0, chunk_bytes: int = 0, timeout_s: float = 30.0):
+        if ffn % comm.world:
+            raise ValueError("ffn must be a multiple of the world size")
+        self.up = ColumnParallelLinear(comm, device, tokens, ffn // comm.world, hidden, out_dtype=torch.bfloat16,
+                                       cluster=cluster, chunk_bytes=chunk_bytes, timeout_s=timeout_s,
+                                       activation=activation)
+        self.down = RowParallelLinear(comm, device, tokens, hidden, ffn // comm.world, cluster=cluster,
+                                      timeout_s=timeout_s)
+
+    @property
+    def launches(self) -> int:
+        return self.up.launches + self.down.launches
+
+    def forward(self, x_rows: torch.Tensor) -> torch.Tensor:
+        return self.down.forward(self.up.forward(x_rows))
+
+    def stock_forward(self, x_rows: torch.Tensor) -> torch.Tensor:
+        return self.down.stock_forward(self.up.stock_forward(x_rows))
+
+    def check(self) -> None:
+        self.up.check()
+        self.down.check()
+
+    def close(self) -> None:
+        self.up.close()
+        self.down.close()
 
 
 # =====================================================================================
@@ -227,6 +283,8 @@ def main(argv: Optional[List[str]] = None) -> int:
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0, help="all-gather granularity in bytes (0 -> 4096)")
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--mlp", action="store_true", help="also time the two layers chained as an MLP block "
+                                                       "(tokens = m, hidden = k, ffn = n)")
     args = ap.parse_args(argv)
 
     comm = Comm()
@@ -304,6 +362,29 @@ def main(argv: Optional[List[str]] = None) -> int:
                               "fused_tflops_per_gpu": round(flops / t_fused / 1e9, 1),
                               "nvlink_GBps_per_gpu": round(args.m * args.k * 2 * (P - 1) / P / (t_fused * 1e6), 1)}
     col.close()
+
+    # ---- the two layers as one MLP block (activation fused into the first GEMM's epilogue) -------------
+    if args.mlp:
+        mlp = ParallelMLP(comm, dev, args.m, args.k, args.n, activation="relu" if args.check else "gelu",
+                          cluster=args.cluster, chunk_bytes=args.chunk)       # hidden = K, ffn = N
+        mlp.up.w.copy_(_dyadic((args.n // P, args.k), device, 500 + comm.rank) / 8)
+        mlp.down.w.copy_(_dyadic((args.k, args.n // P), device, 600 + comm.rank))
+        xr = _dyadic((args.m // P, args.k), device, 700 + comm.rank)
+        if args.check:
+            y = mlp.forward(xr).clone()
+            ref = mlp.stock_forward(xr)
+            if P == 1:
+                ref = ref[: args.m]
+            torch.cuda.synchronize(dev)
+            mlp.check()
+            out["mlp_max_abs_diff"] = comm.max(float((y - ref).abs().max()))
+            out["mlp_ref_max_abs"] = comm.max(float(ref.abs().max()))
+        t_fused = _timed(lambda: mlp.forward(xr), comm, dev, args.steps)
+        t_stock = _timed(lambda: mlp.stock_forward(xr), comm, dev, args.steps)
+        mlp.check()
+        out["mlp"] = {"fused_ms": round(t_fused, 4), "stock_ms": round(t_stock, 4), "speedup": round(t_stock / t_fused, 3),
+                      "fused_tflops_per_gpu": round(4.0 * args.m * (args.n // P) * args.k / t_fused / 1e9, 1)}
+        mlp.close()
     if comm.rank == 0:
         print(json.dumps(out), flush=True)
     ok = (not args.check) or (out["row_parallel_exact"] and out["column_parallel_exact"] and

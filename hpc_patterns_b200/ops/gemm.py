@@ -49,6 +49,9 @@ def gemm_reference(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return a.float() @ b.float().t()
 
 
+ACTIVATIONS = ("none", "relu", "gelu", "silu")   # index = the kernel's activation code
+
+
 def _check_operands(a: torch.Tensor, b: torch.Tensor) -> None:
     if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
         raise TypeError("bf16 operands expected")
@@ -114,7 +117,7 @@ def gemm_all_to_all(a: torch.Tensor, b: torch.Tensor, recv: Sequence[PtrLike], r
 def allgather_gemm(a_full: torch.Tensor, a_src: Sequence[PtrLike], b: torch.Tensor, c: torch.Tensor, rank: int, *,
                    ready: PtrLike = 0, ready_base: int = 0, chunk_bytes: int = 0, done_flags: Sequence[int] = (),
                    done_epoch: int = 0, ticket: int = 0, ticket_base: int = 0, timeout_ns: int = 0, status: int = 0,
-                   ctas: int = 0, stream: Optional[int] = None, cluster: int = 0) -> int:
+                   ctas: int = 0, stream: Optional[int] = None, cluster: int = 0, activation: str = "none") -> int:
     """K-ag-gemm: ``C[M,N] = A[M,K] @ B[N,K].T`` where rank ``q`` holds rows ``[q*M/world, (q+1)*M/world)`` of A.
     ``a_full`` is the local gathered A (this rank's rows already in place), ``a_src[q]`` the peer-mapped address of
     rank q's row block.  One gather thread per CTA pulls the remote rows with TMA bulk copies while the tiles of the
@@ -122,7 +125,11 @@ def allgather_gemm(a_full: torch.Tensor, a_src: Sequence[PtrLike], b: torch.Tens
     block and counts up forever: pass the value before the launch as ``ready_base`` (it grows by
     ``native().allgather_gemm_chunks_per_block(K, chunk_bytes)`` per launch).  The sources are arbitrary row-block
     pointers, so an all-to-all followed by a GEMM (MoE dispatch -> expert GEMM) is the same call with
-    ``a_src[q]`` = slot ``rank`` of rank q's send buffer.  Returns the CTAs launched."""
+    ``a_src[q]`` = slot ``rank`` of rank q's send buffer.  ``activation`` (``none | relu | gelu | silu``; gelu in its
+    tanh form) is applied to the fp32 accumulator in the epilogue, before C is rounded and stored.
+    Returns the CTAs launched."""
+    if activation not in ACTIVATIONS:
+        raise ValueError(f"activation must be one of {ACTIVATIONS}")
     _check_operands(a_full, b)
     world = len(a_src)
     m, k = a_full.shape
@@ -137,4 +144,5 @@ def allgather_gemm(a_full: torch.Tensor, a_src: Sequence[PtrLike], b: torch.Tens
     return native().allgather_gemm(ptr(a_full), [ptr(s) for s in a_src], ptr(b), ptr(c), c.dtype == torch.bfloat16,
                                    ptr(ready), ready_base, chunk_bytes, [int(f) for f in done_flags], done_epoch,
                                    ticket, ticket_base, timeout_ns, status, rank, m, n, k, ctas, dev,
-                                   current_stream(dev) if stream is None else stream, cluster)
+                                   current_stream(dev) if stream is None else stream, cluster,
+                                   ACTIVATIONS.index(activation))

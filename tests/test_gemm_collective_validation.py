@@ -22,6 +22,8 @@ def test_python_wrappers_reject_bad_operands():
     with pytest.raises(ValueError, match="ready"):
         allgather_gemm(_bf16(256, 64), [0, 0], _bf16(256, 64), torch.zeros(256, 256), 0,
                        ready=torch.zeros(1, dtype=torch.int32))
+    with pytest.raises(ValueError, match="activation"):
+        allgather_gemm(_bf16(256, 64), [0, 0], _bf16(256, 64), torch.zeros(256, 256), 0, activation="tanh")
     with pytest.raises(ValueError, match="receive buffer"):
         gemm_all_to_all(_bf16(256, 64), _bf16(256, 64), [torch.zeros(2, 128, 128), torch.zeros(2, 128, 256)], 0)
     with pytest.raises(TypeError):
@@ -59,3 +61,17 @@ def test_ring_rejects_inconsistent_slot_policy():
         C.ring_allreduce(16, 16, 16, 16, 16, 16, world=8, n=1024, n_slots=3)
     with pytest.raises(RuntimeError, match="ack words"):
         C.ring_allreduce(16, 16, 16, 16, 16, 16, world=8, n=1024, n_slots=2)
+
+
+def test_epilogue_activations_match_their_pytorch_twins_on_the_cpu():
+    from hpc_patterns_b200.models.tensor_parallel import apply_activation
+    from hpc_patterns_b200.ops.gemm import ACTIVATIONS
+
+    x = torch.linspace(-4, 4, 33)
+    assert ACTIVATIONS[0] == "none" and torch.equal(apply_activation(x, "none"), x)
+    assert torch.equal(apply_activation(x, "relu"), x.clamp(min=0))
+    t = torch.tanh(0.7978845608 * (x + 0.044715 * x ** 3))          # the formula the kernel evaluates
+    assert torch.allclose(apply_activation(x, "gelu"), 0.5 * x * (1 + t), atol=1e-6)
+    assert torch.allclose(apply_activation(x, "silu"), x / (1 + torch.exp(-x)), atol=1e-6)
+    with pytest.raises(ValueError):
+        apply_activation(x, "tanh")

@@ -148,6 +148,34 @@ def test_allgather_gemm_virtual_ranks(native, dev, world, m, n, k, cluster, chun
                 assert ready[r].tolist() == want
 
 
+@pytest.mark.parametrize("activation", ["relu", "gelu", "silu"])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_allgather_gemm_fused_activation(native, dev, activation, out_dtype):
+    """The activation runs on the fp32 accumulator in the epilogue: relu is exact, gelu (tanh form, tanh.approx) and
+    silu (__expf) are compared with the PyTorch fp32 functions within the approximations' error."""
+    from hpc_patterns_b200.models.tensor_parallel import apply_activation
+    from hpc_patterns_b200.ops.gemm import allgather_gemm, gemm_reference
+
+    world, m, n, k = 2, 512, 512, 128
+    rows = m // world
+    a = _dyadic((m, k), dev, 11)
+    b = _dyadic((n, k), dev, 12)
+    for r in range(world):
+        a_full = torch.zeros(m, k, device=dev, dtype=torch.bfloat16)
+        a_full[r * rows:(r + 1) * rows] = a[r * rows:(r + 1) * rows]
+        ready = torch.zeros(m // 128, dtype=torch.int32, device=dev)
+        c = torch.full((m, n), float("nan"), device=dev, dtype=out_dtype)
+        allgather_gemm(a_full, [a[q * rows:(q + 1) * rows] for q in range(world)], b, c, r, ready=ready,
+                       timeout_ns=int(5e9), activation=activation)
+        torch.cuda.synchronize()
+        ref = apply_activation(gemm_reference(a, b), activation)
+        if activation == "relu":
+            assert torch.equal(c, ref.to(out_dtype))
+        else:
+            tol = 2e-2 if out_dtype == torch.bfloat16 else 2e-3
+            assert torch.allclose(c.float(), ref, rtol=tol, atol=tol), float((c.float() - ref).abs().max())
+
+
 def test_all_to_all_then_gemm_is_the_same_kernel(native, dev):
     """Dispatch -> GEMM: rank r's A is slot r of every rank's send buffer [P, M/P, K] — allgather_gemm with
     a_src[q] = send_q[r] (the sources are arbitrary row-block pointers)."""
