@@ -33,7 +33,7 @@ fi
 # GEMM fused with reduce-scatter / all-gather (written after the GPU budget ran out): one-GPU virtual-rank tests
 # first (exactness of tile order, ownership, gather, counters), then a single-rank timing of both layers
 timeout 600 python -m pytest tests/test_gpu_gemm_collective.py -q --timeout 120 2>&1 | tail -12 | tee $OUT/next_gemm_collective_pytest.txt
-timeout 300 python scripts/tp_bench.py --check --m 8192 --n 8192 --k 4096 2>&1 | tail -2 | tee $OUT/next_tp_bench_n1.json | cut -c1-400
+timeout 300 python scripts/tp_bench.py --check --mlp --m 8192 --n 8192 --k 4096 2>&1 | tail -2 | tee $OUT/next_tp_bench_n1.json | cut -c1-400
 unset HPCP_EXPERIMENTAL
 # ncu of the validated GEMM kernel (CTA-pair multicast variant) for comparison with the 2-SM capture
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_put_kernel -c 1 -f -o $OUT/prof_gemm_put \
