@@ -44,7 +44,11 @@ def main(argv=None) -> int:
         return m(rest)
     if prog == "topology":
         from . import native
-        print(native().topology_discover(rest[0] if rest else ""))
+        try:
+            print(native().topology_discover(rest[0] if rest else ""))
+        except RuntimeError as e:  # no driver / no GPUs / bad fake spec: a message, not a traceback
+            print(f"Error: {e}", file=sys.stderr)
+            return 1
         return 0
     if prog in ("tile-mapping", "tile_mapping"):
         from .parallel.tile_mapping import main as m

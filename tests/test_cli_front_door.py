@@ -29,6 +29,9 @@ def test_concurency_through_front_door(native):
 def test_topology_and_parse(native, tmp_path):
     p = run("topology", "4:switch")
     assert json.loads(p.stdout)["planes"] == [[0, 1, 2, 3]]
+    bad = run("topology", "fake:8:nvswitch")                 # a bad spec is a message and exit 1, not a traceback
+    assert bad.returncode == 1 and bad.stderr.startswith("Error:") and "Traceback" not in bad.stderr
+    assert "tp " in run("--help").stdout
     log = tmp_path / "l.log"
     log.write_text("export A=1\n## fused | C DP | SUCCESS: Close from Theoretical Speedup\n")
     assert "fused" in run("parse", str(log)).stdout
