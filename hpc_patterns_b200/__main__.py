@@ -14,7 +14,20 @@ The reference's program names are accepted too: sycl_con, omp_host_threads, omp_
 """
 from __future__ import annotations
 
+import os
 import sys
+
+_GPU_PROGRAMS = ("peer2pear", "allreduce", "tp", "interop")
+
+
+def _no_gpu_message(prog: str):
+    """The GPU programs fail like the native CLIs on a box without a device: one line, exit status 1."""
+    import torch
+
+    if prog in _GPU_PROGRAMS and not torch.cuda.is_available():
+        hint = f"; bin/{prog} --cpu is the host-only plumbing run" if prog in ("peer2pear", "allreduce") else ""
+        return f"Error: {prog}: no CUDA device (this program runs sm_100a kernels{hint})"
+    return None
 
 
 def main(argv=None) -> int:
@@ -30,6 +43,21 @@ def main(argv=None) -> int:
     if prog in ("peer2pear_i", "peer2pear_w"):
         rest = ["--transport", "sendrecv" if prog.endswith("_i") else "put"] + rest
         prog = "peer2pear"
+    if "-h" not in rest and "--help" not in rest:
+        msg = _no_gpu_message(prog)
+        if msg:
+            print(msg, file=sys.stderr)
+            return 1
+    try:
+        return _dispatch(prog, rest)
+    except (ValueError, RuntimeError) as e:  # usage / environment problems: a message, not a traceback
+        if os.environ.get("HPCP_TRACEBACK"):
+            raise
+        print(f"Error: {prog}: {e}", file=sys.stderr)
+        return 1
+
+
+def _dispatch(prog: str, rest: list) -> int:
     if prog == "concurency":
         from .models.concurency import main as m
         return m(rest)
@@ -44,11 +72,7 @@ def main(argv=None) -> int:
         return m(rest)
     if prog == "topology":
         from . import native
-        try:
-            print(native().topology_discover(rest[0] if rest else ""))
-        except RuntimeError as e:  # no driver / no GPUs / bad fake spec: a message, not a traceback
-            print(f"Error: {e}", file=sys.stderr)
-            return 1
+        print(native().topology_discover(rest[0] if rest else ""))
         return 0
     if prog in ("tile-mapping", "tile_mapping"):
         from .parallel.tile_mapping import main as m

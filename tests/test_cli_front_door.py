@@ -37,6 +37,16 @@ def test_topology_and_parse(native, tmp_path):
     assert "fused" in run("parse", str(log)).stdout
 
 
+def test_python_programs_fail_cleanly_without_gpu(gpu_count):
+    if gpu_count:
+        return
+    for prog in ("peer2pear", "allreduce", "tp", "interop"):
+        p = run(prog)
+        assert p.returncode == 1 and p.stderr.startswith(f"Error: {prog}: no CUDA device"), p.stderr
+        assert "Traceback" not in p.stderr
+    assert run("tp", "--help").returncode == 0            # usage is available everywhere
+
+
 def test_native_clis_fail_cleanly_without_gpu(bin_dir, gpu_count):
     if gpu_count:
         return
