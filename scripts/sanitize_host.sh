@@ -1,0 +1,23 @@
+#!/usr/bin/env bash
+# AddressSanitizer + UndefinedBehaviorSanitizer over the host-only programs (no GPU needed): the OpenMP concurrency
+# bench (driver grammar, autotune, verdict, JSON rows, error paths) and the native self-test (rank runtime, topology,
+# mapping policies, tile / ring orderings).  The device code has its own check: scripts/sanitize.sh (compute-sanitizer).
+set -euo pipefail
+cd "$(dirname "$0")/.."
+out=${1:-build/sanitize_host}; mkdir -p "$out"
+CXX=${HOSTCXX:-/usr/bin/g++}
+FLAGS="-O1 -g -std=c++17 -fopenmp -fsanitize=address,undefined -fno-sanitize-recover=undefined -fno-omit-frame-pointer -Icsrc -I/usr/local/cuda/include"
+$CXX $FLAGS csrc/concurency/main.cpp csrc/concurency/driver.cpp csrc/concurency/backend_cpu.cpp \
+     csrc/concurency/backend_nocuda.cpp -o "$out/omp_con"
+$CXX $FLAGS csrc/tests/native_selftest.cpp csrc/concurency/driver.cpp csrc/p2p/topology_core.cpp -o "$out/native_selftest" -ldl
+export ASAN_OPTIONS=detect_leaks=1:abort_on_error=0 UBSAN_OPTIONS=print_stacktrace=1
+"$out/native_selftest"
+"$out/omp_con" host_threads --globalsize_default_memory 200000 --tripcount_C 1000 --commands C M2D \
+     --commands M2D D2M --commands A H2D --json "$out/rows.jsonl" > "$out/run.log" 2>&1 || true   # verdicts may be FAILURE
+"$out/omp_con" nowait --verbose --repetitions 2 --globalsize_default_memory 50000 --commands C C >> "$out/run.log" 2>&1 || true
+"$out/omp_con" nowait --commands HM >> "$out/run.log" 2>&1 || true      # usage errors exit 1 by design
+"$out/omp_con" >> "$out/run.log" 2>&1 || true
+if grep -E "ERROR: AddressSanitizer|runtime error:|LeakSanitizer" "$out/run.log"; then
+  echo "sanitize_host: FAILED (see $out/run.log)"; exit 1
+fi
+grep -c "^## " "$out/run.log" | xargs echo "sanitize_host: OK, verdict lines:"
