@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# AddressSanitizer + UndefinedBehaviorSanitizer over the host-only programs (no GPU needed): the OpenMP concurrency
+# AddressSanitizer + UndefinedBehaviorSanitizer (+ ThreadSanitizer for the rank runtime) over the host-only programs (no GPU needed): the OpenMP concurrency
 # bench (driver grammar, autotune, verdict, JSON rows, error paths) and the native self-test (rank runtime, topology,
 # mapping policies, tile / ring orderings).  The device code has its own check: scripts/sanitize.sh (compute-sanitizer).
 set -euo pipefail
@@ -10,6 +10,12 @@ FLAGS="-O1 -g -std=c++17 -fopenmp -fsanitize=address,undefined -fno-sanitize-rec
 $CXX $FLAGS csrc/concurency/main.cpp csrc/concurency/driver.cpp csrc/concurency/backend_cpu.cpp \
      csrc/concurency/backend_nocuda.cpp -o "$out/omp_con"
 $CXX $FLAGS csrc/tests/native_selftest.cpp csrc/concurency/driver.cpp csrc/p2p/topology_core.cpp -o "$out/native_selftest" -ldl
+# ThreadSanitizer over the thread-per-rank runtime (barriers, reductions, failure propagation) that every native CLI uses
+$CXX -O1 -g -std=c++17 -fopenmp -fsanitize=thread -Icsrc -I/usr/local/cuda/include csrc/tests/native_selftest.cpp \
+     csrc/concurency/driver.cpp csrc/p2p/topology_core.cpp -o "$out/native_selftest_tsan" -ldl
+if "$out/native_selftest_tsan" 2>&1 | tee "$out/tsan.log" | grep -q "WARNING: ThreadSanitizer"; then
+  echo "sanitize_host: FAILED (data race, see $out/tsan.log)"; exit 1
+fi
 export ASAN_OPTIONS=detect_leaks=1:abort_on_error=0 UBSAN_OPTIONS=print_stacktrace=1
 "$out/native_selftest"
 "$out/omp_con" host_threads --globalsize_default_memory 200000 --tripcount_C 1000 --commands C M2D \
