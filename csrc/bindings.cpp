@@ -355,8 +355,9 @@ PYBIND11_MODULE(_C, m) {
       "gemm_reduce_scatter",
       [](uintptr_t a, uintptr_t b, const std::vector<uintptr_t>& shards, const std::vector<uintptr_t>& done_flags,
          uint32_t done_epoch, uintptr_t ticket, uint32_t ticket_base, int rank, int m_, int n, int k, int ctas,
-         int device, uintptr_t stream, int cluster, uintptr_t c_multicast, bool out_bf16) {
+         int device, uintptr_t stream, int cluster, uintptr_t c_multicast, bool out_bf16, bool tma_epilogue) {
         GemmRsArgs args;
+        args.tma_epilogue = tma_epilogue;
         args.c_multicast = as_ptr<float>(c_multicast);
         args.out_bf16 = out_bf16;
         if (shards.empty() || shards.size() > static_cast<size_t>(kApiMaxRanks))
@@ -383,6 +384,7 @@ PYBIND11_MODULE(_C, m) {
       py::arg("done_epoch") = 0, py::arg("ticket") = 0, py::arg("ticket_base") = 0, py::arg("rank") = 0, py::arg("m"),
       py::arg("n"), py::arg("k"), py::arg("ctas") = 0, py::arg("device") = 0, py::arg("stream") = 0,
       py::arg("cluster") = 0, py::arg("c_multicast") = 0, py::arg("out_bf16") = false,
+      py::arg("tma_epilogue") = false,
       "tcgen05 GEMM whose epilogue adds every tile into the owner's fp32 shard over NVLink (GEMM -> reduce-scatter), "
       "or, with c_multicast, into every rank's copy through the NVSwitch (GEMM -> all-reduce).");
   m.def(

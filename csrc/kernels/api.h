@@ -159,6 +159,10 @@ struct GemmRsArgs {
   const void* a = nullptr;                          // bf16 [M, K_r], K-major
   const void* b = nullptr;                          // bf16 [N, K_r], K-major
   void* shard[kApiMaxRanks] = {nullptr};            // peer-mapped: every rank's [M/world, N], fp32 (bf16 if out_bf16)
+  // true: the additions are issued by the TMA unit — each epilogue warp stages 32 x 32 fp32 pieces in swizzled shared
+  // memory and one cp.reduce.async.bulk.tensor.2d (UTMAREDG.2D.ADD) adds 4 KiB — instead of REDG requests from the
+  // LSU (fp32 shards only).  Same result; which one is faster is a measurement.
+  bool tma_epilogue = false;
   // bf16 shards: REDG.E.ADD.BF16x8 — half the NVLink bytes, but each of the P additions rounds to bf16.
   bool out_bf16 = false;
   // GEMM -> all-reduce through the switch instead: when set, `shard` is ignored and every tile is added with

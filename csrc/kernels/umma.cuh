@@ -302,6 +302,17 @@ __device__ __forceinline__ void epilogue_store_tile(const G& g, uint32_t taddr, 
   }
 }
 
+// smem [32 x 128 B] tile (SWIZZLE_128B layout, 1024-byte aligned) added into a 2-D fp32 tensor at element (x, y) by
+// the TMA unit: one instruction per 4 KiB instead of 256 REDG requests from the LSU.
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, int x, int y, const void* smem_src) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map),
+               "r"(x), "r"(y), "r"(ptx::smem_u32(smem_src))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- persistent GEMM main loop ----
 // The warp-specialised persistent tile loop every GEMM kernel of the suite runs (256 threads, one CTA per SM):
 //   warp 0      TMA producer  : A[128x64] + B[256x64] per stage, kStagesT-deep smem ring, full/empty mbarriers
@@ -660,6 +671,22 @@ inline PFN_cuTensorMapEncodeTiled gemm_tensor_map_encoder() {
   });
   HPCP_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available");
   return fn;
+}
+
+// 2-D fp32 [rows, cols] row-major tensor with a [32 rows x 32 columns] SWIZZLE_128B box (128-byte inner extent):
+// the destination of the TMA-reduce epilogue (cp.reduce.async.bulk.tensor.2d ... .add).
+inline CUtensorMap make_f32_tile_map(const void* base, int rows, int cols) {
+  CUtensorMap map;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 4};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t elem_strides[2] = {1, 1};
+  const CUresult r = gemm_tensor_map_encoder()(
+      &map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, elem_strides,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  HPCP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp32 tile map) failed with code " + std::to_string(r));
+  return map;
 }
 
 // 2-D bf16 [rows, k] K-major tensor with a [box_rows x 64] SWIZZLE_128B box.

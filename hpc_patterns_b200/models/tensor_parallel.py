@@ -64,9 +64,11 @@ class RowParallelLinear(_FusedLinearBase):
     into all copies by the NVSwitch (``multimem.red`` on the multicast mapping; needs NVLS, world >= 2)."""
 
     def __init__(self, comm: Comm, device: int, m: int, n: int, k_local: int, cluster: int = 0, ctas: int = 0,
-                 timeout_s: float = 30.0, reduce: str = "scatter", out_dtype: torch.dtype = torch.float32):
+                 timeout_s: float = 30.0, reduce: str = "scatter", out_dtype: torch.dtype = torch.float32,
+                 epilogue: str = "red"):
         """``out_dtype=torch.bfloat16`` (reduce-scatter only): bf16 shards, half the NVLink bytes, every addition
-        rounds to bf16."""
+        rounds to bf16.  ``epilogue="tma"`` (fp32 reduce-scatter): additions issued by the TMA unit (UTMAREDG)."""
+        self.epilogue = epilogue
         super().__init__(comm, device, timeout_s)
         if out_dtype not in (torch.float32, torch.bfloat16) or (reduce == "all" and out_dtype != torch.float32):
             raise ValueError("out_dtype: float32, or bfloat16 with reduce='scatter'")
@@ -114,7 +116,7 @@ class RowParallelLinear(_FusedLinearBase):
         ctas = gemm_reduce_scatter(x, self.w, shards, self.rank, done_flags=done, done_epoch=self.epoch,
                                    ticket=self.pads.ticket_ptr, ticket_base=self.pads.ticket_issued & 0xFFFFFFFF,
                                    ctas=self.ctas, stream=st, cluster=self.cluster, c_multicast=self._mc,
-                                   out_dtype=self.out_dtype)
+                                   out_dtype=self.out_dtype, epilogue=self.epilogue)
         self.pads.advance_tickets(ctas)
         self.C.wait_flags(self.pads.word(self.rank, self.C.PAD_DONE), self.world, self.epoch, self.pads.timeout_ns,
                           self.pads.status_ptr, st)
@@ -283,6 +285,8 @@ def main(argv: Optional[List[str]] = None) -> int:
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0, help="all-gather granularity in bytes (0 -> 4096)")
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--rs-epilogue", default="red", choices=("red", "tma"),
+                    help="reduce-scatter additions: REDG from the LSU, or one TMA reduce per 32x32 piece")
     ap.add_argument("--mlp", action="store_true", help="also time the two layers chained as an MLP block "
                                                        "(tokens = m, hidden = k, ffn = n)")
     args = ap.parse_args(argv)
@@ -296,7 +300,8 @@ def main(argv: Optional[List[str]] = None) -> int:
 
     # ---- row-parallel: K is sharded, the output rows are scattered -------------------------------
     k_local = args.k // P
-    row = RowParallelLinear(comm, dev, args.m, args.n, k_local, cluster=args.cluster)
+    row = RowParallelLinear(comm, dev, args.m, args.n, k_local, cluster=args.cluster, epilogue=args.rs_epilogue)
+    out["rs_epilogue"] = args.rs_epilogue
     x = _dyadic((args.m, k_local), device, 100 + comm.rank)
     row.w.copy_(_dyadic((args.n, k_local), device, 200 + comm.rank))
     if args.check:

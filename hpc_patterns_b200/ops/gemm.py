@@ -62,7 +62,7 @@ def _check_operands(a: torch.Tensor, b: torch.Tensor) -> None:
 def gemm_reduce_scatter(a: torch.Tensor, b: torch.Tensor, shards: Sequence[PtrLike], rank: int, *,
                         done_flags: Sequence[int] = (), done_epoch: int = 0, ticket: int = 0, ticket_base: int = 0,
                         ctas: int = 0, stream: Optional[int] = None, cluster: int = 0, c_multicast: int = 0,
-                        out_dtype: torch.dtype = torch.float32) -> int:
+                        out_dtype: torch.dtype = torch.float32, epilogue: str = "red") -> int:
     """K-gemm-rs (csrc/kernels/gemm_collective.cu): ``A[M,K_r] @ B[N,K_r].T`` is this rank's partial sum; the
     epilogue adds every 128x256 tile into ``shards[owner]`` (fp32 ``[M/world, N]``, peer-mapped pointers or local
     tensors, one per rank, zeroed by their owners) with ``red.global.add.v4.f32`` over NVLink.  When
@@ -70,7 +70,11 @@ def gemm_reduce_scatter(a: torch.Tensor, b: torch.Tensor, shards: Sequence[PtrLi
     ``c_multicast`` (the NVLS multicast address of a zeroed fp32 ``[M, N]`` buffer that exists on every rank) turns
     the step into GEMM -> all-reduce: every tile is added into all copies by the switch (``multimem.red``);
     ``shards`` then only tells the world size.  ``out_dtype=torch.bfloat16``: bf16 shards, ``REDG.E.ADD.BF16x8`` —
-    half the NVLink bytes, every one of the P additions rounds to bf16.  Returns the CTAs launched."""
+    half the NVLink bytes, every one of the P additions rounds to bf16.  ``epilogue="tma"`` (fp32 shards): the
+    additions are issued by the TMA unit, one ``cp.reduce.async.bulk.tensor.2d`` per 32x32 piece staged in swizzled
+    shared memory, instead of ``REDG`` requests from the LSU (``"red"``).  Returns the CTAs launched."""
+    if epilogue not in ("red", "tma"):
+        raise ValueError("epilogue must be 'red' or 'tma'")
     _check_operands(a, b)
     world = len(shards)
     m, k = a.shape
@@ -87,7 +91,7 @@ def gemm_reduce_scatter(a: torch.Tensor, b: torch.Tensor, shards: Sequence[PtrLi
     return native().gemm_reduce_scatter(ptr(a), ptr(b), [ptr(s) for s in shards], [int(f) for f in done_flags],
                                         done_epoch, ticket, ticket_base, rank, m, n, k, ctas, dev,
                                         current_stream(dev) if stream is None else stream, cluster, int(c_multicast),
-                                        out_dtype == torch.bfloat16)
+                                        out_dtype == torch.bfloat16, epilogue == "tma")
 
 
 def gemm_all_to_all(a: torch.Tensor, b: torch.Tensor, recv: Sequence[PtrLike], rank: int, *,

@@ -15,6 +15,7 @@ run scripts/tp_bench.py --check --mlp --m 2048 --n 2048 --k 2048 --steps 3 2>&1 
 for shape in "8192 8192 8192" "8192 8192 28672" "16384 8192 8192"; do
   set -- $shape
   run scripts/tp_bench.py --check --mlp --m $1 --n $2 --k $3 2>/dev/null | grep '^{' | tee -a $OUT/tp_bench_n$N.jsonl
+  run scripts/tp_bench.py --check --rs-epilogue tma --m $1 --n $2 --k $3 2>/dev/null | grep '^{' | tee -a $OUT/tp_bench_n$N.jsonl
   for chunk in 1024 2048; do
     run scripts/tp_bench.py --m $1 --n $2 --k $3 --chunk $chunk 2>/dev/null | grep '^{' | sed "s/^{/{\"chunk\": $chunk, /" | tee -a $OUT/tp_bench_n$N.jsonl
   done

@@ -26,6 +26,7 @@ ready = torch.zeros(m // 128, dtype=torch.int32, device=dev)
 per_launch = 128 * k * 2 // 4096
 for it in range(3):
     gemm_reduce_scatter(a, b, shards, 0, cluster=cluster)
+    gemm_reduce_scatter(a, b, shards, 0, cluster=cluster, epilogue="tma")
     gemm_all_to_all(a, b, recv, 0, out_dtype=torch.bfloat16, cluster=cluster)
     allgather_gemm(a_full, [a_full[: m // world], a_other], b, c, 0, ready=ready, ready_base=it * per_launch,
                    timeout_ns=int(5e9), cluster=cluster, activation="gelu")

@@ -42,7 +42,8 @@ def _dyadic(shape, dev, seed):
                                                  (4, 2048, 1024, 256, 0), (8, 2048, 768, 512, 0),
                                                  (4, 8192, 2048, 256, 0), (2, 1024, 512, 128, 3),
                                                  (4, 4096, 1024, 512, 3)])
-def test_gemm_reduce_scatter_virtual_ranks(native, dev, world, m, n, k, cluster):
+@pytest.mark.parametrize("epilogue", ["red", "tma"])
+def test_gemm_reduce_scatter_virtual_ranks(native, dev, world, m, n, k, cluster, epilogue):
     """Every virtual rank adds its partial product into the owners' shards; the shards must hold the exact sum
     (operands are small dyadic rationals, so fp32 addition is exact in any order)."""
     from hpc_patterns_b200.ops.gemm import gemm_reduce_scatter, gemm_reference
@@ -59,7 +60,8 @@ def test_gemm_reduce_scatter_virtual_ranks(native, dev, world, m, n, k, cluster)
             done = [pads[q].data_ptr() + 4 * (native.PAD_DONE + r) for q in range(world)]
             ctas = gemm_reduce_scatter(a[r], b[r], shards, r, done_flags=done, done_epoch=epoch,
                                        ticket=pads[r].data_ptr() + 4 * native.PAD_LOCAL, ticket_base=issued[r],
-                                       cluster=cluster, ctas=0 if epoch == 1 else 6)
+                                       cluster=cluster, ctas=0 if epoch == 1 else 6,
+                                       epilogue=epilogue if cluster != 3 else "red")
             issued[r] += ctas
         for q in range(world):
             native.wait_flags(pads[q].data_ptr() + 4 * native.PAD_DONE, world, epoch, int(5e9), 0,
