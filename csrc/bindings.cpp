@@ -341,14 +341,14 @@ PYBIND11_MODULE(_C, m) {
   m.def(
       "gemm_put",
       [](uintptr_t a, uintptr_t b, uintptr_t c_local, uintptr_t c_peer, int m_, int n, int k, bool out_bf16,
-         const py::dict& sync, int ctas, int device, uintptr_t stream, int cluster) {
+         const py::dict& sync, int ctas, int device, uintptr_t stream, int cluster, bool tma_epilogue) {
         return launch_gemm_put(as_ptr<const void>(a), as_ptr<const void>(b), as_ptr<void>(c_local),
                                as_ptr<void>(c_peer), m_, n, k, out_bf16, sync_from(sync), ctas, device,
-                               as_stream(stream), cluster);
+                               as_stream(stream), cluster, tma_epilogue);
       },
       py::arg("a"), py::arg("b"), py::arg("c_local"), py::arg("c_peer"), py::arg("m"), py::arg("n"), py::arg("k"),
       py::arg("out_bf16") = false, py::arg("sync") = py::dict(), py::arg("ctas") = 0, py::arg("device") = 0,
-      py::arg("stream") = 0, py::arg("cluster") = 0,
+      py::arg("stream") = 0, py::arg("cluster") = 0, py::arg("tma_epilogue") = false,
       "tcgen05 GEMM C = A . B^T (bf16 in, fp32 out) whose epilogue stores to c_local and/or the peer-mapped c_peer.");
 
   m.def(

@@ -145,9 +145,11 @@ void launch_tc_busy(const void* operands, float* out, int ctas, uint32_t tripcou
 // out_bf16: C is stored as bf16 (half the NVLink bytes) instead of fp32.
 // cluster: 0 = auto (CTA pairs sharing the B tile by TMA multicast when the shape allows), 1 = off, 2 = force,
 // 3 = 2-SM UMMA (tcgen05.mma.cta_group::2, one 256x256 tile per CTA pair; opt-in).
+// tma_epilogue (opt-in): the C tile leaves through the TMA unit (swizzled smem pieces + cp.async.bulk.tensor.2d stores)
+// instead of st.global from the epilogue warps.
 int launch_gemm_put(const void* a_bf16, const void* b_bf16, void* c_local, void* c_peer, int m, int n,
                     int k, bool out_bf16, const SyncOps& sync, int ctas, int device, cudaStream_t stream,
-                    int cluster = 0);
+                    int cluster = 0, bool tma_epilogue = false);
 
 // ------------------------------------- tensor-core GEMM fused with a collective ----
 // GEMM -> reduce-scatter (tensor-parallel row-parallel layer): C_r = A_r[M,K_r] . B_r[N,K_r]^T is this rank's

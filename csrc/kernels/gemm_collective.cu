@@ -113,13 +113,10 @@ struct ReduceScatterPolicy {
 // piece of its accumulator rows into a dense, 128-byte-swizzled smem tile (lane = row; the 16-byte chunk c of row r
 // goes to chunk c ^ (r % 8): conflict-free for both the writer and the TMA), and ONE cp.reduce.async.bulk.tensor.2d
 // adds the 4 KiB tile into the owner's shard (UTMAREDG.2D.ADD) — 8 instructions per 128x256 accumulator and warp
-// instead of 2048 REDG requests through the LSU.  Two tiles per warp: the TMA reads tile i while the warp fills i+1.
+// instead of 2048 REDG requests through the LSU (umma.cuh: epilogue_tma_tiles).
 struct RsMaps {
   CUtensorMap shard[kApiMaxRanks];  // fp32 [M/P, N] of every owner, box 32 x 32, SWIZZLE_128B
 };
-constexpr uint32_t kRedTileBytes = 32 * 128;
-constexpr uint32_t kRedSmemBytes = kEpiWarps * 2 * kRedTileBytes;  // 32 KiB, replaces the 18 KiB transpose staging
-
 struct ReduceScatterTmaPolicy {
   static constexpr bool kHasAuxWarp = false;
   const RsDev& g;
@@ -131,42 +128,15 @@ struct ReduceScatterTmaPolicy {
   __device__ __forceinline__ void epilogue(uint32_t taddr, float* stage_buf, int m0, int n0, int ew, int lane) const {
     const int owner = (m0 / kBM) / g.shard_tiles_m;
     const int y = m0 - owner * g.shard_tiles_m * kBM + ew * 32;  // first of this warp's rows inside the shard
-    // The tile loop hands every warp a slice of the transpose staging area; this policy re-carves the same area
-    // (base = 1024-aligned start of the epilogue smem) into two 4 KiB tiles per warp.
-    unsigned char* epi_base = reinterpret_cast<unsigned char*>(stage_buf) - static_cast<size_t>(ew) * kEpiWarpBytes;
-    unsigned char* tiles = epi_base + static_cast<size_t>(ew) * 2 * kRedTileBytes;
-#pragma unroll 1
-    for (int round = 0; round < kBN / 32; ++round) {
-      unsigned char* tile = tiles + (round & 1) * kRedTileBytes;
-      // the reduce issued two rounds ago (same tile) must have finished READING it; at most the newest group (the
-      // other tile) may still be pending.  Groups are per thread: lane 0 issued them all.
-      if (lane == 0) ptx::bulk_wait_read<1>();
-      __syncwarp();
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(taddr + round * 32, r);
-      unsigned char* row = tile + lane * 128;
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(row + ((c ^ (lane & 7)) << 4)) = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
-      fence_proxy_async_smem();  // my generic-proxy writes before the async-proxy read of the tile
-      __syncwarp();
-      if (lane == 0) {
-        tma_reduce_add_2d(&maps.shard[owner], n0 + round * 32, y, tile);
-        ptx::bulk_commit();
-      }
-    }
+    const CUtensorMap* map = &maps.shard[owner];
+    epilogue_tma_tiles(false, taddr, stage_buf, ew, lane,
+                       [&](const unsigned char* tile, int col) { tma_reduce_add_2d(map, n0 + col, y, tile); });
   }
   __device__ __forceinline__ void aux_warp(int, unsigned char*) const {}
   __device__ __forceinline__ void finish() const {
-    // Every reduction of this CTA must be PERFORMED (not just read) before the arrival epochs are published.
-    if (threadIdx.x >= 128 && (threadIdx.x & 31) == 0) {
-      ptx::bulk_wait<0>();
-      asm volatile("fence.proxy.async;" ::: "memory");
-    }
+    epilogue_tma_drain();
     if (g.ticket != nullptr)
       last_cta_publish_all(g.ticket, g.ticket_base + gridDim.x, g.done_flag, g.world, g.done_epoch);
-    else
-      __syncthreads();
   }
 };
 
@@ -510,8 +480,8 @@ int launch_gemm_reduce_scatter(const GemmRsArgs& args, int ctas, int device, cud
     HPCP_REQUIRE(!all_reduce && !args.out_bf16 && cluster != 3,
                  "gemm_reduce_scatter: the TMA epilogue exists for fp32 shards and cluster 0/1/2");
     RsMaps maps{};
-    for (int q = 0; q < args.world; ++q) maps.shard[q] = make_f32_tile_map(args.shard[q], args.m / args.world, args.n);
-    constexpr size_t smem_t = gemm_smem_bytes<kStages>(kRedSmemBytes - kEpiWarps * kEpiWarpBytes);
+    for (int q = 0; q < args.world; ++q) maps.shard[q] = make_c_tile_map(args.shard[q], args.m / args.world, args.n, false);
+    constexpr size_t smem_t = gemm_smem_bytes<kStages>(kTmaEpiSmemBytes - kEpiWarps * kEpiWarpBytes);
     static_assert(smem_t + 1024 <= 227 * 1024, "GEMM stages + two reduce tiles per epilogue warp must fit in 227 KiB");
     if (!pairs || grid < 2) {
       const CUtensorMap map_b = make_kmajor_map(args.b, args.n, args.k, kBN);

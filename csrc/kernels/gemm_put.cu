@@ -80,6 +80,42 @@ __global__ void __launch_bounds__(kThreads, 1)
   gemm_persistent<kCluster, kStages>(map_a, map_b, g.tiles_m, g.tiles_n, g.k, PutPolicy{g});
 }
 
+// Alternative epilogue (opt-in, `tma_epilogue`): the C tile leaves through the TMA unit — swizzled [32 x 128 B]
+// pieces in shared memory, one cp.async.bulk.tensor.2d store (UTMASTG) per piece and destination — instead of
+// 128-bit st.global from the epilogue warps.  Frees the LSU and sends the peer copy as bulk stores.
+struct PutMaps {
+  CUtensorMap c_local;  // valid iff g.c_local != nullptr
+  CUtensorMap c_peer;   // valid iff g.c_peer != nullptr
+};
+struct PutTmaPolicy {
+  static constexpr bool kHasAuxWarp = false;
+  const GemmDev& g;
+  const PutMaps& maps;
+  __device__ __forceinline__ void coords(int tile, int* m_blk, int* n_blk) const {
+    tile_coords(tile, g.tiles_m, g.tiles_n, m_blk, n_blk);
+  }
+  __device__ __forceinline__ void a_rows_ready(int) const {}
+  __device__ __forceinline__ void epilogue(uint32_t taddr, float* stage_buf, int m0, int n0, int ew, int lane) const {
+    epilogue_tma_tiles(g.out_bf16 != 0, taddr, stage_buf, ew, lane, [&](const unsigned char* tile, int col) {
+      if (g.c_peer != nullptr) tma_store_2d(&maps.c_peer, n0 + col, m0 + ew * 32, tile);
+      if (g.c_local != nullptr) tma_store_2d(&maps.c_local, n0 + col, m0 + ew * 32, tile);
+    });
+  }
+  __device__ __forceinline__ void aux_warp(int, unsigned char*) const {}
+  __device__ __forceinline__ void finish() const {
+    epilogue_tma_drain();  // the bulk stores are performed before the arrival epoch is published
+    if (g.sync.ticket != nullptr)
+      last_cta_publish(g.sync.ticket, g.sync.ticket_base + gridDim.x, g.sync.signal_flag, g.sync.signal_epoch);
+  }
+};
+
+template <int kCluster>
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm_put_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                        const __grid_constant__ GemmDev g, const __grid_constant__ PutMaps maps) {
+  gemm_persistent<kCluster, kStages>(map_a, map_b, g.tiles_m, g.tiles_n, g.k, PutTmaPolicy{g, maps});
+}
+
 // 2-SM UMMA variant (tcgen05.mma.cta_group::2): the same policy on umma.cuh's gemm_persistent_2sm.
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_put_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -91,7 +127,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
 int launch_gemm_put(const void* a_bf16, const void* b_bf16, void* c_local, void* c_peer, int m, int n,
                     int k, bool out_bf16, const SyncOps& sync, int ctas, int device, cudaStream_t stream,
-                    int cluster) {
+                    int cluster, bool tma_epilogue) {
   HPCP_REQUIRE(m > 0 && n > 0 && k > 0 && m % kBM == 0 && n % kBN == 0 && k % kBK == 0,
                "gemm_put: M, N, K must be multiples of 128, 256, 64");
   HPCP_REQUIRE(c_local != nullptr || c_peer != nullptr, "gemm_put: no output");
@@ -120,6 +156,37 @@ int launch_gemm_put(const void* a_bf16, const void* b_bf16, void* c_local, void*
   const int tiles = g.tiles_m * g.tiles_n;
   const int sms = device_sm_count(device);
   int grid = std::min(tiles, ctas > 0 ? ctas : sms);
+  if (tma_epilogue) {
+    HPCP_REQUIRE(!two_sm, "gemm_put: the TMA epilogue exists for cluster 0/1/2");
+    PutMaps maps{};
+    if (c_local != nullptr) maps.c_local = make_c_tile_map(c_local, m, n, out_bf16);
+    if (c_peer != nullptr) maps.c_peer = make_c_tile_map(c_peer, m, n, out_bf16);
+    constexpr size_t smem_t = gemm_smem_bytes<kStages>(kTmaEpiSmemBytes - kEpiWarps * kEpiWarpBytes);
+    static_assert(smem_t + 1024 <= 227 * 1024, "GEMM stages + two store tiles per epilogue warp must fit in 227 KiB");
+    if (!use_cluster || grid < 2) {
+      const CUtensorMap map_b_full = use_cluster ? make_kmajor_map(b_bf16, n, k, kBN) : map_b;
+      HPCP_ENABLE_SMEM(gemm_put_tma_kernel<1>, smem_t);
+      gemm_put_tma_kernel<1><<<grid, kThreads, smem_t, stream>>>(map_a, map_b_full, g, maps);
+      HPCP_CUDA(cudaGetLastError());
+      return grid;
+    }
+    grid &= ~1;
+    HPCP_ENABLE_SMEM(gemm_put_tma_kernel<2>, smem_t);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_t;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    HPCP_CUDA(cudaLaunchKernelEx(&cfg, gemm_put_tma_kernel<2>, map_a, map_b, g, maps));
+    return grid;
+  }
   if (!use_cluster || grid < 2) {
     const CUtensorMap map_b_full = use_cluster ? make_kmajor_map(b_bf16, n, k, kBN) : map_b;
     HPCP_ENABLE_SMEM(gemm_put_kernel<1>, kSmemBytes);

@@ -309,8 +309,82 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, int x,
                "r"(x), "r"(y), "r"(ptx::smem_u32(smem_src))
                : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int y, const void* smem_src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(x),
+               "r"(y), "r"(ptx::smem_u32(smem_src))
+               : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// Epilogue walk for the TMA unit: the warp's 32 accumulator rows leave in [32 rows x 128 bytes] pieces (32 fp32 or
+// 64 bf16 columns) staged in dense, 128-byte-swizzled shared memory — lane = row, the 16-byte chunk c of row r goes
+// to chunk c ^ (r % 8), conflict-free for the writer and the layout a SWIZZLE_128B tensor map expects — and lane 0
+// calls issue(tile, col) (one or more cp.async.bulk.tensor / cp.reduce.async.bulk.tensor instructions on a tensor
+// map with a 32-row x 128-byte box), which this function commits as one bulk group.  Two 4 KiB tiles per warp,
+// carved out of the (1024-byte aligned) epilogue area: the TMA reads one while the warp fills the other.
+// The caller's finish() must wait for the groups (lane 0 of warps 4..7: bulk_wait<0>) before it signals anything.
+constexpr uint32_t kTmaTileBytes = 32 * 128;
+constexpr uint32_t kTmaEpiSmemBytes = kEpiWarps * 2 * kTmaTileBytes;  // 32 KiB instead of the 18 KiB transpose staging
+template <class Issue>
+__device__ __forceinline__ void epilogue_tma_tiles(bool out_bf16, uint32_t taddr, float* stage_buf, int ew, int lane,
+                                                   Issue issue) {
+  unsigned char* epi_base = reinterpret_cast<unsigned char*>(stage_buf) - static_cast<size_t>(ew) * kEpiWarpBytes;
+  unsigned char* tiles = epi_base + static_cast<size_t>(ew) * 2 * kTmaTileBytes;
+  const int cols_per_round = out_bf16 ? 64 : 32;
+  int round = 0;
+#pragma unroll 1
+  for (int col = 0; col < kBN; col += cols_per_round, ++round) {
+    unsigned char* tile = tiles + (round & 1) * kTmaTileBytes;
+    // The group issued two rounds ago used this tile: it must have finished READING it (groups are per thread, lane
+    // 0 issued them all; at most the newest one — the other tile — may still be pending).
+    if (lane == 0) ptx::bulk_wait_read<1>();
+    __syncwarp();
+    unsigned char* row = tile + lane * 128;
+    if (out_bf16) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + col + half * 32, r);
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 pk;
+          __nv_bfloat162 t;
+          t = __floats2bfloat162_rn(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+          pk.x = *reinterpret_cast<uint32_t*>(&t);
+          t = __floats2bfloat162_rn(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          pk.y = *reinterpret_cast<uint32_t*>(&t);
+          t = __floats2bfloat162_rn(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
+          pk.z = *reinterpret_cast<uint32_t*>(&t);
+          t = __floats2bfloat162_rn(__uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
+          pk.w = *reinterpret_cast<uint32_t*>(&t);
+          const int c = half * 4 + j / 8;  // 16-byte chunk of the 128-byte row
+          *reinterpret_cast<uint4*>(row + ((c ^ (lane & 7)) << 4)) = pk;
+        }
+      }
+    } else {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(taddr + col, r);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(row + ((c ^ (lane & 7)) << 4)) = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+    }
+    fence_proxy_async_smem();  // my generic-proxy writes before the async-proxy read of the tile
+    __syncwarp();
+    if (lane == 0) {
+      issue(tile, col);
+      ptx::bulk_commit();
+    }
+  }
+}
+// finish() part of the TMA epilogues: every bulk group of this CTA must be PERFORMED before anything is signalled
+// (and must have stopped reading shared memory before the CTA retires).
+__device__ __forceinline__ void epilogue_tma_drain() {
+  if (threadIdx.x >= 128 && (threadIdx.x & 31) == 0) {
+    ptx::bulk_wait<0>();
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
 }
 
 // ---------------------------------------------------------------- persistent GEMM main loop ----
@@ -673,19 +747,20 @@ inline PFN_cuTensorMapEncodeTiled gemm_tensor_map_encoder() {
   return fn;
 }
 
-// 2-D fp32 [rows, cols] row-major tensor with a [32 rows x 32 columns] SWIZZLE_128B box (128-byte inner extent):
-// the destination of the TMA-reduce epilogue (cp.reduce.async.bulk.tensor.2d ... .add).
-inline CUtensorMap make_f32_tile_map(const void* base, int rows, int cols) {
+// 2-D fp32 / bf16 [rows, cols] row-major tensor with a [32 rows x 128 bytes] SWIZZLE_128B box: the destination of
+// the TMA epilogues (cp.async.bulk.tensor.2d store, cp.reduce.async.bulk.tensor.2d ... .add).
+inline CUtensorMap make_c_tile_map(const void* base, int rows, int cols, bool bf16) {
   CUtensorMap map;
+  const size_t elem = bf16 ? 2 : 4;
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 4};
-  const cuuint32_t box[2] = {32, 32};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * elem};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem), 32};
   const cuuint32_t elem_strides[2] = {1, 1};
   const CUresult r = gemm_tensor_map_encoder()(
-      &map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, elem_strides,
-      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  HPCP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp32 tile map) failed with code " + std::to_string(r));
+      &map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
+      strides, box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  HPCP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (C tile map) failed with code " + std::to_string(r));
   return map;
 }
 

@@ -20,11 +20,15 @@ from ._util import PtrLike, current_stream, ptr
 
 def gemm_put(a: torch.Tensor, b: torch.Tensor, c_local: Optional[torch.Tensor] = None, c_peer: PtrLike = 0,
              sync: Optional[dict] = None, ctas: int = 0, stream: Optional[int] = None,
-             out_dtype: torch.dtype = torch.float32, cluster: int = 0) -> int:
+             out_dtype: torch.dtype = torch.float32, cluster: int = 0, epilogue: str = "st") -> int:
     """Launch the fused GEMM(+put).  ``out_dtype`` fp32 or bf16 (c_local / c_peer hold that type).
     ``cluster``: 0 auto, 1 = single CTAs, 2 = CTA pairs sharing the B tile through TMA multicast,
     3 = 2-SM UMMA (``tcgen05.mma.cta_group::2``: one 256x256 tile per CTA pair; opt-in).
+    ``epilogue``: ``"st"`` = 128-bit stores from the epilogue warps (the measured kernel), ``"tma"`` (opt-in, not yet
+    run on a GPU) = swizzled smem pieces + ``cp.async.bulk.tensor.2d`` stores issued by the TMA unit.
     Returns the number of CTAs launched (for ticket bookkeeping)."""
+    if epilogue not in ("st", "tma"):
+        raise ValueError("epilogue must be 'st' or 'tma'")
     if out_dtype not in (torch.float32, torch.bfloat16):
         raise TypeError("out_dtype must be float32 or bfloat16")
     if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16:
@@ -41,7 +45,7 @@ def gemm_put(a: torch.Tensor, b: torch.Tensor, c_local: Optional[torch.Tensor] =
     return native().gemm_put(ptr(a), ptr(b), ptr(c_local) if c_local is not None else 0,
                              ptr(c_peer) if not isinstance(c_peer, int) else c_peer, m, n, k,
                              out_dtype == torch.bfloat16, sync or {}, ctas, dev,
-                             current_stream(dev) if stream is None else stream, cluster)
+                             current_stream(dev) if stream is None else stream, cluster, epilogue == "tma")
 
 
 def gemm_reference(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:

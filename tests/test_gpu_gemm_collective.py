@@ -74,6 +74,31 @@ def test_gemm_reduce_scatter_virtual_ranks(native, dev, world, m, n, k, cluster,
             assert pads[q][native.PAD_DONE:native.PAD_DONE + world].tolist() == [epoch] * world
 
 
+@pytest.mark.parametrize("m,n,k,cluster", [(128, 256, 64, 1), (512, 768, 256, 1), (2048, 1024, 512, 0), (1024, 512, 128, 2)])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_gemm_put_tma_store_epilogue(native, dev, m, n, k, cluster, out_dtype):
+    """gemm_put with the C tile leaving through the TMA unit (swizzled smem pieces + UTMASTG) instead of st.global:
+    same bits as the fp32 reference, local and 'peer' copy."""
+    from hpc_patterns_b200.ops.gemm import gemm_put, gemm_reference
+
+    a = _dyadic((m, k), dev, 1)
+    b = _dyadic((n, k), dev, 2)
+    c_local = torch.full((m, n), float("nan"), device=dev, dtype=out_dtype)
+    c_peer = torch.full((m, n), float("nan"), device=dev, dtype=out_dtype)
+    pad = torch.zeros(256, dtype=torch.int32, device=dev)
+    sync = {"signal_flag": pad.data_ptr() + 4 * native.PAD_DONE, "signal_epoch": 5,
+            "ticket": pad.data_ptr() + 4 * native.PAD_LOCAL, "ticket_base": 0}
+    ctas = gemm_put(a, b, c_local, c_peer, sync=sync, out_dtype=out_dtype, cluster=cluster, epilogue="tma")
+    torch.cuda.synchronize()
+    ref = gemm_reference(a, b).to(out_dtype)
+    assert torch.equal(c_local, ref) and torch.equal(c_peer, ref)
+    assert int(pad[native.PAD_DONE]) == 5 and int(pad[native.PAD_LOCAL]) == ctas
+    c_peer.fill_(float("nan"))
+    gemm_put(a, b, None, c_peer, out_dtype=out_dtype, cluster=cluster, ctas=4, epilogue="tma")   # few persistent CTAs
+    torch.cuda.synchronize()
+    assert torch.equal(c_peer, ref)
+
+
 @pytest.mark.parametrize("world,m,n,k,cluster", [(2, 512, 256, 64, 1), (4, 2048, 512, 64, 0)])
 def test_gemm_reduce_scatter_bf16_shards(native, dev, world, m, n, k, cluster):
     """bf16 shards (REDG.E.ADD.BF16x8).  Ternary operands and K = 64: every partial sum and every running total is an
