@@ -116,6 +116,12 @@ __global__ void __launch_bounds__(kThreads, 1)
   gemm_persistent<kCluster, kStages>(map_a, map_b, g.tiles_m, g.tiles_n, g.k, PutTmaPolicy{g, maps});
 }
 
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm_put_2sm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                            const __grid_constant__ GemmDev g, const __grid_constant__ PutMaps maps) {
+  gemm_persistent_2sm(map_a, map_b, g.tiles_m, g.tiles_n, g.k, PutTmaPolicy{g, maps});
+}
+
 // 2-SM UMMA variant (tcgen05.mma.cta_group::2): the same policy on umma.cuh's gemm_persistent_2sm.
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_put_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -157,7 +163,6 @@ int launch_gemm_put(const void* a_bf16, const void* b_bf16, void* c_local, void*
   const int sms = device_sm_count(device);
   int grid = std::min(tiles, ctas > 0 ? ctas : sms);
   if (tma_epilogue) {
-    HPCP_REQUIRE(!two_sm, "gemm_put: the TMA epilogue exists for cluster 0/1/2");
     PutMaps maps{};
     if (c_local != nullptr) maps.c_local = make_c_tile_map(c_local, m, n, out_bf16);
     if (c_peer != nullptr) maps.c_peer = make_c_tile_map(c_peer, m, n, out_bf16);
@@ -171,11 +176,16 @@ int launch_gemm_put(const void* a_bf16, const void* b_bf16, void* c_local, void*
       return grid;
     }
     grid &= ~1;
-    HPCP_ENABLE_SMEM(gemm_put_tma_kernel<2>, smem_t);
+    constexpr size_t smem_t2 = gemm_2sm_smem_bytes(kTmaEpiSmemBytes - kEpiWarps * kEpiWarpBytes);
+    static_assert(smem_t2 + 1024 <= 227 * 1024, "2-SM stages + two store tiles per epilogue warp must fit in 227 KiB");
+    if (two_sm)
+      HPCP_ENABLE_SMEM(gemm_put_2sm_tma_kernel, smem_t2);
+    else
+      HPCP_ENABLE_SMEM(gemm_put_tma_kernel<2>, smem_t);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem_t;
+    cfg.dynamicSmemBytes = two_sm ? smem_t2 : smem_t;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -184,7 +194,10 @@ int launch_gemm_put(const void* a_bf16, const void* b_bf16, void* c_local, void*
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    HPCP_CUDA(cudaLaunchKernelEx(&cfg, gemm_put_tma_kernel<2>, map_a, map_b, g, maps));
+    if (two_sm)
+      HPCP_CUDA(cudaLaunchKernelEx(&cfg, gemm_put_2sm_tma_kernel, map_a, map_b, g, maps));
+    else
+      HPCP_CUDA(cudaLaunchKernelEx(&cfg, gemm_put_tma_kernel<2>, map_a, map_b, g, maps));
     return grid;
   }
   if (!use_cluster || grid < 2) {

@@ -65,6 +65,8 @@ def main():
         if os.environ.get("HPCP_EXPERIMENTAL"):  # 2-SM UMMA variant (cta_group::2), opt-in until validated
             t_2sm = timed(lambda: gemm_put(a, b, c, 0, out_dtype=torch.bfloat16, cluster=3), comm, dev)
             row["gemm_tflops_2sm"] = flops / t_2sm / 1e9
+            t_2sm_tma = timed(lambda: gemm_put(a, b, c, 0, out_dtype=torch.bfloat16, cluster=3, epilogue="tma"), comm, dev)
+            row["gemm_tflops_2sm_tma_epilogue"] = flops / t_2sm_tma / 1e9
             row["max_abs_diff_2sm_vs_cublas"] = float((c.float() - c_ref.float()).abs().max())
         epoch = [0]
 

@@ -74,7 +74,8 @@ def test_gemm_reduce_scatter_virtual_ranks(native, dev, world, m, n, k, cluster,
             assert pads[q][native.PAD_DONE:native.PAD_DONE + world].tolist() == [epoch] * world
 
 
-@pytest.mark.parametrize("m,n,k,cluster", [(128, 256, 64, 1), (512, 768, 256, 1), (2048, 1024, 512, 0), (1024, 512, 128, 2)])
+@pytest.mark.parametrize("m,n,k,cluster", [(128, 256, 64, 1), (512, 768, 256, 1), (2048, 1024, 512, 0), (1024, 512, 128, 2),
+                                           (1024, 1024, 256, 3)])
 @pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
 def test_gemm_put_tma_store_epilogue(native, dev, m, n, k, cluster, out_dtype):
     """gemm_put with the C tile leaving through the TMA unit (swizzled smem pieces + UTMASTG) instead of st.global:
