@@ -19,3 +19,14 @@ def test_sass_listings_are_in_sync_with_the_sources(tmp_path):
     summary = open(os.path.join(committed, "SUMMARY.md")).read()
     for mnemonic in ("UTCHMMA", "UTMALDG.2D", "LDTM.x32", "UBLKCP", "LDGMC", "UTCHMMA.2CTA", "REDG.E.ADD.F32x4"):
         assert mnemonic in summary, mnemonic
+
+
+def test_kernels_that_ran_on_a_gpu_are_byte_identical():
+    """docs/sass/VALIDATED.sha256 lists the SASS fingerprints of the kernels as they ran on a B200; refactors around
+    them (shared headers, policy templates, new variants) must not change a single instruction."""
+    import sys
+
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "sass_fingerprint.py")], cwd=ROOT,
+                       capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "validated kernels are byte-identical" in p.stdout
