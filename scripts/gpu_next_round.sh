@@ -23,6 +23,9 @@ torch.cuda.synchronize()" > $OUT/next_ncu.log 2>&1
 else
   echo "2-SM UMMA variant FAILED or hung: see $OUT/next_2sm_pytest.txt"
 fi
+# the plain GEMM->put as an instantiation of the policy template (same loop, different register allocation): if it
+# passes the regular gemm_put tests the written-out copy in gemm_put.cu can be retired
+HPCP_GEMM_PUT_TEMPLATE=1 timeout 300 python -m pytest tests/test_gpu_kernels.py -k "gemm_put and not 2sm" -q --timeout 120 2>&1 | tail -3 | tee $OUT/next_gemm_put_template_pytest.txt
 # L2 cache-policy variant of the flagship (opt-in): exactness, then N=1 timing next to the default
 if timeout 120 python -m pytest tests/test_gpu_kernels.py -k "l2_hint" -x -q --timeout 60 2>&1 | tail -2 | tee $OUT/next_l2hint_pytest.txt | grep -q passed; then
   for r in 1 3; do
