@@ -290,6 +290,9 @@ def main(argv: Optional[List[str]] = None) -> int:
     ap.add_argument("--mlp", action="store_true", help="also time the two layers chained as an MLP block "
                                                        "(tokens = m, hidden = k, ffn = n)")
     args = ap.parse_args(argv)
+    if not torch.cuda.is_available():
+        print("Error: tp: no CUDA device (this program runs sm_100a kernels)", flush=True)
+        return 1
 
     comm = Comm()
     dev = comm.local_rank % torch.cuda.device_count()
