@@ -272,15 +272,17 @@ def _dyadic(shape, dev, seed):
 
 
 def main(argv: Optional[List[str]] = None) -> int:
-    """``torchrun --nproc-per-node N -m hpc_patterns_b200 tp [--check] [--m M --n N --k K]``: both fused layers next to
+    """``torchrun --nproc-per-node N -m hpc_patterns_b200 tp [--check] [--tokens M --out-features N --in-features K]``: both fused layers next to
     the stock pattern (cuBLAS + NCCL); one JSON line from rank 0."""
     import argparse
     import json
 
     ap = argparse.ArgumentParser(prog="tp")
-    ap.add_argument("--m", type=int, default=8192, help="rows (tokens) of the whole problem")
-    ap.add_argument("--n", type=int, default=8192, help="output features of the whole problem")
-    ap.add_argument("--k", type=int, default=8192, help="input features of the whole problem")
+    # Long names on purpose: under torchrun, `--m` / `--n` would be read as abbreviations of ITS options (--module,
+    # --max-restarts, --nnodes, ...) even when they follow the script name.
+    ap.add_argument("--tokens", dest="m", type=int, default=8192, help="M: rows (tokens) of the whole problem")
+    ap.add_argument("--out-features", dest="n", type=int, default=8192, help="N: output features of the whole problem")
+    ap.add_argument("--in-features", dest="k", type=int, default=8192, help="K: input features of the whole problem")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--cluster", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0, help="all-gather granularity in bytes (0 -> 4096)")
@@ -288,7 +290,7 @@ def main(argv: Optional[List[str]] = None) -> int:
     ap.add_argument("--rs-epilogue", default="red", choices=("red", "tma"),
                     help="reduce-scatter additions: REDG from the LSU, or one TMA reduce per 32x32 piece")
     ap.add_argument("--mlp", action="store_true", help="also time the two layers chained as an MLP block "
-                                                       "(tokens = m, hidden = k, ffn = n)")
+                                                       "(tokens = M, hidden = K, ffn = N)")
     args = ap.parse_args(argv)
     if not torch.cuda.is_available():
         print("Error: tp: no CUDA device (this program runs sm_100a kernels)", flush=True)

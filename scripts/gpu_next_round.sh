@@ -36,7 +36,7 @@ fi
 # GEMM fused with reduce-scatter / all-gather (written after the GPU budget ran out): one-GPU virtual-rank tests
 # first (exactness of tile order, ownership, gather, counters), then a single-rank timing of both layers
 timeout 600 python -m pytest tests/test_gpu_gemm_collective.py -q --timeout 120 2>&1 | tail -12 | tee $OUT/next_gemm_collective_pytest.txt
-timeout 300 python scripts/tp_bench.py --check --mlp --m 8192 --n 8192 --k 4096 2>&1 | tail -2 | tee $OUT/next_tp_bench_n1.json | cut -c1-400
+timeout 300 python scripts/tp_bench.py --check --mlp --tokens 8192 --out-features 8192 --in-features 4096 2>&1 | tail -2 | tee $OUT/next_tp_bench_n1.json | cut -c1-400
 if grep -q passed $OUT/next_gemm_collective_pytest.txt; then   # ncu of the three fused kernels (virtual ranks, one GPU)
   for kern in gemm_reduce_scatter_kernel gemm_reduce_scatter_tma_kernel gemm_all_to_all_kernel allgather_gemm_kernel; do
     timeout 400 ncu --set full --clock-control none --import-source on -k regex:$kern -c 1 -f -o $OUT/prof_$kern \

@@ -11,12 +11,12 @@ timeout 300 python -m pytest tests/test_gpu_multi.py -k two_slots -q --timeout 1
 for slots in 0 2; do
   timeout 120 bin/allreduce -n $N -p 25 --iters 5 $([ $slots = 2 ] && echo --slots 2) --json $OUT/ring_slots_n$N.jsonl | tail -1
 done
-run scripts/tp_bench.py --check --mlp --m 2048 --n 2048 --k 2048 --steps 3 2>&1 | tail -3 | tee $OUT/tp_check_n$N.json
+run scripts/tp_bench.py --check --mlp --tokens 2048 --out-features 2048 --in-features 2048 --steps 3 2>&1 | tail -3 | tee $OUT/tp_check_n$N.json
 for shape in "8192 8192 8192" "8192 8192 28672" "16384 8192 8192"; do
   set -- $shape
-  run scripts/tp_bench.py --check --mlp --m $1 --n $2 --k $3 2>/dev/null | grep '^{' | tee -a $OUT/tp_bench_n$N.jsonl
-  run scripts/tp_bench.py --check --rs-epilogue tma --m $1 --n $2 --k $3 2>/dev/null | grep '^{' | tee -a $OUT/tp_bench_n$N.jsonl
+  run scripts/tp_bench.py --check --mlp --tokens $1 --out-features $2 --in-features $3 2>/dev/null | grep '^{' | tee -a $OUT/tp_bench_n$N.jsonl
+  run scripts/tp_bench.py --check --rs-epilogue tma --tokens $1 --out-features $2 --in-features $3 2>/dev/null | grep '^{' | tee -a $OUT/tp_bench_n$N.jsonl
   for chunk in 1024 2048; do
-    run scripts/tp_bench.py --m $1 --n $2 --k $3 --chunk $chunk 2>/dev/null | grep '^{' | sed "s/^{/{\"chunk\": $chunk, /" | tee -a $OUT/tp_bench_n$N.jsonl
+    run scripts/tp_bench.py --tokens $1 --out-features $2 --in-features $3 --chunk $chunk 2>/dev/null | grep '^{' | sed "s/^{/{\"chunk\": $chunk, /" | tee -a $OUT/tp_bench_n$N.jsonl
   done
 done

@@ -9,7 +9,7 @@
 then times them: device events, max over ranks, min over iterations.  One JSON line from rank 0.
 Same as `python -m hpc_patterns_b200 tp ...`.
 
-  python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 scripts/tp_bench.py --m 8192 --n 8192 --k 28672
+  python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 scripts/tp_bench.py --tokens 8192 --out-features 8192 --in-features 28672
 """
 import os
 import sys

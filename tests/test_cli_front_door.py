@@ -162,3 +162,25 @@ def test_reference_program_names_and_json_report_pipeline(bin_dir, tmp_path):
     text = report.render(report.load_rows([str(rows)]))
     assert "## peer2pear" in text and "## allreduce miniapp" in text and "## concurrency bench" in text
     assert "| two-sided | sendrecv | host |" in text and "| one-sided | put | host |" in text
+
+
+def test_program_options_do_not_collide_with_torchrun_abbreviations():
+    """torchrun's argparse resolves ABBREVIATIONS of its own options anywhere on the command line, even after the
+    script name: a program option such as `--m` dies with "ambiguous option" (or is silently eaten when it is the
+    prefix of exactly one torchrun option).  Every long option of the programs that are launched under torchrun
+    must therefore not be a prefix of any torchrun option."""
+    import re
+
+    from torch.distributed.run import get_args_parser
+
+    theirs = [o for a in get_args_parser()._actions for o in a.option_strings if o.startswith("--")]
+    programs = ["bench.py", "hpc_patterns_b200/models/tensor_parallel.py", "hpc_patterns_b200/models/allreduce.py",
+                "hpc_patterns_b200/models/peer2pear.py", "scripts/gemm_put_bench.py"]
+    clashes = []
+    for rel in programs:
+        src = open(os.path.join(ROOT, rel)).read()
+        for opt in set(re.findall(r'add_argument\(\s*"(--[A-Za-z0-9_-]+)"', src)):
+            hit = [t for t in theirs if t.startswith(opt)]
+            if hit:
+                clashes.append((rel, opt, hit))
+    assert not clashes, clashes

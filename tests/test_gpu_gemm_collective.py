@@ -249,8 +249,8 @@ def test_allgather_gemm_reports_a_missing_block(native, dev):
 def test_tensor_parallel_layers_torchrun():
     n = min(torch.cuda.device_count(), 4)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
-           "127.0.0.1", "--master-port", "29641", os.path.join(ROOT, "scripts", "tp_bench.py"), "--check", "--m",
-           "2048", "--n", "1024", "--k", "1024", "--steps", "3"]
+           "127.0.0.1", "--master-port", "29641", os.path.join(ROOT, "scripts", "tp_bench.py"), "--check",
+           "--tokens", "2048", "--out-features", "1024", "--in-features", "1024", "--steps", "3"]
     p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout + p.stderr
     assert '"row_parallel_exact": true' in p.stdout and '"column_parallel_exact": true' in p.stdout
