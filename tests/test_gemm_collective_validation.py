@@ -75,3 +75,39 @@ def test_epilogue_activations_match_their_pytorch_twins_on_the_cpu():
     assert torch.allclose(apply_activation(x, "silu"), x / (1 + torch.exp(-x)), atol=1e-6)
     with pytest.raises(ValueError):
         apply_activation(x, "tanh")
+
+
+def test_python_wrappers_marshal_arguments_the_way_the_extension_expects(monkeypatch):
+    """No GPU here, so the launch itself fails — but it must fail INSIDE the native launcher (RuntimeError: no driver /
+    tensor-map encoder), not at the pybind boundary (TypeError: wrong number / order / type of arguments)."""
+    import hpc_patterns_b200
+    from hpc_patterns_b200.ops import gemm as G
+
+    real = hpc_patterns_b200.native()
+
+    class Proxy:
+        def __getattr__(self, name):
+            fn = getattr(real, name)
+            return lambda *a, **k: fn(*[0 if x is None else x for x in a], **k)   # CPU tensors have device index None
+
+    monkeypatch.setattr(G, "native", lambda: Proxy())
+    monkeypatch.setattr(G, "current_stream", lambda dev: 0)
+    a, b = _bf16(512, 128), _bf16(256, 128)
+    calls = [
+        lambda: G.gemm_put(a, b, torch.zeros(512, 256), 0),
+        lambda: G.gemm_put(a, b, torch.zeros(512, 256, dtype=torch.bfloat16), 16, out_dtype=torch.bfloat16, cluster=2,
+                           epilogue="tma", sync={"ticket": 16, "ticket_base": 3}),
+        lambda: G.gemm_reduce_scatter(a, b, [torch.zeros(256, 256), torch.zeros(256, 256)], 1, done_flags=[16, 32],
+                                      done_epoch=2, ticket=16, ticket_base=4, epilogue="tma"),
+        lambda: G.gemm_reduce_scatter(a, b, [16, 32], 0, out_dtype=torch.bfloat16, cluster=1),
+        lambda: G.gemm_reduce_scatter(a, b, [0, 0], 0, c_multicast=4096),
+        lambda: G.gemm_all_to_all(a, b, [torch.zeros(2, 256, 256), torch.zeros(2, 256, 256)], 0, done_flags=[16, 32],
+                                  ticket=16),
+        lambda: G.allgather_gemm(a, [a[:256], a[256:]], b, torch.zeros(512, 256), 0,
+                                 ready=torch.zeros(4, dtype=torch.int32), ready_base=8, chunk_bytes=2048,
+                                 done_flags=[16, 32], done_epoch=1, ticket=16, timeout_ns=10, status=16,
+                                 activation="silu"),
+    ]
+    for call in calls:
+        with pytest.raises(RuntimeError):
+            call()
