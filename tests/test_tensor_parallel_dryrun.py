@@ -170,3 +170,57 @@ def test_parallel_mlp_chains_the_layers(fakes):
     assert a2[0] is mlp.up.y                                   # the hidden activations feed the second GEMM in place
     assert mlp.launches == mlp.up.launches + mlp.down.launches > 0
     mlp.close()
+
+
+def test_tp_program_end_to_end_dry(fakes, monkeypatch, capsys):
+    """`python -m hpc_patterns_b200 tp --check --mlp ...` with every GPU-facing piece replaced: the whole program
+    (argument handling, the three layers, the MLP block, the JSON line) runs; the numbers mean nothing."""
+    import json
+
+    rec, ops = fakes
+    shim = tp.torch
+
+    class Event:
+        def __init__(self, enable_timing=False):
+            pass
+
+        def record(self, *a):
+            pass
+
+        def elapsed_time(self, other):
+            return 1.0
+
+    shim.cuda = types.SimpleNamespace(is_available=lambda: True, device_count=lambda: 8, set_device=lambda d: None,
+                                      synchronize=lambda d=None: None, Event=Event,
+                                      current_stream=lambda d=None: types.SimpleNamespace(cuda_stream=0))
+    shim.device = lambda kind, index=0: torch.device("cpu")
+    shim.Generator = lambda device=None: torch.Generator()
+    shim.randint = lambda lo, hi, shape, device=None, generator=None: torch.randint(lo, hi, shape, generator=generator)
+
+    class Comm(FakeComm):
+        def __init__(self):
+            super().__init__(0, 1)
+
+        def barrier(self):
+            pass
+
+        def max(self, v):
+            return v
+
+        def min(self, v):
+            return v
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(tp, "Comm", Comm)
+    # the stock twins run for real on the CPU (world = 1: plain matmuls)
+    rc = tp.main(["--check", "--mlp", "--tokens", "256", "--out-features", "512", "--in-features", "256", "--steps", "1",
+                  "--rs-epilogue", "tma", "--chunk", "1024", "--cluster", "1"])
+    out = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert out["ranks"] == 1 and (out["m"], out["n"], out["k"]) == (256, 512, 256) and out["rs_epilogue"] == "tma"
+    for key in ("row_parallel", "column_parallel", "mlp"):
+        assert {"fused_ms", "stock_ms", "speedup"} <= set(out[key])
+    assert "row_parallel_exact" in out and "column_parallel_exact" in out and "mlp_max_abs_diff" in out
+    assert rc in (0, 1)                                          # the recorders compute nothing, so 'exact' is false
+    assert [name for name, _, _ in ops].count("allgather_gemm") >= 3
