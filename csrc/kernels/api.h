@@ -244,7 +244,8 @@ void launch_count_mismatch(const void* v, size_t n, double expected, ElemType ty
 // accumulations in ONE launch per rank.  Hop t of chunk c is read once, added
 // into VC and forwarded to the right neighbour's slot over NVLink; arrival is
 // signalled per chunk, so communication, accumulation and forwarding pipeline
-// across the ring without any host involvement.
+// across the ring without any host involvement.  Launches that reuse the same slots must be separated by a
+// cross-rank barrier (launch_barrier_all): flow control covers the hops of ONE launch.
 struct RingArgs {
   const void* va = nullptr;       // local input block (hop 0)
   void* vc = nullptr;             // local accumulator (VC += every hop)

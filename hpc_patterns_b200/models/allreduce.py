@@ -134,7 +134,11 @@ class AllreduceMiniapp:
         self.C.init3(va, vb, vc, self.n, float(self.rank), float(self.rank), 0.0, self.dtype, self._stream())
 
     def run_once(self) -> None:
-        """Enqueue one allreduce on the current stream (no host sync except for ring-nccl)."""
+        """Enqueue one allreduce on the current stream (no host sync except for ring-nccl).
+
+        Consecutive calls must be separated by a cross-rank barrier (``run()`` does: ``pads.device_barrier``): the
+        fused ring's receive slots are reused by the next launch, and nothing inside one launch tells a rank that
+        its neighbour has finished READING the previous launch's last hops."""
         C, pads, st = self.C, self.pads, self._stream()
         me, P = self.rank, self.world
         va, vc = self._ptrs()
