@@ -508,14 +508,23 @@ PYBIND11_MODULE(_C, m) {
   m.def("ring_forwards", &ring_forwards);
   m.def("ring_waits_for_ack", &ring_waits_for_ack);
   m.def("ring_publishes_ack", &ring_publishes_ack);
+  m.def("ring_pull_keeps_copy", &ring_pull_keeps_copy);
+  m.def("ring_pull_copy_slot", &ring_pull_copy_slot);
+  m.def("ring_pull_src_slot", &ring_pull_src_slot);
+  m.def("ring_pull_waits_for_ack", &ring_pull_waits_for_ack);
+  m.def("ring_pull_publishes_ack", &ring_pull_publishes_ack);
   m.def("ring_num_chunks", &ring_num_chunks, py::arg("n"), py::arg("chunk_elems") = 0);
   m.def(
       "ring_allreduce",
       [](uintptr_t va, uintptr_t vc, uintptr_t slots_local, uintptr_t slots_right,
          uintptr_t arrived_local, uintptr_t arrived_right, int world, size_t n, size_t chunk_elems,
          uint32_t epoch_base, uint64_t timeout_ns, uintptr_t status, const std::string& dtype, int ctas,
-         int device, uintptr_t stream, int n_slots, uintptr_t ack_local, uintptr_t ack_left) {
+         int device, uintptr_t stream, int n_slots, uintptr_t ack_local, uintptr_t ack_left, bool pull,
+         uintptr_t va_left, uintptr_t slots_left) {
         RingArgs a;
+        a.pull = pull;
+        a.va_left = as_ptr<const void>(va_left);
+        a.slots_left = as_ptr<const void>(slots_left);
         a.n_slots = n_slots;
         a.ack_local = as_ptr<uint32_t>(ack_local);
         a.ack_left = as_ptr<uint32_t>(ack_left);
@@ -537,7 +546,8 @@ PYBIND11_MODULE(_C, m) {
       py::arg("arrived_local"), py::arg("arrived_right"), py::arg("world"), py::arg("n"),
       py::arg("chunk_elems") = 0, py::arg("epoch_base") = 0, py::arg("timeout_ns") = 0,
       py::arg("status") = 0, py::arg("dtype") = "float", py::arg("ctas") = 0, py::arg("device") = 0,
-      py::arg("stream") = 0, py::arg("n_slots") = 0, py::arg("ack_local") = 0, py::arg("ack_left") = 0);
+      py::arg("stream") = 0, py::arg("n_slots") = 0, py::arg("ack_local") = 0, py::arg("ack_left") = 0,
+      py::arg("pull") = false, py::arg("va_left") = 0, py::arg("slots_left") = 0);
   m.def(
       "allreduce_two_shot",
       [](const std::vector<uintptr_t>& va, const std::vector<uintptr_t>& vc,

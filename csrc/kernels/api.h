@@ -266,6 +266,12 @@ struct RingArgs {
   int n_slots = 0;
   uint32_t* ack_local = nullptr;
   uint32_t* ack_left = nullptr;
+  // Pull variant: the receiver LOADS every block from its left neighbour's memory (va_left for hop 1, slots_left for
+  // the later hops; both peer-mapped) and keeps a local copy in slots_local for its own right neighbour;
+  // slots_right is not used.  Same arrival / ack words, same slot policies.
+  bool pull = false;
+  const void* va_left = nullptr;
+  const void* slots_left = nullptr;
 };
 size_t ring_num_chunks(size_t n, size_t chunk_elems);
 void launch_ring_allreduce(const RingArgs& args, ElemType type, int ctas, int device,

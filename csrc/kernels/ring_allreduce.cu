@@ -162,6 +162,82 @@ __global__ void __launch_bounds__(512) ring_allreduce_kernel(const __grid_consta
   }
 }
 
+// ------------------------------------------------------------ K-ring, pull variant ----
+// Same data movement (every rank receives P-1 full blocks and accumulates P), but the bytes cross NVLink as LOADS
+// issued by the receiver instead of stores issued by the sender: SM-issued peer loads reach the copy-engine rate
+// (720-778 GB/s measured for `get`) where SM-issued peer stores stay 4-8 % below it.  Per (hop, chunk):
+//   wait (acquire) arrival word c  -> the left neighbour holds hop t-1 of chunk c (its VA for t = 1, else a slot)
+//   load the chunk from the LEFT neighbour's memory, add it into VC, keep a local copy for the right neighbour
+//   publish (release) arrival word c on the RIGHT neighbour: "hop t of chunk c can be read from me".
+struct RingPullDev {
+  const uint4* va;
+  uint4* vc;
+  const uint4* va_left;      // peer-mapped: the left neighbour's VA
+  const uint4* slots_left;   // peer-mapped: the left neighbour's local copies
+  uint4* slots_local;        // my copies, read by the right neighbour
+  uint32_t* arrived_local;
+  uint32_t* arrived_right;
+  uint32_t* ack_local;       // two slots: written by the right neighbour ("hop t of chunk c read")
+  uint32_t* ack_left;
+  int world;
+  size_t nvec, chunk_vec, n_chunks;
+  uint32_t epoch_base;
+  uint64_t timeout_ns;
+  uint32_t* status;
+};
+
+template <typename T, bool kTwoSlots>
+__global__ void __launch_bounds__(512) ring_pull_kernel(const __grid_constant__ RingPullDev a) {
+  __shared__ int ok_s;
+  for (int t = 0; t < a.world; ++t) {
+    const uint4* src = t == 0   ? a.va
+                       : t == 1 ? a.va_left
+                                : a.slots_left + static_cast<size_t>(ring_pull_src_slot(t, kTwoSlots)) * a.nvec;
+    uint4* copy = ring_pull_keeps_copy(t, a.world)
+                      ? a.slots_local + static_cast<size_t>(ring_pull_copy_slot(t, kTwoSlots)) * a.nvec
+                      : nullptr;
+    for (size_t c = blockIdx.x; c < a.n_chunks; c += gridDim.x) {
+      if (t > 0) {
+        if (threadIdx.x == 0)
+          ok_s = wait_epoch(a.arrived_local + c, a.epoch_base + t, a.timeout_ns, a.status) ? 1 : 0;
+        __syncthreads();
+        if (!ok_s) return;
+      }
+      if (kTwoSlots && ring_pull_waits_for_ack(t, a.world)) {
+        if (threadIdx.x == 0)
+          ok_s = wait_epoch(a.ack_local + c, a.epoch_base + t - 1, a.timeout_ns, a.status) ? 1 : 0;
+        __syncthreads();
+        if (!ok_s) return;
+      }
+      const size_t begin = c * a.chunk_vec;
+      const size_t end = begin + a.chunk_vec < a.nvec ? begin + a.chunk_vec : a.nvec;
+      size_t i = begin + threadIdx.x;
+      for (; i + 3 * blockDim.x < end; i += 4 * blockDim.x) {
+        uint4 x[4], acc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x[k] = t == 0 ? ptx::ld_weak_v4(src + i + k * blockDim.x) : ptx::ld_peer_v4(src + i + k * blockDim.x);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] = a.vc[i + k * blockDim.x];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (copy) copy[i + k * blockDim.x] = x[k];
+          a.vc[i + k * blockDim.x] = Vec4<T>::add(acc[k], x[k]);
+        }
+      }
+      for (; i < end; i += blockDim.x) {
+        const uint4 x = t == 0 ? ptx::ld_weak_v4(src + i) : ptx::ld_peer_v4(src + i);
+        if (copy) copy[i] = x;
+        a.vc[i] = Vec4<T>::add(a.vc[i], x);
+      }
+      __syncthreads();  // the chunk's copy is complete (and ok_s consumed by everyone)
+      // "hop t of chunk c can be read from me": VA at hop 0 (always there), the copy at hops 1 .. P-2.
+      if (t + 1 < a.world && threadIdx.x == 0) publish_epoch_light(a.arrived_right + c, a.epoch_base + t + 1);
+      if (kTwoSlots && ring_pull_publishes_ack(t, a.world) && threadIdx.x == 0)
+        publish_epoch_light(a.ack_left + c, a.epoch_base + t);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- two-shot ----
 struct TwoShotDev {
   const uint4* va[kApiMaxRanks];
@@ -374,7 +450,7 @@ void launch_ring_allreduce(const RingArgs& args, ElemType type, int ctas, int de
   d.epoch_base = args.epoch_base;
   d.timeout_ns = args.timeout_ns;
   d.status = args.status;
-  const bool ack = args.n_slots == 2 && args.world > 3;  // with P <= 3 no slot is ever written twice
+  const bool ack = args.n_slots == 2 && args.world > 3 && !args.pull;  // with P <= 3 no slot is ever written twice
   HPCP_REQUIRE(args.n_slots == 0 || args.n_slots == 2 || args.n_slots == args.world - 1,
                "ring: n_slots must be 0 (= world-1, no flow control) or 2 (double buffer + acks)");
   HPCP_REQUIRE(!ack || (args.ack_local != nullptr && args.ack_left != nullptr), "ring: n_slots=2 needs the ack words");
@@ -404,6 +480,41 @@ void launch_ring_allreduce(const RingArgs& args, ElemType type, int ctas, int de
     grid = best;
   }
   const bool two_slots = args.n_slots == 2;  // slot index t % 2 even when no ack is ever needed (P <= 3)
+  if (args.pull) {
+    HPCP_REQUIRE(args.world == 1 || (args.va_left != nullptr && (args.world == 2 || args.slots_left != nullptr)),
+                 "ring: the pull variant needs the left neighbour's VA and slots (peer-mapped)");
+    HPCP_REQUIRE(!two_slots || args.world <= 4 || (args.ack_local != nullptr && args.ack_left != nullptr),
+                 "ring: pull with n_slots=2 needs the ack words");
+    RingPullDev p{};
+    p.va = d.va;
+    p.vc = d.vc;
+    p.va_left = static_cast<const uint4*>(args.va_left);
+    p.slots_left = static_cast<const uint4*>(args.slots_left);
+    p.slots_local = static_cast<uint4*>(args.slots_local);
+    p.arrived_local = d.arrived_local;
+    p.arrived_right = d.arrived_right;
+    p.ack_local = args.ack_local;
+    p.ack_left = args.ack_left;
+    p.world = d.world;
+    p.nvec = d.nvec;
+    p.chunk_vec = d.chunk_vec;
+    p.n_chunks = d.n_chunks;
+    p.epoch_base = d.epoch_base;
+    p.timeout_ns = d.timeout_ns;
+    p.status = d.status;
+    if (two_slots) {
+      if (type == ElemType::kFloat)
+        ring_pull_kernel<float, true><<<grid, 512, 0, stream>>>(p);
+      else
+        ring_pull_kernel<int, true><<<grid, 512, 0, stream>>>(p);
+    } else if (type == ElemType::kFloat) {
+      ring_pull_kernel<float, false><<<grid, 512, 0, stream>>>(p);
+    } else {
+      ring_pull_kernel<int, false><<<grid, 512, 0, stream>>>(p);
+    }
+    HPCP_CUDA(cudaGetLastError());
+    return;
+  }
   if (two_slots) {
     if (type == ElemType::kFloat)
       ring_allreduce_kernel<float, true><<<grid, 512, 0, stream>>>(d);

@@ -60,6 +60,7 @@ struct Config {
   uint64_t timeout_ns = 30ull * 1000 * 1000 * 1000;
   std::string json_path;
   int slots = 0;     // --slots 2: the reference's VA/VB double buffer with per-chunk acks (default: P-1 slots)
+  bool pull = false; // --pull: the fused ring moves its bytes as peer LOADS (receiver-driven) instead of peer stores
   bool cpu = false;  // --cpu: host-only plumbing run (threads as ranks, memcpy as send/recv)
 };
 
@@ -81,6 +82,8 @@ void print_help() {
                " --coll auto|nvls|twoshot   collective used with -a\n"
                " --iters N --warmup N  timed / untimed repetitions (min is reported)\n"
                " --ctas N --chunk N    kernel tuning (CTAs per rank, elements per ring chunk)\n"
+               " --pull                fused ring, receiver-driven: every block is LOADED from the left neighbour's\n"
+               "                       memory (peer loads reach the copy-engine rate, peer stores stay 4-8 % below)\n"
                " --slots 2             fused ring with two receive slots + per-chunk acks (the reference's VA/VB\n"
                "                       double buffer) instead of P-1 slots without flow control\n"
                " --json FILE           append one JSON row\n"
@@ -183,6 +186,11 @@ void rank_main(RankCtx& ctx, Shared& sh) {
       a.timeout_ns = cfg.timeout_ns;
       a.status = status;
       a.n_slots = cfg.slots;
+      if (cfg.pull) {  // receiver-driven: load from the left neighbour instead of being stored into
+        a.pull = true;
+        a.va_left = sh.va.ptr[left];
+        a.slots_left = sh.slots.ptr[left];
+      }
       if (cfg.slots == 2) {  // ack words follow the arrival words on every pad
         a.ack_local = my_pad + kPadWords + sh.n_chunks;
         a.ack_left = pad_of(sh, left) + kPadWords + sh.n_chunks;
@@ -362,6 +370,7 @@ int main(int argc, char** argv) {
                                        {"json", required_argument, nullptr, 8},
                                        {"cpu", no_argument, nullptr, 9},
                                        {"slots", required_argument, nullptr, 10},
+                                       {"pull", no_argument, nullptr, 11},
                                        {"help", no_argument, nullptr, 'h'},
                                        {nullptr, 0, nullptr, 0}};
     int opt;
@@ -387,6 +396,7 @@ int main(int argc, char** argv) {
         case 8: cfg.json_path = optarg; break;
         case 9: cfg.cpu = true; break;
         case 10: cfg.slots = std::atoi(optarg); break;
+        case 11: cfg.pull = true; break;
         default: print_help(); return 1;
       }
     }

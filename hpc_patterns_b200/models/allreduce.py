@@ -64,9 +64,10 @@ class AllreduceResult:
 class AllreduceMiniapp:
     def __init__(self, comm: Comm, device: int, log2_elems: int = 25, dtype: str = "float",
                  algo: str = "ring", chunk_elems: int = 0, ctas: int = 0, timeout_s: float = 30.0,
-                 slots: int = 0):
+                 slots: int = 0, pull: bool = False):
         """``slots=2`` (fused ring only): two receive slots + per-chunk acks — the reference's VA/VB double
-        buffer — instead of ``world-1`` slots without flow control."""
+        buffer — instead of ``world-1`` slots without flow control.  ``pull=True`` (fused ring only): receiver-driven,
+        every block is loaded from the left neighbour's memory instead of being stored into the right neighbour's."""
         if algo not in ALGOS:
             raise ValueError(f"algo must be one of {ALGOS}")
         if dtype not in _TORCH_DTYPE:
@@ -84,6 +85,7 @@ class AllreduceMiniapp:
         if slots not in (0, 2):
             raise ValueError("slots must be 0 (world-1 slots) or 2")
         self.slots_policy = slots if algo == "ring" else 0
+        self.pull = bool(pull) and algo == "ring"
         self.n_chunks = self.C.ring_num_chunks(n, chunk_elems)
         # arrival words, then (two-slot ring) ack words
         self.pads = SignalPads(comm, device, extra_words=self.n_chunks * (2 if self.slots_policy == 2 else 1),
@@ -148,7 +150,9 @@ class AllreduceMiniapp:
                              self.chunk_elems, self.ring_epoch, pads.timeout_ns, pads.status_ptr,
                              self.dtype, self.ctas, self.device, st, self.slots_policy,
                              pads.chunk_word(me, self.n_chunks) if self.slots_policy == 2 else 0,
-                             pads.chunk_word(self.left, self.n_chunks) if self.slots_policy == 2 else 0)
+                             pads.chunk_word(self.left, self.n_chunks) if self.slots_policy == 2 else 0,
+                             self.pull, self.va.ptrs[self.left] if self.pull else 0,
+                             self.slots.ptrs[self.left] if self.pull else 0)
             self.ring_epoch += P
             self.launches += 1
         elif self.algo == "twoshot":
@@ -267,6 +271,8 @@ def main(argv: Optional[List[str]] = None) -> int:
     ap.add_argument("--json", default=None)
     ap.add_argument("--slots", type=int, default=0, choices=(0, 2),
                     help="fused ring: 2 = two receive slots + per-chunk acks (VA/VB double buffer); default world-1 slots")
+    ap.add_argument("--pull", action="store_true",
+                    help="fused ring, receiver-driven: blocks are loaded from the left neighbour (peer loads)")
     args = ap.parse_args(argv)
     comm = Comm()
     from ..parallel.tile_mapping import selected_device
@@ -283,7 +289,7 @@ def main(argv: Optional[List[str]] = None) -> int:
                 print(f"# NVLS unavailable ({e}); using two-shot P2P", flush=True)
             algo = "twoshot"
     if app is None:
-        app = AllreduceMiniapp(comm, device, args.p, args.type, algo, slots=args.slots)
+        app = AllreduceMiniapp(comm, device, args.p, args.type, algo, slots=args.slots, pull=args.pull)
     res = app.run(args.iters, args.warmup)
     if comm.rank == 0:
         row = res.row()

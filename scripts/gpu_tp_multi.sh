@@ -8,9 +8,9 @@ N=${1:-$(nvidia-smi -L | wc -l)}
 export HPCP_EXPERIMENTAL=1
 run() { timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29655 "$@"; }
 # two-slot K-ring (VA/VB double buffer + acks): exactness at P = 2 and 4, then timing next to the default at P = N
-timeout 300 python -m pytest tests/test_gpu_multi.py -k two_slots -q --timeout 120 2>&1 | tail -4 | tee $OUT/ring_two_slots_pytest_n$N.txt
-for slots in 0 2; do
-  timeout 120 bin/allreduce -n $N -p 25 --iters 5 $([ $slots = 2 ] && echo --slots 2) --json $OUT/ring_slots_n$N.jsonl | tail -1
+timeout 400 python -m pytest tests/test_gpu_multi.py -k "two_slots or pull_ring" -q --timeout 120 2>&1 | tail -4 | tee $OUT/ring_variants_pytest_n$N.txt
+for variant in "" "--slots 2" "--pull" "--pull --slots 2"; do   # default (validated) first, then the three new variants
+  timeout 120 bin/allreduce -n $N -p 25 --iters 5 $variant --json $OUT/ring_variants_n$N.jsonl | tail -1 | sed "s/^/[$variant] /"
 done
 run scripts/tp_bench.py --check --mlp --tokens 2048 --out-features 2048 --in-features 2048 --steps 3 2>&1 | tail -3 | tee $OUT/tp_check_n$N.json
 # GPU-minutes are charged per GPU: on more than two GPUs only the two headline shapes and one gather granularity

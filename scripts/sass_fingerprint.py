@@ -27,7 +27,7 @@ MANIFEST = os.path.join(ROOT, "docs", "sass", "VALIDATED.sha256")
 # demangled-name patterns of kernels written after the last GPU call (opt-in paths, GPU tests behind HPCP_EXPERIMENTAL)
 UNVALIDATED = (
     r"gemm_put_2sm", r"gemm_put_tma_kernel", r"gemm_put_policy_kernel", r"gemm_reduce_scatter", r"gemm_allreduce", r"gemm_all_to_all",
-    r"allgather_gemm", r"wait_flags_kernel", r"ring_allreduce_kernel<\w+, true>", r"triad_put_tma_kernel<\w+, true>",
+    r"allgather_gemm", r"wait_flags_kernel", r"ring_allreduce_kernel<\w+, true>", r"ring_pull_kernel", r"triad_put_tma_kernel<\w+, true>",
     r"nvls_kernel<\w+, (1|2|8), \d+>", r"nvls_kernel<\w+, \d+, 1024>",
 )
 

@@ -61,6 +61,10 @@ def test_ring_rejects_inconsistent_slot_policy():
         C.ring_allreduce(16, 16, 16, 16, 16, 16, world=8, n=1024, n_slots=3)
     with pytest.raises(RuntimeError, match="ack words"):
         C.ring_allreduce(16, 16, 16, 16, 16, 16, world=8, n=1024, n_slots=2)
+    with pytest.raises(RuntimeError, match="left neighbour"):
+        C.ring_allreduce(16, 16, 16, 16, 16, 16, world=4, n=1024, pull=True)
+    with pytest.raises(RuntimeError, match="ack words"):
+        C.ring_allreduce(16, 16, 16, 16, 16, 16, world=8, n=1024, n_slots=2, pull=True, va_left=16, slots_left=16)
 
 
 def test_epilogue_activations_match_their_pytorch_twins_on_the_cpu():

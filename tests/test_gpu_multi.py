@@ -87,15 +87,29 @@ def test_cli_allreduce_oversubscribed(bin_dir):
 
 @needs2
 @pytest.mark.skipif(not os.environ.get("HPCP_EXPERIMENTAL"), reason="written without GPU access, not yet run: opt-in")
-@pytest.mark.parametrize("args", [["--type", "float"], ["--type", "int", "--chunk", "1024"], ["-S", "-p", "16"]])
+@pytest.mark.parametrize("args", [["--type", "float"], ["--type", "int", "--chunk", "1024"], ["-S", "-p", "16"],
+                                  ["--pull"], ["--pull", "--type", "int"]])
 def test_cli_allreduce_two_slots(bin_dir, args):
     """Fused ring with the reference's VA/VB double buffer + per-chunk acks.  Four ranks even on two GPUs
     (oversubscribed): the ack channel only matters from P = 4 on.  Rules: csrc/kernels/ring_order.h, modelled on the
     CPU in tests/test_ring_protocol.py."""
     env = {"CUDA_VISIBLE_DEVICES": "0,1"} if _ngpu() < 4 else None
-    for n in (2, 4):
+    for n in (2, 4, 6):   # six ranks: the pull variant's acks only matter from P = 5 on
         rc, out, err = _run([os.path.join(bin_dir, "allreduce"), "-n", str(n), "-p", "20", "--iters", "3", "--slots",
                              "2"] + args, env=env)
+        assert rc == 0, out + err
+        assert out.count("Passed") == n
+
+
+@needs2
+@pytest.mark.skipif(not os.environ.get("HPCP_EXPERIMENTAL"), reason="written without GPU access, not yet run: opt-in")
+@pytest.mark.parametrize("args", [[], ["--type", "int", "--chunk", "2048"], ["-H", "-p", "16"]])
+def test_cli_allreduce_pull_ring(bin_dir, args):
+    """Receiver-driven fused ring (peer loads instead of peer stores), P-1 copy slots."""
+    env = {"CUDA_VISIBLE_DEVICES": "0,1"} if _ngpu() < 4 else None
+    for n in (2, 3, 4):
+        rc, out, err = _run([os.path.join(bin_dir, "allreduce"), "-n", str(n), "-p", "20", "--iters", "3", "--pull"]
+                            + args, env=env)
         assert rc == 0, out + err
         assert out.count("Passed") == n
 
