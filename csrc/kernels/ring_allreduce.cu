@@ -456,6 +456,12 @@ void launch_ring_allreduce(const RingArgs& args, ElemType type, int ctas, int de
   HPCP_REQUIRE(!ack || (args.ack_local != nullptr && args.ack_left != nullptr), "ring: n_slots=2 needs the ack words");
   d.ack_local = args.ack_local;
   d.ack_left = args.ack_left;
+  HPCP_REQUIRE(!args.pull || args.world == 1 ||
+                   (args.va_left != nullptr && (args.world == 2 || args.slots_left != nullptr)),
+               "ring: the pull variant needs the left neighbour's VA and slots (peer-mapped)");
+  HPCP_REQUIRE(!args.pull || args.n_slots != 2 || args.world <= 4 ||
+                   (args.ack_local != nullptr && args.ack_left != nullptr),
+               "ring: pull with n_slots=2 needs the ack words");
   // All CTAs may spin on arrival words: the grid must be co-resident (<= 4 CTAs of
   // 512 threads per SM).
   const int sms = device_sm_count(device);
@@ -481,10 +487,6 @@ void launch_ring_allreduce(const RingArgs& args, ElemType type, int ctas, int de
   }
   const bool two_slots = args.n_slots == 2;  // slot index t % 2 even when no ack is ever needed (P <= 3)
   if (args.pull) {
-    HPCP_REQUIRE(args.world == 1 || (args.va_left != nullptr && (args.world == 2 || args.slots_left != nullptr)),
-                 "ring: the pull variant needs the left neighbour's VA and slots (peer-mapped)");
-    HPCP_REQUIRE(!two_slots || args.world <= 4 || (args.ack_local != nullptr && args.ack_left != nullptr),
-                 "ring: pull with n_slots=2 needs the ack words");
     RingPullDev p{};
     p.va = d.va;
     p.vc = d.vc;
