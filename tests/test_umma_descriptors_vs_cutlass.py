@@ -25,11 +25,12 @@ int main() { row<128, 256>(); row<256, 256>(); row<128, 128>(); row<256, 64>(); 
 
 
 def _cutlass_include():
-    try:
-        import flashinfer
-    except Exception:
+    import importlib.util
+
+    spec = importlib.util.find_spec("flashinfer")          # located, not imported
+    if spec is None or not spec.submodule_search_locations:
         return None
-    d = os.path.join(os.path.dirname(flashinfer.__file__), "data", "cutlass", "include")
+    d = os.path.join(list(spec.submodule_search_locations)[0], "data", "cutlass", "include")
     return d if os.path.exists(os.path.join(d, "cute", "arch", "mma_sm100_desc.hpp")) else None
 
 
