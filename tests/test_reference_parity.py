@@ -51,6 +51,7 @@ def _shape(text: str):
             continue
         if "WARNING: Large Unbalance" in line:                 # timing-dependent in both programs
             continue
+        line = re.sub(r"-?nan|\binf", "N", line)       # a 0 us measurement divides by zero in both programs
         line = re.sub(r"\d+(\.\d+)?(e[+-]?\d+)?", "N", line)
         line = re.sub(r"(SUCCESS|FAILURE): .*", "VERDICT", line)
         out.append(line)
@@ -107,3 +108,45 @@ def test_parsers_are_interchangeable(ref_bins, bin_dir, tmp_path):
                               text=True, env=env)
         assert theirs.returncode == 0 and mine.returncode == 0, theirs.stderr + mine.stderr
         assert mine.stdout == theirs.stdout and "OMP_PROC_BIND=false" in mine.stdout
+
+
+# ------------------------------------------------------------------------------------------------ differential fuzz ----
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+
+# Not in the alphabet on purpose: two-letter tokens with a `C` ("CC", "CM", ...) and the empty token.  The reference
+# accepts them (its check is "letters from CMDH, not HM / MH", main.cpp:186-191) and then times a meaningless copy
+# "from C to C" with globalsize_CC = 1, or a nameless command; here they are usage errors.
+_TOKENS = ["C", "M2D", "D2M", "MD", "DM", "H2D", "D2H", "HD", "DH", "C2", "2C", "M2D2", "HM", "MH", "X", "M2X"]
+_groups = st.lists(st.lists(st.sampled_from(_TOKENS), min_size=0, max_size=3), min_size=0, max_size=3)
+_flags = st.lists(st.sampled_from([["--verbose"], ["--enable_profiling"], ["--queues", "1"], ["--queues", "2"],
+                                   ["--repetitions", "1"], ["--min_bandwidth", "0.000001"], ["--bogus"], ["-x"],
+                                   ["--tripcount_C", "7"], ["--globalsize_C", "2"]]),
+                  min_size=0, max_size=3)
+
+
+@given(groups=_groups, flags=_flags, mode=st.sampled_from(["nowait", "serial", "in_order", ""]))
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+def test_random_command_lines_behave_like_the_reference(ref_bins, bin_dir, groups, flags, mode):
+    """Random argv (valid and invalid) through the reference binary and ours: same exit status, same usage-or-run
+    decision, same sequence of line shapes.  Sizes are tiny, the verdict text itself is normalised away."""
+    argv = [mode] if mode else []
+    for f in flags:
+        argv += f
+    argv += ["--globalsize_default_memory", "2000", "--tripcount_C", "50", "--repetitions", "2"]
+    for cmd in ("MD", "DM", "HD", "DH"):       # explicit sizes: no autotuning, whose result depends on 0 us timings
+        argv += ["--globalsize_" + cmd, "2000"]
+    for g in groups:
+        argv += ["--commands"] + list(g)
+    ref = subprocess.run([ref_bins["nowait"]] + argv, capture_output=True, text=True, timeout=120)
+    ours = subprocess.run([os.path.join(bin_dir, "omp_con")] + argv, capture_output=True, text=True, timeout=120)
+    ref_usage = "--commands" in ref.stdout and "## " not in ref.stdout and ref.returncode == 1
+    ours_usage = "--commands" in ours.stdout and "## " not in ours.stdout and ours.returncode == 1
+    assert ours.returncode in (0, 1), (argv, ours.returncode, ours.stderr[-300:])                 # we never crash
+    if ref.returncode < 0:
+        # the reference's offload allocator aborts ("Wrong Allocation") for device buffers when g++ has no offload
+        # device to fall back to — an artefact of building it for the host; nothing to compare with
+        return
+    assert ref_usage == ours_usage, (argv, ref.stdout[-300:], ours.stdout[-300:])
+    if not ref_usage:
+        assert (ref.returncode in (0, 1)) and (ours.returncode in (0, 1)), (argv, ref.returncode, ours.returncode)
+        assert _shape(ours.stdout) == _shape(ref.stdout), (argv, ref.stdout, ours.stdout)
