@@ -71,7 +71,9 @@ def main(argv: Optional[List[str]] = None) -> int:
         return 2
     with open(argv[0]) as f:
         text = f.read()
-    print(render(parse_log(text), argv[1] if len(argv) > 1 else "simple"))
+    out = render(parse_log(text), argv[1] if len(argv) > 1 else "simple")
+    if out:  # a log without verdict lines prints nothing at all (like the reference's parser)
+        print(out)
     return 0
 
 

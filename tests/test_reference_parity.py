@@ -150,3 +150,32 @@ def test_random_command_lines_behave_like_the_reference(ref_bins, bin_dir, group
     if not ref_usage:
         assert (ref.returncode in (0, 1)) and (ours.returncode in (0, 1)), (argv, ref.returncode, ours.returncode)
         assert _shape(ours.stdout) == _shape(ref.stdout), (argv, ref.stdout, ours.stdout)
+
+
+_modes = st.sampled_from(["nowait", "host_threads", "in_order", "out_of_order", "fused", "serial"])
+_cmds = st.lists(st.sampled_from(["C", "MD", "DM", "HD", "DH", "DP", "A", "T"]), min_size=1, max_size=3).map(" ".join)
+_verdict = st.tuples(_modes, _cmds, st.sampled_from(["SUCCESS: Close from Theoretical Speedup",
+                                                     "FAILURE: Far from Theoretical Speedup",
+                                                     "FAILURE: Minimun Bandwish not reached"])
+                     ).map(lambda t: f"## {t[0]} | {t[1]} | {t[2]}")
+_export = st.lists(st.sampled_from(["CUDA_VISIBLE_DEVICES=0", "HPCP_FUSED_COPY_ENGINE=1", "OMP_PROC_BIND=false",
+                                    "CUDA_DEVICE_MAX_CONNECTIONS=32", "A=1 B=2"]), min_size=1, max_size=2
+                   ).map(lambda v: "+ export " + " ".join(v))
+_noise = st.sampled_from(["# nowait | C MD | Starting Benchmarking...", "Minimum Measured Total Time Serial: 12us",
+                          "  Minimum Time Command 0 (  C): 7us", "Speedup Relative to Serial: 1.9x", "",
+                          "Parameters used:", "  tripcount_C: 40000", "+ ./omp_con nowait --commands C M2D"])
+
+
+@given(lines=st.lists(st.one_of(_verdict, _verdict, _export, _noise), min_size=0, max_size=25),
+       fmt=st.sampled_from(["simple", "github", "plain"]))
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+def test_random_logs_render_like_the_reference_parser(tmp_path, lines, fmt):
+    """The reference's parse.py and ours print the same tables for any log a sweep script can produce."""
+    log = tmp_path / "fuzz.log"
+    log.write_text("\n".join(lines) + "\n")
+    theirs = subprocess.run([sys.executable, os.path.join(REF_CON, "parse.py"), str(log), fmt], capture_output=True,
+                            text=True, timeout=60)
+    mine = subprocess.run([sys.executable, "-m", "hpc_patterns_b200.utils.parse", str(log), fmt], capture_output=True,
+                          text=True, env=dict(os.environ, PYTHONPATH=ROOT), timeout=60)
+    assert theirs.returncode == 0 and mine.returncode == 0, theirs.stderr + mine.stderr
+    assert mine.stdout == theirs.stdout, (lines, theirs.stdout, mine.stdout)
