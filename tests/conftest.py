@@ -8,6 +8,18 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# Property tests draw the SAME examples on every run of the suite (what passed here is what runs elsewhere);
+# HYPOTHESIS_PROFILE=explore draws fresh ones.
+try:
+    from hypothesis import settings as _hyp_settings
+
+    _hyp_settings.register_profile("suite", derandomize=True, deadline=None)
+    _hyp_settings.register_profile("explore", deadline=None)
+    _hyp_settings.load_profile(os.environ.get("HYPOTHESIS_PROFILE", "suite"))
+except ImportError:  # hypothesis is optional for the GPU box
+    pass
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs at least one CUDA GPU (run with -m gpu on a B200 box)")
 
