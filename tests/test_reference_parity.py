@@ -124,7 +124,7 @@ _flags = st.lists(st.sampled_from([["--verbose"], ["--enable_profiling"], ["--qu
                   min_size=0, max_size=3)
 
 
-@given(groups=_groups, flags=_flags, mode=st.sampled_from(["nowait", "serial", "in_order", ""]))
+@given(groups=_groups, flags=_flags, mode=st.sampled_from(["nowait", "host_threads", "serial", "in_order", ""]))
 @settings(max_examples=60, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture])
 def test_random_command_lines_behave_like_the_reference(ref_bins, bin_dir, groups, flags, mode):
     """Random argv (valid and invalid) through the reference binary and ours: same exit status, same usage-or-run
@@ -138,7 +138,7 @@ def test_random_command_lines_behave_like_the_reference(ref_bins, bin_dir, group
         argv += ["--globalsize_" + cmd, "2000"]
     for g in groups:
         argv += ["--commands"] + list(g)
-    ref = subprocess.run([ref_bins["nowait"]] + argv, capture_output=True, text=True, timeout=120)
+    ref = subprocess.run([ref_bins.get(mode, ref_bins["nowait"])] + argv, capture_output=True, text=True, timeout=120)
     ours = subprocess.run([os.path.join(bin_dir, "omp_con")] + argv, capture_output=True, text=True, timeout=120)
     ref_usage = "--commands" in ref.stdout and "## " not in ref.stdout and ref.returncode == 1
     ours_usage = "--commands" in ours.stdout and "## " not in ours.stdout and ours.returncode == 1
