@@ -425,6 +425,25 @@ void launch_pairs(Kernel kernel, int grid, size_t smem, cudaStream_t stream, con
   HPCP_CUDA(cudaLaunchKernelEx(&cfg, kernel, args...));
 }
 
+// One launch of a tile-loop kernel family: `single` on plain CTAs (B box = the whole 256-row tile), or `pair` on
+// clusters of two (each CTA fetches half of the B tile: box = 128 rows).  Returns the number of CTAs launched.
+template <class Single, class Pair, class... Rest>
+int launch_tile_loop(Single single, Pair pair, bool pairs, int grid, size_t smem_single, size_t smem_pair,
+                     cudaStream_t stream, const CUtensorMap& map_a, const void* b, int n, int k, const Rest&... rest) {
+  if (!pairs || grid < 2) {
+    const CUtensorMap map_b = make_kmajor_map(b, n, k, kBN);
+    HPCP_ENABLE_SMEM(single, smem_single);
+    single<<<grid, kThreads, smem_single, stream>>>(map_a, map_b, rest...);
+    HPCP_CUDA(cudaGetLastError());
+    return grid;
+  }
+  grid &= ~1;  // whole pairs
+  const CUtensorMap map_b = make_kmajor_map(b, n, k, kBN / 2);
+  HPCP_ENABLE_SMEM(pair, smem_pair);
+  launch_pairs(pair, grid, smem_pair, stream, map_a, map_b, rest...);
+  return grid;
+}
+
 }  // namespace
 
 void launch_wait_flags(const uint32_t* flags, int count, uint32_t epoch, uint64_t timeout_ns, uint32_t* status,
@@ -483,47 +502,19 @@ int launch_gemm_reduce_scatter(const GemmRsArgs& args, int ctas, int device, cud
     for (int q = 0; q < args.world; ++q) maps.shard[q] = make_c_tile_map(args.shard[q], args.m / args.world, args.n, false);
     constexpr size_t smem_t = gemm_smem_bytes<kStages>(kTmaEpiSmemBytes - kEpiWarps * kEpiWarpBytes);
     static_assert(smem_t + 1024 <= 227 * 1024, "GEMM stages + two reduce tiles per epilogue warp must fit in 227 KiB");
-    if (!pairs || grid < 2) {
-      const CUtensorMap map_b = make_kmajor_map(args.b, args.n, args.k, kBN);
-      HPCP_ENABLE_SMEM(gemm_reduce_scatter_tma_kernel<1>, smem_t);
-      gemm_reduce_scatter_tma_kernel<1><<<grid, kThreads, smem_t, stream>>>(map_a, map_b, g, maps);
-      HPCP_CUDA(cudaGetLastError());
-      return grid;
-    }
-    grid &= ~1;
-    const CUtensorMap map_b = make_kmajor_map(args.b, args.n, args.k, kBN / 2);
-    HPCP_ENABLE_SMEM(gemm_reduce_scatter_tma_kernel<2>, smem_t);
-    launch_pairs(gemm_reduce_scatter_tma_kernel<2>, grid, smem_t, stream, map_a, map_b, g, maps);
-    return grid;
+    return launch_tile_loop(gemm_reduce_scatter_tma_kernel<1>, gemm_reduce_scatter_tma_kernel<2>, pairs, grid, smem_t,
+                            smem_t, stream, map_a, args.b, args.n, args.k, g, maps);
   }
-  if (!pairs || grid < 2) {
-    const CUtensorMap map_b = make_kmajor_map(args.b, args.n, args.k, kBN);
-    if (all_reduce) {
-      HPCP_ENABLE_SMEM(gemm_allreduce_kernel<1>, smem);
-      gemm_allreduce_kernel<1><<<grid, kThreads, smem, stream>>>(map_a, map_b, g);
-    } else {
-      HPCP_ENABLE_SMEM(gemm_reduce_scatter_kernel<1>, smem);
-      gemm_reduce_scatter_kernel<1><<<grid, kThreads, smem, stream>>>(map_a, map_b, g);
-    }
-    HPCP_CUDA(cudaGetLastError());
-    return grid;
-  }
-  HPCP_REQUIRE(cluster != 3 || grid >= 2, "gemm_reduce_scatter: cluster=3 needs at least two CTAs");
-  grid &= ~1;
-  const CUtensorMap map_b = make_kmajor_map(args.b, args.n, args.k, kBN / 2);
+  if (all_reduce)
+    return launch_tile_loop(gemm_allreduce_kernel<1>, gemm_allreduce_kernel<2>, pairs, grid, smem, smem, stream, map_a,
+                            args.b, args.n, args.k, g);
   if (cluster == 3) {
-    HPCP_ENABLE_SMEM(gemm_reduce_scatter_2sm_kernel, gemm_2sm_smem_bytes(0));
-    launch_pairs(gemm_reduce_scatter_2sm_kernel, grid, gemm_2sm_smem_bytes(0), stream, map_a, map_b, g);
-    return grid;
+    HPCP_REQUIRE(grid >= 2, "gemm_reduce_scatter: cluster=3 needs at least two CTAs");
+    return launch_tile_loop(gemm_reduce_scatter_kernel<1>, gemm_reduce_scatter_2sm_kernel, true, grid, smem,
+                            gemm_2sm_smem_bytes(0), stream, map_a, args.b, args.n, args.k, g);
   }
-  if (all_reduce) {
-    HPCP_ENABLE_SMEM(gemm_allreduce_kernel<2>, smem);
-    launch_pairs(gemm_allreduce_kernel<2>, grid, smem, stream, map_a, map_b, g);
-    return grid;
-  }
-  HPCP_ENABLE_SMEM(gemm_reduce_scatter_kernel<2>, smem);
-  launch_pairs(gemm_reduce_scatter_kernel<2>, grid, smem, stream, map_a, map_b, g);
-  return grid;
+  return launch_tile_loop(gemm_reduce_scatter_kernel<1>, gemm_reduce_scatter_kernel<2>, pairs, grid, smem, smem, stream,
+                          map_a, args.b, args.n, args.k, g);
 }
 
 int launch_gemm_all_to_all(const GemmA2aArgs& args, int ctas, int device, cudaStream_t stream, int cluster) {
@@ -556,18 +547,8 @@ int launch_gemm_all_to_all(const GemmA2aArgs& args, int ctas, int device, cudaSt
   const CUtensorMap map_a = make_kmajor_map(args.a, args.m, args.k, kBM);
   int grid = std::min(s.tiles_m * s.tiles_n, ctas > 0 ? ctas : device_sm_count(device));
   constexpr size_t smem = gemm_smem_bytes<kStages>(0);
-  if (!pairs || grid < 2) {
-    const CUtensorMap map_b = make_kmajor_map(args.b, args.n, args.k, kBN);
-    HPCP_ENABLE_SMEM(gemm_all_to_all_kernel<1>, smem);
-    gemm_all_to_all_kernel<1><<<grid, kThreads, smem, stream>>>(map_a, map_b, g);
-    HPCP_CUDA(cudaGetLastError());
-    return grid;
-  }
-  grid &= ~1;
-  const CUtensorMap map_b = make_kmajor_map(args.b, args.n, args.k, kBN / 2);
-  HPCP_ENABLE_SMEM(gemm_all_to_all_kernel<2>, smem);
-  launch_pairs(gemm_all_to_all_kernel<2>, grid, smem, stream, map_a, map_b, g);
-  return grid;
+  return launch_tile_loop(gemm_all_to_all_kernel<1>, gemm_all_to_all_kernel<2>, pairs, grid, smem, smem, stream, map_a,
+                          args.b, args.n, args.k, g);
 }
 
 uint32_t allgather_gemm_chunks_per_block(int k, int chunk_bytes) {
@@ -628,26 +609,15 @@ int launch_allgather_gemm(const AgGemmArgs& args, int ctas, int device, cudaStre
   constexpr size_t smem = gemm_smem_bytes<kStages>(kGatherSmemBytes);
   static_assert(smem + 1024 <= 227 * 1024,  // + the static barriers, padded to the 1 KiB alignment of the ring
                 "GEMM stages + epilogue staging + gather ring must fit in 227 KiB");
-  if (!pairs || grid < 2) {
-    const CUtensorMap map_b = make_kmajor_map(args.b, args.n, args.k, kBN);
-    HPCP_ENABLE_SMEM(allgather_gemm_kernel<1>, smem);
-    allgather_gemm_kernel<1><<<grid, kThreads, smem, stream>>>(map_a, map_b, g);
-    HPCP_CUDA(cudaGetLastError());
-    return grid;
-  }
-  HPCP_REQUIRE(cluster != 3 || grid >= 2, "allgather_gemm: cluster=3 needs at least two CTAs");
-  grid &= ~1;
-  const CUtensorMap map_b = make_kmajor_map(args.b, args.n, args.k, kBN / 2);
   if (cluster == 3) {
+    HPCP_REQUIRE(grid >= 2, "allgather_gemm: cluster=3 needs at least two CTAs");
     constexpr size_t smem2 = gemm_2sm_smem_bytes(kGatherSmemBytes);
     static_assert(smem2 + 1024 <= 227 * 1024, "2-SM stages + epilogue staging + gather ring must fit in 227 KiB");
-    HPCP_ENABLE_SMEM(allgather_gemm_2sm_kernel, smem2);
-    launch_pairs(allgather_gemm_2sm_kernel, grid, smem2, stream, map_a, map_b, g);
-    return grid;
+    return launch_tile_loop(allgather_gemm_kernel<1>, allgather_gemm_2sm_kernel, true, grid, smem, smem2, stream, map_a,
+                            args.b, args.n, args.k, g);
   }
-  HPCP_ENABLE_SMEM(allgather_gemm_kernel<2>, smem);
-  launch_pairs(allgather_gemm_kernel<2>, grid, smem, stream, map_a, map_b, g);
-  return grid;
+  return launch_tile_loop(allgather_gemm_kernel<1>, allgather_gemm_kernel<2>, pairs, grid, smem, smem, stream, map_a,
+                          args.b, args.n, args.k, g);
 }
 
 }  // namespace hpcp
