@@ -20,7 +20,17 @@ template <int M, int N> void row() {
   auto d = UMMA::make_instr_desc<bfloat16_t, bfloat16_t, float, M, N, UMMA::Major::K, UMMA::Major::K>();
   printf("%d %d %08x %08x\n", M, N, uint32_t(d), hpcp::umma::make_idesc(M, N));
 }
-int main() { row<128, 256>(); row<256, 256>(); row<128, 128>(); row<256, 64>(); return 0; }
+int main() {
+  row<128, 256>(); row<256, 256>(); row<128, 128>(); row<256, 64>();
+  // The 128-byte swizzle the TMA epilogues write by hand (umma.cuh: epilogue_tma_tiles: chunk c of row r at
+  // c ^ (r % 8)) against CUTLASS's Swizzle<3,4,3>, the layout a SWIZZLE_128B tensor map reads / writes.
+  int bad = 0;
+  for (int r = 0; r < 32; ++r)
+    for (int c = 0; c < 8; ++c)
+      bad += int(Swizzle<3, 4, 3>{}(r * 128 + c * 16)) != r * 128 + ((c ^ (r & 7)) << 4);
+  printf("swizzle_mismatches %d\n", bad);
+  return 0;
+}
 """
 
 
@@ -50,3 +60,4 @@ def test_instruction_descriptor_matches_cutlass(tmp_path):
     assert len(rows) == 4
     for m, n, theirs, ours in rows:
         assert theirs == ours, (m, n, theirs, ours)
+    assert "swizzle_mismatches 0" in out
