@@ -32,7 +32,7 @@ constexpr uint32_t kEpiWarpBytes = 32 * kStageRowWords * 4;  // 4608 B per epilo
 // Shared-memory matrix descriptor, K-major, SWIZZLE_128B: 8-row x 128-byte atoms, atoms stacked every 1024 bytes
 // (stride byte offset); leading byte offset unused for swizzled K-major (encoded 1); descriptor version 1
 // (Blackwell); layout type 2 = SWIZZLE_128B.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+__host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);  // start address  [0,14)
   d |= static_cast<uint64_t>(1) << 16;                      // LBO            [16,30)

@@ -29,6 +29,21 @@ int main() {
     for (int c = 0; c < 8; ++c)
       bad += int(Swizzle<3, 4, 3>{}(r * 128 + c * 16)) != r * 128 + ((c ^ (r & 7)) << 4);
   printf("swizzle_mismatches %d\n", bad);
+  // Shared-memory matrix descriptor (K-major, SWIZZLE_128B, 8-row x 128-byte atoms every 1024 bytes) against
+  // CUTLASS's bit-field definition of the same descriptor.
+  int bad_desc = 0;
+  for (uint32_t addr : {0x0u, 0x400u, 0xC000u, 0x2A400u, 0x38C00u}) {
+    UMMA::SmemDescriptor d;
+    d.start_address_ = uint16_t((addr & 0x3FFFF) >> 4);
+    d.leading_byte_offset_ = 1;
+    d.stride_byte_offset_ = 1024 >> 4;
+    d.version_ = 1;
+    d.base_offset_ = 0;
+    d.lbo_mode_ = 0;
+    d.layout_type_ = uint8_t(UMMA::LayoutType::SWIZZLE_128B);
+    bad_desc += uint64_t(d) != hpcp::umma::make_smem_desc(addr);
+  }
+  printf("smem_desc_mismatches %d\n", bad_desc);
   return 0;
 }
 """
@@ -60,4 +75,4 @@ def test_instruction_descriptor_matches_cutlass(tmp_path):
     assert len(rows) == 4
     for m, n, theirs, ours in rows:
         assert theirs == ours, (m, n, theirs, ours)
-    assert "swizzle_mismatches 0" in out
+    assert "swizzle_mismatches 0" in out and "smem_desc_mismatches 0" in out
