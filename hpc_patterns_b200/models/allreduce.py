@@ -270,7 +270,8 @@ def main(argv: Optional[List[str]] = None) -> int:
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--json", default=None)
     ap.add_argument("--slots", type=int, default=0, choices=(0, 2),
-                    help="fused ring: 2 = two receive slots + per-chunk acks (VA/VB double buffer); default world-1 slots")
+                    help="fused ring: 2 = two receive slots + per-chunk acks (VA/VB double buffer); "
+                         "default world-1 slots")
     ap.add_argument("--pull", action="store_true",
                     help="fused ring, receiver-driven: blocks are loaded from the left neighbour (peer loads)")
     args = ap.parse_args(argv)

@@ -272,8 +272,8 @@ def _dyadic(shape, dev, seed):
 
 
 def main(argv: Optional[List[str]] = None) -> int:
-    """``torchrun --nproc-per-node N -m hpc_patterns_b200 tp [--check] [--tokens M --out-features N --in-features K]``: both fused layers next to
-    the stock pattern (cuBLAS + NCCL); one JSON line from rank 0."""
+    """``torchrun --nproc-per-node N -m hpc_patterns_b200 tp [--check] [--tokens M --out-features N --in-features K]``:
+    the fused layers next to the stock pattern (cuBLAS + NCCL); one JSON line from rank 0."""
     import argparse
     import json
 
@@ -392,7 +392,8 @@ def main(argv: Optional[List[str]] = None) -> int:
         t_fused = _timed(lambda: mlp.forward(xr), comm, dev, args.steps)
         t_stock = _timed(lambda: mlp.stock_forward(xr), comm, dev, args.steps)
         mlp.check()
-        out["mlp"] = {"fused_ms": round(t_fused, 4), "stock_ms": round(t_stock, 4), "speedup": round(t_stock / t_fused, 3),
+        out["mlp"] = {"fused_ms": round(t_fused, 4), "stock_ms": round(t_stock, 4),
+                      "speedup": round(t_stock / t_fused, 3),
                       "fused_tflops_per_gpu": round(4.0 * args.m * (args.n // P) * args.k / t_fused / 1e9, 1)}
         mlp.close()
     if comm.rank == 0:

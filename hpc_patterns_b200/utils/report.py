@@ -63,7 +63,8 @@ def p2p_table(rows: List[Dict]) -> str:
 
 
 def allreduce_table(rows: List[Dict]) -> str:
-    out = ["| algo | type | ranks | elements | ms | GB/s sent per rank | / 770 | / 900 |", "|---|---|---|---|---|---|---|---|"]
+    out = ["| algo | type | ranks | elements | ms | GB/s sent per rank | / 770 | / 900 |",
+           "|---|---|---|---|---|---|---|---|"]
     for r in rows:
         if r.get("pattern") != "allreduce":
             continue
@@ -90,8 +91,8 @@ def tensor_parallel_table(rows: List[Dict], root: str = ".") -> str:
     layer).  The roofline of a fused layer is the slower of its GEMM at the measured cuBLAS rate and its bytes over
     NVLink at the measured 770 GB/s per direction."""
     peak = measured_bf16_tflops(root)
-    out = ["| layer | ranks | M | N | K | fused ms | stock ms (cuBLAS + NCCL) | speed-up | TFLOP/s per GPU | roofline ms "
-           "(tensor / NVLink) | fraction |", "|---|---|---|---|---|---|---|---|---|---|---|"]
+    out = ["| layer | ranks | M | N | K | fused ms | stock ms (cuBLAS + NCCL) | speed-up | TFLOP/s per GPU | "
+           "roofline ms (tensor / NVLink) | fraction |", "|---|---|---|---|---|---|---|---|---|---|---|"]
     for r in rows:
         if "row_parallel" not in r and "column_parallel" not in r:
             continue
@@ -106,24 +107,27 @@ def tensor_parallel_table(rows: List[Dict], root: str = ".") -> str:
             t_tensor = flops / (peak * 1e9)
             t_link = link_bytes / (NVLINK_MEASURED_GBPS * 1e6)
             roof = max(t_tensor, t_link)
-            out.append(f"| {name}{' (chunk ' + str(r['chunk']) + ')' if 'chunk' in r else ''} | {P} | {m} | {n} | {k} | "
-                       f"{d['fused_ms']:.4f} | {d['stock_ms']:.4f} | {d['speedup']:.2f} | "
-                       f"{flops / d['fused_ms'] / 1e9:.0f} | {t_tensor:.3f} / {t_link:.3f} | {roof / d['fused_ms']:.2f} |")
+            label = name + (f" (chunk {r['chunk']})" if "chunk" in r else "")
+            out.append(f"| {label} | {P} | {m} | {n} | {k} | {d['fused_ms']:.4f} | {d['stock_ms']:.4f} | "
+                       f"{d['speedup']:.2f} | {flops / d['fused_ms'] / 1e9:.0f} | {t_tensor:.3f} / {t_link:.3f} | "
+                       f"{roof / d['fused_ms']:.2f} |")
     return "\n".join(out)
 
 
 def gemm_table(rows: List[Dict], root: str = ".") -> str:
     """Rows of scripts/gemm_put_bench.py."""
     peak = measured_bf16_tflops(root)
-    out = ["| M | N | K | ranks | ours TFLOP/s | 2-SM UMMA | cuBLAS | ours / measured peak | fused GEMM->put ms | stock ms |",
-           "|---|---|---|---|---|---|---|---|---|---|"]
+    out = ["| M | N | K | ranks | ours TFLOP/s | 2-SM UMMA | cuBLAS | ours / measured peak | fused GEMM->put ms | "
+           "stock ms |", "|---|---|---|---|---|---|---|---|---|---|"]
     for r in rows:
         if "gemm_tflops" not in r:
             continue
         two = r.get("gemm_tflops_2sm")
+        best = max(r["gemm_tflops"], two or 0)
+        nan = float("nan")
         out.append(f"| {r['m']} | {r['n']} | {r['k']} | {r.get('ranks', 1)} | {r['gemm_tflops']:.0f} | "
-                   f"{'%.0f' % two if two else '-'} | {r['cublas_tflops']:.0f} | {max(r['gemm_tflops'], two or 0) / peak:.2f} | "
-                   f"{r.get('fused_gemm_put_ms', float('nan')):.3f} | {r.get('stock_cublas_then_memcpy_ms', float('nan')):.3f} |")
+                   f"{'%.0f' % two if two else '-'} | {r['cublas_tflops']:.0f} | {best / peak:.2f} | "
+                   f"{r.get('fused_gemm_put_ms', nan):.3f} | {r.get('stock_cublas_then_memcpy_ms', nan):.3f} |")
     return "\n".join(out)
 
 
