@@ -254,7 +254,7 @@ struct AgDev {
   void* c_local;                              // fp32 or bf16 [M, N]
   void* c_peer;                               // unused (kept for the shared epilogue): always null
   int out_bf16;
-  int activation;                             // 0 none, 1 relu, 2 gelu (tanh form), 3 silu — applied to C before it is stored
+  int activation;                             // 0 none, 1 relu, 2 gelu (tanh form), 3 silu: applied before the store
   uint32_t* ready;                            // local [M/128] arrival counters (monotonic)
   uint32_t ready_target;                      // value a peer block's counter reaches when it is complete
   uint32_t chunk_bytes;                       // gather granularity, divides the 128-row block size

@@ -215,7 +215,8 @@ __global__ void __launch_bounds__(512) ring_pull_kernel(const __grid_constant__ 
       for (; i + 3 * blockDim.x < end; i += 4 * blockDim.x) {
         uint4 x[4], acc[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) x[k] = t == 0 ? ptx::ld_weak_v4(src + i + k * blockDim.x) : ptx::ld_peer_v4(src + i + k * blockDim.x);
+        for (int k = 0; k < 4; ++k)
+          x[k] = t == 0 ? ptx::ld_weak_v4(src + i + k * blockDim.x) : ptx::ld_peer_v4(src + i + k * blockDim.x);
 #pragma unroll
         for (int k = 0; k < 4; ++k) acc[k] = a.vc[i + k * blockDim.x];
 #pragma unroll

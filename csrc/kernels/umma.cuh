@@ -368,7 +368,8 @@ __device__ __forceinline__ void epilogue_tma_tiles(bool out_bf16, uint32_t taddr
       tmem_ld_32x32b_x32(taddr + col, r);
 #pragma unroll
       for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(row + ((c ^ (lane & 7)) << 4)) = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+        *reinterpret_cast<uint4*>(row + ((c ^ (lane & 7)) << 4)) =
+            make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
     }
     fence_proxy_async_smem();  // my generic-proxy writes before the async-proxy read of the tile
     __syncwarp();
