@@ -13,6 +13,7 @@
 #include <cstring>
 #include <iostream>
 #include <sstream>
+#include <type_traits>
 
 #include "common/cuda_check.h"
 #include "common/driver_api.h"
@@ -59,6 +60,21 @@ CopyTuning tuning_from(const py::dict& d) {
   if (d.contains("blocked")) t.blocked = d["blocked"].cast<int>();
   if (d.contains("halo_ctas")) t.halo_ctas = d["halo_ctas"].cast<int>();
   if (d.contains("l2_hint")) t.l2_hint = d["l2_hint"].cast<int>();
+  return t;
+}
+
+HaloMode halo_mode_from(const std::string& s) {
+  if (s == "none") return HaloMode::kNone;
+  if (s == "pull") return HaloMode::kPull;
+  if (s == "push") return HaloMode::kPush;
+  throw std::invalid_argument("halo mode must be 'pull', 'push' or 'none'");
+}
+
+HaloTuning halo_tuning_from(const py::dict& d) {
+  HaloTuning t;
+  if (d.contains("ctas")) t.ctas = d["ctas"].cast<int>();
+  if (d.contains("tile_kb")) t.tile_kb = d["tile_kb"].cast<int>();
+  if (d.contains("stages")) t.stages = d["stages"].cast<int>();
   return t;
 }
 
@@ -295,6 +311,70 @@ PYBIND11_MODULE(_C, m) {
           launch_verify_triad(as_ptr<const float>(a), n, src_rank, s,
                               as_ptr<unsigned long long>(mismatch), as_stream(stream));
         });
+
+  // --------------------------------------------- fused stencil + halo exchange ----
+  m.attr("HALO_FLAG_BYTES") = static_cast<size_t>(kHaloFlagBytes);
+  m.attr("HALO_FLAG_SETS") = kHaloFlagSets;
+  m.attr("HALO_MAX_CTAS") = kHaloMaxCtas;
+  m.def(
+      "halo_stencil_ctas",
+      [](size_t row_elems, const std::string& mode, const py::dict& tune, int device) {
+        return halo_stencil_ctas(row_elems, halo_tuning_from(tune), halo_mode_from(mode), device);
+      },
+      py::arg("row_elems"), py::arg("mode") = "pull", py::arg("tune") = py::dict(), py::arg("device") = 0);
+  m.def(
+      "halo_stencil",
+      [](const py::dict& d, const std::string& mode, const py::dict& tune, int device, uintptr_t stream) {
+        HaloStencilArgs a;
+        auto pair = [&](const char* key, auto& dst) {
+          if (!d.contains(key)) return;
+          const auto v = d[key].cast<std::vector<uintptr_t>>();
+          HPCP_REQUIRE(v.size() == 2, std::string("halo_stencil: '") + key + "' must hold two addresses");
+          for (int q = 0; q < 2; ++q) dst[q] = as_ptr<std::remove_pointer_t<std::decay_t<decltype(dst[0])>>>(v[q]);
+        };
+        pair("u", a.u);
+        pair("left_u", a.left_u);
+        pair("right_u", a.right_u);
+        pair("halo_lo", a.halo_lo);
+        pair("halo_hi", a.halo_hi);
+        pair("left_halo_hi", a.left_halo_hi);
+        pair("right_halo_lo", a.right_halo_lo);
+        if (d.contains("flags_local")) a.flags_local = as_ptr<uint32_t>(d["flags_local"].cast<uintptr_t>());
+        if (d.contains("flags_left")) a.flags_left = as_ptr<uint32_t>(d["flags_left"].cast<uintptr_t>());
+        if (d.contains("flags_right")) a.flags_right = as_ptr<uint32_t>(d["flags_right"].cast<uintptr_t>());
+        if (d.contains("flag_set")) a.flag_set = d["flag_set"].cast<int>();
+        a.rows = d["rows"].cast<int>();
+        a.row_elems = d["row_elems"].cast<size_t>();
+        if (d.contains("tile_begin")) a.tile_begin = d["tile_begin"].cast<size_t>();
+        if (d.contains("tile_end")) a.tile_end = d["tile_end"].cast<size_t>();
+        if (d.contains("alpha")) a.alpha = d["alpha"].cast<float>();
+        if (d.contains("s")) a.s = d["s"].cast<float>();
+        if (d.contains("step_base")) a.step_base = d["step_base"].cast<uint32_t>();
+        if (d.contains("steps")) a.steps = d["steps"].cast<int>();
+        if (d.contains("timeout_ns")) a.timeout_ns = d["timeout_ns"].cast<uint64_t>();
+        if (d.contains("status")) a.status = as_ptr<uint32_t>(d["status"].cast<uintptr_t>());
+        return launch_halo_stencil(a, halo_mode_from(mode), halo_tuning_from(tune), device, as_stream(stream));
+      },
+      py::arg("args"), py::arg("mode") = "pull", py::arg("tune") = py::dict(), py::arg("device") = 0,
+      py::arg("stream") = 0,
+      "Fused 3-point slab stencil + halo exchange with both ring neighbours (pull / push / none); `steps` steps in one "
+      "persistent launch.  Returns the number of CTAs.");
+  m.def("halo_init", [](uintptr_t u, uintptr_t halo_lo, uintptr_t halo_hi, int rows, size_t row_elems, int rank,
+                        int world, uintptr_t stream) {
+    launch_halo_init(as_ptr<float>(u), as_ptr<float>(halo_lo), as_ptr<float>(halo_hi), rows, row_elems, rank, world,
+                     as_stream(stream));
+  });
+  m.def("halo_verify_from_init", [](uintptr_t u, int rows, size_t row_elems, int rank, int world, uint32_t steps,
+                                    float alpha, float s, uintptr_t mismatch, uintptr_t stream) {
+    launch_halo_verify_from_init(as_ptr<const float>(u), rows, row_elems, rank, world, steps, alpha, s,
+                                 as_ptr<unsigned long long>(mismatch), as_stream(stream));
+  });
+  m.def("halo_verify_step", [](uintptr_t u_new, uintptr_t u_old, uintptr_t up_row, uintptr_t dn_row, int rows,
+                               size_t row_elems, float alpha, float s, uintptr_t mismatch, uintptr_t stream) {
+    launch_halo_verify_step(as_ptr<const float>(u_new), as_ptr<const float>(u_old), as_ptr<const float>(up_row),
+                            as_ptr<const float>(dn_row), rows, row_elems, alpha, s,
+                            as_ptr<unsigned long long>(mismatch), as_stream(stream));
+  });
 
   // ------------------------------------------------- concurrency payloads ----
   m.def("busy_wait", [](uintptr_t out, size_t n_items, size_t tripcount, uintptr_t stream) {

@@ -103,6 +103,59 @@ void launch_fill_triad_inputs(float* b, float* c, size_t n, int rank, cudaStream
 void launch_verify_triad(const float* a, size_t n, int src_rank, float s,
                          unsigned long long* mismatch_count, cudaStream_t stream);
 
+// ------------------------------------- fused stencil + halo exchange (flagship) ----
+// One step: u'[r][j] = alpha*u[r][j] + s*(u[r-1][j] + u[r+1][j]) over this rank's slab [rows][row_elems] of a field
+// that is periodic in r and split over the ring of ranks; rows -1 / `rows` are the neighbours' boundary rows.
+// kPull reads them out of the neighbours' fields over NVLink inside the kernel, kPush stores the new boundary rows
+// into the neighbours' halo buffers from inside the kernel, kNone only reads local halo buffers (the compute kernel of
+// the stock kernel -> library transfer -> wait arm).  `steps` steps run in ONE persistent launch; neighbouring CTAs of
+// the same index synchronise through monotonic step words (no grid barrier, no host sync).  See halo_stencil.cu.
+enum class HaloMode : int { kNone = 0, kPull = 1, kPush = 2 };
+constexpr int kHaloFlagWords = 8;    // one 32-byte sector per flag word
+constexpr int kHaloMaxCtas = 1024;   // flag words per side
+constexpr int kHaloFlagSets = 16;    // independent flag sets (chunked launches of one step use one set per chunk)
+constexpr size_t kHaloFlagBytes = static_cast<size_t>(kHaloFlagSets) * 2 * kHaloMaxCtas * kHaloFlagWords * 4;
+struct HaloTuning {
+  int ctas = 0;     // 0 -> every resident CTA slot (SMs x occupancy); always clamped to it
+  int tile_kb = 0;  // bytes of a row per shared-memory stage in KiB; 0 -> 16
+  int stages = 0;   // shared-memory stages (>= 6); 0 -> 12
+};
+struct HaloStencilArgs {
+  float* u[2] = {nullptr, nullptr};                 // local field, ping-pong: step g reads u[g&1], writes u[(g+1)&1]
+  const float* left_u[2] = {nullptr, nullptr};      // pull: the left / right neighbour's u[0], u[1] (peer-mapped)
+  const float* right_u[2] = {nullptr, nullptr};
+  float* halo_lo[2] = {nullptr, nullptr};           // push / none: local halo rows by step parity (from the left ...
+  float* halo_hi[2] = {nullptr, nullptr};           // ... and from the right neighbour)
+  float* left_halo_hi[2] = {nullptr, nullptr};      // push: the left neighbour's halo_hi (receives my new row 0)
+  float* right_halo_lo[2] = {nullptr, nullptr};     // push: the right neighbour's halo_lo (receives my new last row)
+  uint32_t* flags_local = nullptr;                  // kHaloFlagBytes of zeroed words on every rank
+  uint32_t* flags_left = nullptr;                   // the neighbours' flag buffers (peer-mapped)
+  uint32_t* flags_right = nullptr;
+  int flag_set = 0;
+  int rows = 0;
+  size_t row_elems = 0;                             // multiple of 4
+  size_t tile_begin = 0, tile_end = 0;              // column tiles of a row to process; end 0 -> all
+  float alpha = 0.5f, s = 0.25f;
+  uint32_t step_base = 0;                           // global index of the first step of this launch
+  int steps = 1;
+  uint64_t timeout_ns = 0;
+  uint32_t* status = nullptr;
+};
+// CTAs a launch with this geometry uses (identical on every rank; the flag words are indexed by it).
+int halo_stencil_ctas(size_t row_elems, const HaloTuning& tune, HaloMode mode, int device);
+int launch_halo_stencil(const HaloStencilArgs& args, HaloMode mode, const HaloTuning& tune, int device,
+                        cudaStream_t stream);
+// u[r][j] = u0(rank*rows + r, j); halo_lo / halo_hi (may be null) = the neighbours' boundary rows of the initial field.
+void launch_halo_init(float* u, float* halo_lo, float* halo_hi, int rows, size_t row_elems, int rank, int world,
+                      cudaStream_t stream);
+// Exact check of this rank's rows after `steps` steps against the closed-form initial field (world*rows <= 128).
+void launch_halo_verify_from_init(const float* u, int rows, size_t row_elems, int rank, int world, uint32_t steps,
+                                  float alpha, float s, unsigned long long* mismatch_count, cudaStream_t stream);
+// Exact check of one step: u_new against the stencil of u_old with the given boundary rows (any may be peer-mapped).
+void launch_halo_verify_step(const float* u_new, const float* u_old, const float* up_row, const float* dn_row,
+                             int rows, size_t row_elems, float alpha, float s, unsigned long long* mismatch_count,
+                             cudaStream_t stream);
+
 // ------------------------------------------- fused concurrency "megakernel" ----
 // One persistent launch that executes a whole command group of the concurrency
 // benchmark: CTAs are partitioned between the commands, so compute and copies

@@ -276,9 +276,7 @@ def main(argv: Optional[List[str]] = None) -> int:
                     help="fused ring, receiver-driven: blocks are loaded from the left neighbour (peer loads)")
     args = ap.parse_args(argv)
     comm = Comm()
-    from ..parallel.tile_mapping import selected_device
-
-    device = selected_device(default=comm.local_rank) % max(torch.cuda.device_count(), 1)
+    device = comm.device   # chosen before the process group was bound to it (Comm.pick_device)
     algo = args.algo
     app = None
     if args.a:

@@ -411,9 +411,7 @@ def main(argv: Optional[List[str]] = None) -> int:
     ap.add_argument("--json", default=None)
     args = ap.parse_args(argv)
     comm = Comm()
-    from ..parallel.tile_mapping import selected_device
-
-    device = selected_device(default=comm.local_rank) % max(torch.cuda.device_count(), 1)
+    device = comm.device   # chosen before the process group was bound to it (Comm.pick_device)
     sizes = sweep_sizes() if args.sweep else (args.bytes or [REFERENCE_MESSAGE_BYTES])
     bench = P2PBench(comm, device, max(sizes), args.transport, args.engine, iters=args.iters,
                      label=args.label)

@@ -297,7 +297,7 @@ def main(argv: Optional[List[str]] = None) -> int:
         return 1
 
     comm = Comm()
-    dev = comm.local_rank % torch.cuda.device_count()
+    dev = comm.device
     torch.cuda.set_device(dev)
     device = torch.device("cuda", dev)
     P = comm.world

@@ -21,12 +21,17 @@ import torch.distributed as dist
 class Comm:
     """rank / world / barrier / scalar reductions / object all-gather."""
 
-    def __init__(self, backend: str | None = None, timeout_s: float = 600.0):
+    def __init__(self, backend: str | None = None, timeout_s: float = 600.0, device: int | None = None):
+        """``device``: the CUDA ordinal this rank computes on.  Default: what the rank->device wrapper chose
+        (``HPCP_DEVICE`` under ``tile_mapping ... SET``), else LOCAL_RANK, wrapped to the visible devices — the
+        process group is bound to THAT device, so NCCL collectives and the kernels agree on the GPU
+        (``spread`` on 8 GPUs puts rank 1 on GPU 4, not on GPU LOCAL_RANK)."""
         self.rank = int(os.environ.get("RANK", "0"))
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", str(self.rank)))
         self._owns_group = False
         self.backend = "single"
+        self.device = self.pick_device(self.local_rank) if device is None else int(device)
         if self.world > 1:
             if not dist.is_initialized():
                 if backend is None:
@@ -35,11 +40,20 @@ class Comm:
                 os.environ.setdefault("MASTER_PORT", "29511")
                 kwargs = {}
                 if torch.cuda.is_available():
-                    kwargs["device_id"] = torch.device("cuda", self.local_rank)
+                    torch.cuda.set_device(self.device)
+                    kwargs["device_id"] = torch.device("cuda", self.device)
                 dist.init_process_group(backend, rank=self.rank, world_size=self.world,
                                         timeout=datetime.timedelta(seconds=timeout_s), **kwargs)
                 self._owns_group = True
             self.backend = dist.get_backend()
+
+    @staticmethod
+    def pick_device(local_rank: int, n_devices: int | None = None) -> int:
+        from .tile_mapping import selected_device
+
+        if n_devices is None:
+            n_devices = torch.cuda.device_count() if torch.cuda.is_available() else 0
+        return selected_device(default=local_rank) % max(n_devices, 1)
 
     # -- collectives on host scalars / objects -------------------------------------------
     def barrier(self) -> None:

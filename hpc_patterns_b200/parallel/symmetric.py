@@ -55,6 +55,21 @@ class SymmetricBuffer:
                     self.ptrs.append(p)
             comm.barrier()
 
+    @classmethod
+    def local_group(cls, comms: list, nbytes: int, devices: List[int], zero: bool = True) -> List["SymmetricBuffer"]:
+        """In-process twin for ``parallel.local.LocalGroup``: one allocation per virtual rank (several may share a
+        GPU), every view sees all of them through plain pointers (peer access must be enabled between the GPUs)."""
+        C = native()
+        local = [C.alloc(int(nbytes), "D", dev, zero) for dev in devices]
+        out = []
+        for comm, dev, ptr in zip(comms, devices, local):
+            b = cls.__new__(cls)
+            b.C, b.comm, b.nbytes, b.device = C, comm, int(nbytes), dev
+            b.rank, b.world = comm.rank, comm.world
+            b.local_ptr, b._opened, b.ptrs = ptr, [], list(local)
+            out.append(b)
+        return out
+
     def tensor(self, dtype: torch.dtype = torch.uint8) -> torch.Tensor:
         return tensor_from_ptr(self.local_ptr, self.nbytes, self.device, dtype)
 
@@ -73,17 +88,22 @@ class SymmetricBuffer:
 class SignalPads:
     """Per-rank signal pad (see csrc/common/signal.cuh) + status word + epoch bookkeeping."""
 
-    def __init__(self, comm: Comm, device: int, extra_words: int = 0, timeout_s: float = 20.0):
+    def __init__(self, comm: Comm, device: int, extra_words: int = 0, timeout_s: float = 20.0,
+                 buf: Optional[SymmetricBuffer] = None):
         self.C = native()
         self.comm = comm
         self.device = device
         self.rank, self.world = comm.rank, comm.world
         self.extra_words = int(extra_words)
-        words = self.C.PAD_WORDS + self.extra_words + self.C.PAD_TAIL_WORDS
-        self.buf = SymmetricBuffer(comm, words * 4, device, zero=True)
+        self.buf = buf if buf is not None else SymmetricBuffer(comm, self.pad_bytes(extra_words), device, zero=True)
         self.timeout_ns = int(timeout_s * 1e9)
         self.ticket_issued = 0
         self.barrier_epoch = 0
+
+    @staticmethod
+    def pad_bytes(extra_words: int = 0) -> int:
+        C = native()
+        return 4 * (C.PAD_WORDS + int(extra_words) + C.PAD_TAIL_WORDS)
 
     def word(self, rank: int, index: int) -> int:
         return self.buf.ptrs[rank] + 4 * index

@@ -1,10 +1,16 @@
 """Sample SM clocks / throttle reasons while a timed region runs.
 
-Follows the profiling recipe: the sampler starts right before the timed region, is
-stopped right after it, and the summary (median SM MHz under load, max SM MHz, active
-throttle reasons) is attached to every reported number.  Timed regions here are tens of
-milliseconds, far shorter than an ``nvidia-smi -lms`` period, so the primary sampler is an
-NVML polling thread (``pynvml``, ~1 kHz); ``nvidia-smi`` is the fallback.
+Follows the profiling recipe: samples are taken DURING the timed regions and the summary
+(median SM MHz under load, max SM MHz, active throttle reasons) is attached to every reported
+number.  Timed regions here are tens of milliseconds, far shorter than an ``nvidia-smi -lms``
+period, so the primary sampler is an NVML polling thread (``pynvml``, ~1 kHz); ``nvidia-smi``
+is the fallback.
+
+``start()`` does all the slow work (``nvmlInit``, handle lookup, thread start) and must be called
+well before any timed region — never between a cross-rank barrier and the start event: NVML
+calls take tens of milliseconds when eight processes keep the GPUs busy, and the other ranks'
+kernels would wait for this rank inside their timed region (that was the 7.3 ms/step of the
+round-1 8-GPU record).  ``pause()`` / ``resume()`` only flip a flag the polling thread reads.
 """
 from __future__ import annotations
 
@@ -51,6 +57,7 @@ class ClockSampler:
         self.period_s = max(period_ms, 0.2) * 1e-3
         self._thread: Optional[threading.Thread] = None
         self._stop = threading.Event()
+        self._active = True
         self._sm: List[float] = []
         self._power: List[float] = []
         self._reasons: set = set()
@@ -62,6 +69,9 @@ class ClockSampler:
     # ---- NVML thread ---------------------------------------------------------------
     def _nvml_loop(self, nv, handle) -> None:
         while not self._stop.is_set():
+            if not self._active:
+                time.sleep(self.period_s)
+                continue
             try:
                 self._sm.append(float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)))
                 self._power.append(nv.nvmlDeviceGetPowerUsage(handle) / 1000.0)
@@ -76,7 +86,14 @@ class ClockSampler:
                 pass
             time.sleep(self.period_s)
 
-    def start(self) -> "ClockSampler":
+    def pause(self) -> None:
+        self._active = False
+
+    def resume(self) -> None:
+        self._active = True
+
+    def start(self, paused: bool = False) -> "ClockSampler":
+        self._active = not paused
         try:
             import pynvml as nv
 

@@ -7,14 +7,44 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 from hpc_patterns_b200.models.allreduce import AllreduceMiniapp  # noqa: E402
+from hpc_patterns_b200.models.halo import HaloStencil  # noqa: E402
 from hpc_patterns_b200.models.peer2pear import FusedTriadExchange, P2PBench  # noqa: E402
 from hpc_patterns_b200.parallel.comm import Comm  # noqa: E402
 
 
 def main():
     comm = Comm()
-    dev = comm.local_rank
+    dev = comm.device
     torch.cuda.set_device(dev)
+    # flagship: stencil fused with the halo exchange, across processes (CUDA IPC peer mappings) ---------------
+    for mode in ("pull", "push"):
+        for rows, nbytes, tune in ((1, 1 << 20, {"tile_kb": 4, "stages": 6}), (3, (8 << 20) + 4096, {})):
+            hs = HaloStencil(comm, dev, message_bytes=nbytes, rows=rows, mode=mode, tune=tune)
+            hs.step(1)
+            hs.step(6)                       # persistent: six steps, one launch, neighbours spin on each other
+            hs.step(1)
+            torch.cuda.synchronize()
+            hs.check()
+            assert hs.verify_from_init() == 0, (mode, rows)
+            comm.barrier()
+            assert hs.verify_last_step() == 0, (mode, rows)
+            comm.barrier()
+            hs.reset()
+            for how in ("memcpy", "nccl"):
+                hs.stock_step(how)
+            hs.step(2)
+            torch.cuda.synchronize()
+            assert hs.verify_from_init() == 0, (mode, rows, "stock")
+            if mode == "push":
+                hs.reset()
+                bufs = hs.make_host_buffers()
+                for i in range(3):
+                    hs.step_from_host(bufs[i & 1], bufs[(i + 1) & 1], chunks=4)
+                assert hs.verify_from_init() == 0
+                assert torch.equal(bufs[1], hs.u_tensor().cpu())
+            hs.close()
+    if comm.rank == 0:
+        print("HALO OK")
     # peer2pear, every transport
     for transport in ("put", "get", "sendrecv", "memcpy", "nccl"):
         for engine in (("ldst", "tma") if transport in ("put", "get", "sendrecv") else ("ldst",)):

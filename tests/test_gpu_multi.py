@@ -131,16 +131,41 @@ def test_torchrun_workers():
 @needs2
 def test_bench_two_gpus():
     rc, out, err = _torchrun(2, [os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "5", "--warmup", "3",
-                                 "--e2e-steps", "2"], port=29611)
+                                 "--e2e-steps", "2", "--preheat-ms", "50"], port=29611)
     assert rc == 0, out[-3000:] + err[-3000:]
     line = [l for l in out.splitlines() if l.startswith("{")][-1]
     d = json.loads(line)
-    assert d["n_gpus"] == 2 and d["value"] > 0 and d["wrong_words"] == 0 and d["gpu_launches"] == 5
+    assert d["n_gpus"] == 2 and d["value"] > 0 and d["wrong_words"] == 0 and d["gpu_launches"] >= 1
+    assert d["e2e"]["wrong_words"] == 0 and d["stock"]["wrong_words"] == 0
 
 
 def test_bench_one_gpu():
     rc, out, err = _run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "5", "--warmup", "3",
-                         "--e2e-steps", "2"])
+                         "--e2e-steps", "2", "--preheat-ms", "50"])
     assert rc == 0, out[-3000:] + err[-3000:]
     d = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
-    assert d["n_gpus"] == 1 and d["value"] > 0 and d["e2e"]["value"] > 0
+    assert d["n_gpus"] == 1 and d["value"] > 0 and d["e2e"]["value"] > 0 and d["wrong_words"] == 0
+    assert len(d["blocks_ms_per_step"]) == 5 and d["clocks"]["sm_mhz"]
+    assert d["e2e"]["h2d_bytes_per_step"] == d["config"]["rows"] * d["config"]["message_bytes"]
+
+
+# ---- the same native programs with MORE RANKS THAN GPUS (oversubscription, as the reference's devices.hpp:46-47 deals
+# ranks round-robin): on a 1-GPU box every "peer" is the GPU itself, so epochs, tickets, acks and timeouts of the
+# cross-GPU protocols are exercised without NVLink.  These run on ANY GPU count.
+@pytest.mark.parametrize("transport", ["put", "get", "sendrecv", "memcpy"])
+def test_cli_peer2pear_virtual_ranks(bin_dir, transport):
+    rc, out, err = _run([os.path.join(bin_dir, "peer2pear"), "v", "-n", "2", "--transport", transport,
+                         "--bytes", str(4 << 20), "--bytes", "1024", "--iters", "3"],
+                        env={"CUDA_VISIBLE_DEVICES": "0"}, timeout=180)
+    assert rc == 0, out + err
+    assert out.count("Unidirectional Bandwidth:") == 2 and "VERIFICATION FAILED" not in out
+
+
+@pytest.mark.parametrize("args", [[], ["--algo", "ring-unfused"], ["-a", "--coll", "twoshot"], ["--type", "int"],
+                                  ["-a", "--coll", "twoshot", "--type", "int"]])
+@pytest.mark.parametrize("n", [2, 4])
+def test_cli_allreduce_virtual_ranks(bin_dir, args, n):
+    rc, out, err = _run([os.path.join(bin_dir, "allreduce"), "-n", str(n), "-p", "18", "--iters", "2"] + args,
+                        env={"CUDA_VISIBLE_DEVICES": "0"}, timeout=180)
+    assert rc == 0, out + err
+    assert out.count("Passed") == n
