@@ -17,6 +17,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstring>
+#include <exception>
 #include <iostream>
 #include <limits>
 #include <numeric>
@@ -487,21 +488,48 @@ class CudaBackend final : public Backend {
     BenchResult res;
     res.total_us = std::numeric_limits<long>::max();
     double dev_best = std::numeric_limits<double>::max();
+    // A copy that touches pageable memory blocks its calling thread while the driver stages it, and (measured,
+    // profiles/r1_call7_1gpu: `fused | C MD` ran at the serial time) it does not reliably overlap a kernel enqueued
+    // by the SAME thread just before it.  Each side copy therefore gets its own host thread — the reference's
+    // host_threads idiom (concurency/bench_omp.cpp:67-69) for the one thing a kernel cannot do itself: x86 B200s
+    // cannot dereference pageable memory from the SMs.  HPCP_FUSED_SIDE_THREADS=0 restores the single-thread order.
+    const bool side_threads = [] {
+      const char* e = std::getenv("HPCP_FUSED_SIDE_THREADS");
+      return e == nullptr || std::atoi(e) != 0;
+    }();
     for (int r = 0; r < req.n_repetitions; ++r) {
       const auto t0 = Clock::now();
       if (req.enable_profiling) HPCP_CUDA(cudaEventRecord(g0, s));
-      // Side *kernels* (T) first: a resident-wave kernel launched earlier would otherwise hold the
-      // SMs.  Side *copies* last: a pageable cudaMemcpyAsync blocks the host until it is staged, so
-      // everything else must already be in flight.
+      // Side *kernels* (T) first: a resident-wave kernel launched earlier would otherwise hold the SMs.
       for (size_t k = 0; k < side.size(); ++k)
         if (!side[k]->is_copy()) side[k]->submit(side_streams[k]);
+      std::vector<std::thread> helpers;
+      std::vector<std::exception_ptr> helper_error(side.size());
+      if (side_threads) {
+        for (size_t k = 0; k < side.size(); ++k) {
+          if (!side[k]->is_copy()) continue;
+          helpers.emplace_back([&, k] {
+            try {
+              HPCP_CUDA(cudaSetDevice(device_));
+              side[k]->submit(side_streams[k]);
+              HPCP_CUDA(cudaStreamSynchronize(side_streams[k]));
+            } catch (...) {
+              helper_error[k] = std::current_exception();
+            }
+          });
+        }
+      }
       if (!fused.empty())
         launch_fused_bench(fused.data(), static_cast<int>(fused.size()), engine, CopyTuning{},
                            device_, s);
       if (req.enable_profiling) HPCP_CUDA(cudaEventRecord(g1, s));
-      for (size_t k = 0; k < side.size(); ++k)
-        if (side[k]->is_copy()) side[k]->submit(side_streams[k]);
+      if (!side_threads)
+        for (size_t k = 0; k < side.size(); ++k)
+          if (side[k]->is_copy()) side[k]->submit(side_streams[k]);
       HPCP_CUDA(cudaStreamSynchronize(s));
+      for (auto& t : helpers) t.join();
+      for (auto& e : helper_error)
+        if (e) std::rethrow_exception(e);
       for (auto& q : side_streams) HPCP_CUDA(cudaStreamSynchronize(q));
       const long t = elapsed_us(t0, Clock::now());
       note_rep(req, r, t);

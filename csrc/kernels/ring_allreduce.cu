@@ -463,11 +463,27 @@ void launch_ring_allreduce(const RingArgs& args, ElemType type, int ctas, int de
   HPCP_REQUIRE(!args.pull || args.n_slots != 2 || args.world <= 4 ||
                    (args.ack_local != nullptr && args.ack_left != nullptr),
                "ring: pull with n_slots=2 needs the ack words");
-  // All CTAs may spin on arrival words: the grid must be co-resident (<= 4 CTAs of
-  // 512 threads per SM).
+  // All CTAs may spin on arrival (and ack) words, so the whole grid must be co-resident: clamp it with the real
+  // occupancy of the instantiation that is about to run (512 threads x its register count), never with a guess.
+  // Ranks that share a GPU divide the clamp among themselves on the caller's side (`ctas`).
+  const bool two_slots_k = args.n_slots == 2;
+  const void* kernel = nullptr;
+  if (args.pull)
+    kernel = two_slots_k ? (type == ElemType::kFloat ? reinterpret_cast<const void*>(ring_pull_kernel<float, true>)
+                                                      : reinterpret_cast<const void*>(ring_pull_kernel<int, true>))
+                         : (type == ElemType::kFloat ? reinterpret_cast<const void*>(ring_pull_kernel<float, false>)
+                                                      : reinterpret_cast<const void*>(ring_pull_kernel<int, false>));
+  else
+    kernel = two_slots_k ? (type == ElemType::kFloat ? reinterpret_cast<const void*>(ring_allreduce_kernel<float, true>)
+                                                      : reinterpret_cast<const void*>(ring_allreduce_kernel<int, true>))
+                         : (type == ElemType::kFloat ? reinterpret_cast<const void*>(ring_allreduce_kernel<float>)
+                                                      : reinterpret_cast<const void*>(ring_allreduce_kernel<int>));
+  int per_sm = 0;
+  HPCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 512, 0));
+  HPCP_REQUIRE(per_sm >= 1, "ring: the kernel does not fit on an SM");
   const int sms = device_sm_count(device);
-  int grid = ctas > 0 ? ctas : sms * 2;
-  grid = std::min(grid, sms * 4);
+  int grid = ctas > 0 ? ctas : sms * std::min(per_sm, 2);
+  grid = std::min(grid, sms * per_sm);
   grid = static_cast<int>(std::min<size_t>(static_cast<size_t>(grid), std::max<size_t>(d.n_chunks, 1)));
   if (ctas <= 0 && d.n_chunks > static_cast<size_t>(grid)) {
     // Chunks are dealt round-robin: pick the grid in [3/4 cap, cap] that wastes the least

@@ -436,7 +436,9 @@ int main(int argc, char** argv) {
     if (cfg.use_collective) {
       bool want_nvls = cfg.coll == "nvls";
       if (cfg.coll == "auto") {
-        want_nvls = ranks_per_dev == 1 && cfg.kind == AllocKind::kDevice;
+        // int: two-shot (128-bit peer loads for every type) — multimem.ld_reduce has no vector form for .s32 and ran
+        // 2.5x slower than float (profiles/r1_call3_8gpu); float: in-switch reduction where multicast exists.
+        want_nvls = ranks_per_dev == 1 && cfg.kind == AllocKind::kDevice && cfg.type == ElemType::kFloat;
         for (int d : devices) want_nvls = want_nvls && NodeMemory::multicast_supported(d);
       }
       if (want_nvls) {

@@ -88,10 +88,19 @@ int device_for_rank(const std::string& policy, int local_rank, int n_devices,
   if (local_rank < 0) throw std::invalid_argument("device_for_rank: negative rank");
   if (policy == "compact") return local_rank % n_devices;
   if (policy == "spread") {
+    // Round-robin over the domains (contiguous blocks; the first n % d hold one more GPU), skipping exhausted ones:
+    // every GPU is used for any count; equal blocks give (r % d) * per + r / d.  Same rule in
+    // parallel/tile_mapping.py and scripts/tile_mapping.sh.
     const int d = std::max(1, std::min(n_domains, n_devices));
-    const int per = std::max(1, n_devices / d);
-    const int r = local_rank % (per * d);
-    return (r % d) * per + (r / d) % per;
+    const int base = n_devices / d, extra = n_devices % d;
+    const int r = local_rank % n_devices;
+    int seen = 0;
+    for (int level = 0;; ++level)
+      for (int k = 0; k < d; ++k)
+        if (level < base + (k < extra ? 1 : 0)) {
+          if (seen == r) return k * base + std::min(k, extra) + level;
+          ++seen;
+        }
   }
   if (policy == "compact_plan") {
     const std::vector<int> flat = flatten(planes);

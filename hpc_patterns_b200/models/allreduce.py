@@ -96,7 +96,11 @@ class AllreduceMiniapp:
         self.va = self.vb = self.vc = self.slots = None
         self._symm = None
         if algo == "nvls":
-            self._init_nvls()
+            try:
+                self._init_nvls()
+            except Exception:
+                self.pads.close()   # collectively allocated just above: do not leak it on the failure path
+                raise
         else:
             self.va = SymmetricBuffer(comm, self.nbytes, device)
             self.vc = SymmetricBuffer(comm, self.nbytes, device)
@@ -257,6 +261,23 @@ class AllreduceMiniapp:
         self.pads.close()
 
 
+def choose_collective(comm: Comm, device: int, dtype: str, log2_elems: int):
+    """Which one-launch collective the ``-a`` path (↔ MPI_Allreduce, allreduce-mpi-sycl.cpp:61-67) uses.
+
+    Decided BEFORE anything is allocated and agreed across ranks (min over ranks of the local probe), so ranks can
+    neither diverge on the algorithm nor leak a half-built instance:
+      * int:   two-shot — ``multimem.ld_reduce`` has no vector form for .s32 (one 4-byte request per thread, measured
+               2.5x slower than float, profiles/r1_call3_8gpu), peer loads are 128-bit for every type;
+      * float: NVLS (in-switch reduction) when every rank reports multicast support, else two-shot."""
+    C = native()
+    if dtype != "float":
+        return "twoshot", "integer reductions use vector peer loads; multimem.ld_reduce.s32 is scalar"
+    ok = comm.world >= 2 and bool(C.multicast_supported(device))
+    if comm.min(1.0 if ok else 0.0) < 1.0:
+        return "twoshot", "NVLS multicast unavailable on at least one rank"
+    return "nvls", "multicast supported on every rank"
+
+
 def main(argv: Optional[List[str]] = None) -> int:
     """``torchrun --nproc-per-node N -m hpc_patterns_b200.models.allreduce [-a] [-p k] [--algo ...]``"""
     import argparse
@@ -280,15 +301,10 @@ def main(argv: Optional[List[str]] = None) -> int:
     algo = args.algo
     app = None
     if args.a:
-        try:
-            app = AllreduceMiniapp(comm, device, args.p, args.type, "nvls")
-            algo = "nvls"
-        except Exception as e:
-            if comm.rank == 0:
-                print(f"# NVLS unavailable ({e}); using two-shot P2P", flush=True)
-            algo = "twoshot"
-    if app is None:
-        app = AllreduceMiniapp(comm, device, args.p, args.type, algo, slots=args.slots, pull=args.pull)
+        algo, why = choose_collective(comm, device, args.type, args.p)
+        if comm.rank == 0:
+            print(f"# -a: {algo} ({why})", flush=True)
+    app = AllreduceMiniapp(comm, device, args.p, args.type, algo, slots=args.slots, pull=args.pull)
     res = app.run(args.iters, args.warmup)
     if comm.rank == 0:
         row = res.row()

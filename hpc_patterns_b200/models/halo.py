@@ -181,9 +181,10 @@ class HaloStencil:
         C, pads, st = self.C, self.pads, self._stream()
         self._xepoch = getattr(self, "_xepoch", 0) + 1
         par = (self.g + 1) & 1
-        for dst_rank, row, dst in ((self.left, 0, self.halo_ptr(self.left, "hi", par)),
-                                   (self.right, self.rows - 1, self.halo_ptr(self.right, "lo", par))):
-            section = C.PAD_DONE if dst_rank == self.left else C.PAD_ACK
+        # message "to the left" is announced in the PAD_DONE section, "to the right" in PAD_ACK (two distinct words
+        # even when both neighbours are the same rank, or this rank itself)
+        for dst_rank, row, dst, section in ((self.left, 0, self.halo_ptr(self.left, "hi", par), C.PAD_DONE),
+                                            (self.right, self.rows - 1, self.halo_ptr(self.right, "lo", par), C.PAD_ACK)):
             sync = pads.sync_ops(signal_rank=dst_rank, signal_section=section, epoch=self._xepoch)
             pads.advance_tickets(C.copy(dst, self.u_ptr(self.rank, par, row), self.row_bytes, False, engine, {},
                                         sync, self.device, st))

@@ -43,6 +43,24 @@ def flatten(planes: Sequence[Sequence[int]]) -> List[int]:
     return [g for p in planes for g in p]
 
 
+def _spread(rank: int, n_devices: int, n_domains: int) -> int:
+    """Round-robin over the domains (contiguous blocks of GPUs; the first n % d blocks hold one more), skipping a
+    domain once it is exhausted — every GPU is used for any device count, and with equal blocks this is
+    ``(r % d) * per + r // d``.  Identical in scripts/tile_mapping.sh and csrc/p2p/topology_core.cpp."""
+    d = max(1, min(n_domains, n_devices))
+    base, extra = divmod(n_devices, d)
+    r = rank % n_devices
+    seen = 0
+    level = 0
+    while True:
+        for k in range(d):
+            if level < base + (1 if k < extra else 0):
+                if seen == r:
+                    return k * base + min(k, extra) + level
+                seen += 1
+        level += 1
+
+
 def device_for_rank(policy: str, rank: int, n_devices: int,
                     planes: Optional[Sequence[Sequence[int]]] = None, n_domains: int = 2) -> int:
     """Pure policy function (mirrors csrc/p2p/topology_core.cpp:device_for_rank)."""
@@ -53,10 +71,7 @@ def device_for_rank(policy: str, rank: int, n_devices: int,
     if policy == "compact":
         return rank % n_devices
     if policy == "spread":
-        d = max(1, min(n_domains, n_devices))
-        per = max(1, n_devices // d)
-        r = rank % (per * d)
-        return (r % d) * per + (r // d) % per
+        return _spread(rank, n_devices, n_domains)
     if policy == "compact_plan":
         flat = flatten(planes or [])
         if not flat:

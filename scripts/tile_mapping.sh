@@ -15,9 +15,21 @@ num_domain=2   # the two halves of an HGX baseboard (PCIe switch / NUMA domains)
 policy="${1:-}"; shift || true
 case "$policy" in
   compact)      gpu=$(( rank % num_gpu )) ;;
-  spread)       per=$(( num_gpu / num_domain )); (( per > 0 )) || per=1
-                r=$(( rank % (per * num_domain) ))
-                gpu=$(( (r % num_domain) * per + (r / num_domain) % per )) ;;
+  spread)       # round-robin over the domains (contiguous blocks, the first n % d one GPU larger), skipping exhausted
+                # ones — the rule of parallel/tile_mapping.py::_spread and topology_core.cpp::device_for_rank
+                (( num_domain > num_gpu )) && num_domain=$num_gpu
+                base=$(( num_gpu / num_domain )); extra=$(( num_gpu % num_domain ))
+                r=$(( rank % num_gpu )); seen=0; level=0; gpu=-1
+                while (( gpu < 0 )); do
+                  for (( k = 0; k < num_domain; k++ )); do
+                    size=$(( base + (k < extra ? 1 : 0) ))
+                    if (( level < size )); then
+                      if (( seen == r )); then gpu=$(( k * base + (k < extra ? k : extra) + level )); break; fi
+                      seen=$(( seen + 1 ))
+                    fi
+                  done
+                  level=$(( level + 1 ))
+                done ;;
   compact_plan) gpu="$("$here/bin/topology" $(( rank % num_gpu )))" ;;
   *) echo "tile_mapping.sh: unknown policy '$policy' (compact|spread|compact_plan)" >&2; exit 2 ;;
 esac

@@ -71,3 +71,30 @@ def test_selected_device(monkeypatch):
     assert tm.selected_device() == 6
     monkeypatch.delenv("HPCP_DEVICE")
     assert tm.selected_device(default=2) == 2
+
+
+def test_spread_policy_bash_python_and_native_agree(native):
+    """The three implementations of the policies are documented as identical: check them against each other, including
+    the edges the round-1 review found (one GPU, odd GPU counts — every GPU must be used)."""
+    import os
+    import subprocess
+
+    from hpc_patterns_b200.parallel import tile_mapping as tm
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "scripts", "tile_mapping.sh")
+    for n in (1, 2, 3, 5, 8):
+        used = set()
+        for rank in range(2 * n + 1):
+            want = tm.device_for_rank("spread", rank, n)
+            used.add(want)
+            assert native.topology_device_for_rank("spread", rank, n, [], 2) == want
+            env = dict(os.environ, LOCAL_RANK=str(rank), HPCP_NUM_DEVICES=str(n))
+            out = subprocess.run(["bash", script, "spread", "SET", "bash", "-c", "echo $HPCP_DEVICE"], env=env,
+                                 capture_output=True, text=True, timeout=30)
+            assert out.returncode == 0 and int(out.stdout.strip()) == want, (n, rank, out.stdout, out.stderr)
+            cvd = subprocess.run(["bash", script, "compact", "CVD", "bash", "-c", "echo $CUDA_VISIBLE_DEVICES"], env=env,
+                                 capture_output=True, text=True, timeout=30)
+            assert int(cvd.stdout.strip()) == tm.device_for_rank("compact", rank, n)
+        assert used == set(range(n)), (n, used)
+    assert [tm.device_for_rank("spread", r, 8) for r in range(8)] == [0, 4, 1, 5, 2, 6, 3, 7]
