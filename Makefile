@@ -42,7 +42,8 @@ cli: $(CLIS) aliases
 #   peer2pear_i / peer2pear_w (Isend/Irecv vs -DUSE_WIN builds, p2p/run.sh:4-5), sycl_con (run_sycl.sh:6),
 #   omp_host_threads / omp_nowait (one build per mode upstream, run_omp.sh:6-7; the mode is argv[1] here).
 aliases: $(CLIS)
-	@for n in allreduce.float allreduce.int allreduce-mpi-sycl.float allreduce-mpi-sycl.int \
+	@for n in allreduce.float allreduce.int allreduce.double allreduce.long allreduce.short allreduce.uint allreduce.uchar \
+	          allreduce-mpi-sycl.float allreduce-mpi-sycl.int \
 	          allreduce-usm-mpi-omp-offload.float allreduce-map-mpi-omp-offload.float; do ln -sf allreduce bin/$$n; done
 	@ln -sf peer2pear bin/peer2pear_i; ln -sf peer2pear bin/peer2pear_w
 	@ln -sf concurency bin/sycl_con; ln -sf omp_con bin/omp_host_threads; ln -sf omp_con bin/omp_nowait

@@ -17,6 +17,7 @@
 
 #include "common/cuda_check.h"
 #include "common/driver_api.h"
+#include "common/dtype_traits.h"
 #include "common/peer_mem.h"
 #include "common/signal_layout.h"
 #include "concurency/bench.hpp"
@@ -44,9 +45,9 @@ CopyEngine engine_from(const std::string& s) {
 }
 
 ElemType elem_from(const std::string& s) {
-  if (s == "float" || s == "float32") return ElemType::kFloat;
-  if (s == "int" || s == "int32") return ElemType::kInt;
-  throw std::invalid_argument("dtype must be float32 or int32");
+  ElemType t;
+  if (elem_type_from_name(s, &t)) return t;
+  throw std::invalid_argument("dtype must be one of float int uint double long ulong short ushort uchar");
 }
 
 CopyTuning tuning_from(const py::dict& d) {
@@ -593,7 +594,8 @@ PYBIND11_MODULE(_C, m) {
   m.def("ring_pull_src_slot", &ring_pull_src_slot);
   m.def("ring_pull_waits_for_ack", &ring_pull_waits_for_ack);
   m.def("ring_pull_publishes_ack", &ring_pull_publishes_ack);
-  m.def("ring_num_chunks", &ring_num_chunks, py::arg("n"), py::arg("chunk_elems") = 0);
+  m.def("ring_num_chunks", &ring_num_chunks, py::arg("n"), py::arg("chunk_elems") = 0, py::arg("elem_bytes") = 4);
+  m.def("elem_size", [](const std::string& dtype) { return elem_size(elem_from(dtype)); });
   m.def(
       "ring_allreduce",
       [](uintptr_t va, uintptr_t vc, uintptr_t slots_local, uintptr_t slots_right,

@@ -3,10 +3,12 @@
 // Plays the role of mpi::get_datatype<T>() in the reference
 // (aurora.mpich.miniapps/src/include/mpi_datatype.hpp:18-51: C++ type -> MPI_Datatype,
 // default MPI_BYTE).  There is no MPI here; what a collective kernel needs to
-// know about T is its size, whether an arithmetic reduction exists for it
-// (float -> f32 adds / multimem.add.f32, int -> s32 adds) and a printable name.
-// Types without a native reduction fall back to "bytes" (copy-only), the
-// analogue of MPI_BYTE.
+// know about T is its size, whether an arithmetic reduction exists for it and a
+// printable name.  Every type the reference's trait maps to an MPI_SUM-capable
+// datatype (short/int/long/float/double and the unsigned integers, :28-51) has
+// SUM kernels here (ring, accumulate, two-shot: csrc/kernels/ring_allreduce.cu);
+// `long double` has no device representation on NVIDIA GPUs and, like any other
+// type, falls back to "bytes" (copy-only), the analogue of MPI_BYTE.
 #pragma once
 
 #include <cstddef>
@@ -38,13 +40,15 @@ struct dtype_of {
 
 HPCP_DTYPE(float, "float", true, ElemType::kFloat, "float32");
 HPCP_DTYPE(int, "int", true, ElemType::kInt, "int32");
-HPCP_DTYPE(unsigned int, "unsigned int", true, ElemType::kInt, "uint32");  // two's complement add
-HPCP_DTYPE(double, "double", false, ElemType::kFloat, "float64");
-HPCP_DTYPE(long, "long", false, ElemType::kInt, "int64");
-HPCP_DTYPE(unsigned long, "unsigned long", false, ElemType::kInt, "uint64");
-HPCP_DTYPE(short, "short", false, ElemType::kInt, "int16");
-HPCP_DTYPE(unsigned short, "unsigned short", false, ElemType::kInt, "uint16");
-HPCP_DTYPE(unsigned char, "unsigned char", false, ElemType::kInt, "uint8");
+HPCP_DTYPE(unsigned int, "unsigned int", true, ElemType::kUInt, "uint32");
+HPCP_DTYPE(double, "double", true, ElemType::kDouble, "float64");
+HPCP_DTYPE(long, "long", true, ElemType::kLong, "int64");
+HPCP_DTYPE(long long, "long", true, ElemType::kLong, "int64");
+HPCP_DTYPE(unsigned long, "unsigned long", true, ElemType::kULong, "uint64");
+HPCP_DTYPE(unsigned long long, "unsigned long", true, ElemType::kULong, "uint64");
+HPCP_DTYPE(short, "short", true, ElemType::kShort, "int16");
+HPCP_DTYPE(unsigned short, "unsigned short", true, ElemType::kUShort, "uint16");
+HPCP_DTYPE(unsigned char, "unsigned char", true, ElemType::kUChar, "uint8");
 #undef HPCP_DTYPE
 
 template <typename T>
@@ -52,18 +56,47 @@ constexpr DTypeInfo get_dtype(const T& = T{}) {
   return dtype_of<T>::value;
 }
 
-// Run-time lookup by name ("float" | "int"); returns false if unknown / not reducible.
+// Run-time lookup by name (C++ spelling, torch spelling or a short alias); false if unknown.
 inline bool elem_type_from_name(const std::string& name, ElemType* out) {
-  if (name == "float" || name == "float32" || name == "f32") {
-    *out = ElemType::kFloat;
-    return true;
-  }
-  if (name == "int" || name == "int32" || name == "s32") {
-    *out = ElemType::kInt;
-    return true;
-  }
+  struct Row {
+    const char* name;
+    ElemType type;
+  };
+  static const Row rows[] = {
+      {"float", ElemType::kFloat},    {"float32", ElemType::kFloat},       {"f32", ElemType::kFloat},
+      {"int", ElemType::kInt},        {"int32", ElemType::kInt},           {"s32", ElemType::kInt},
+      {"uint", ElemType::kUInt},      {"unsigned", ElemType::kUInt},       {"unsigned int", ElemType::kUInt},
+      {"uint32", ElemType::kUInt},    {"u32", ElemType::kUInt},
+      {"double", ElemType::kDouble},  {"float64", ElemType::kDouble},      {"f64", ElemType::kDouble},
+      {"long", ElemType::kLong},      {"int64", ElemType::kLong},          {"s64", ElemType::kLong},
+      {"ulong", ElemType::kULong},    {"unsigned long", ElemType::kULong}, {"uint64", ElemType::kULong},
+      {"u64", ElemType::kULong},
+      {"short", ElemType::kShort},    {"int16", ElemType::kShort},         {"s16", ElemType::kShort},
+      {"ushort", ElemType::kUShort},  {"unsigned short", ElemType::kUShort}, {"uint16", ElemType::kUShort},
+      {"u16", ElemType::kUShort},
+      {"uchar", ElemType::kUChar},    {"unsigned char", ElemType::kUChar}, {"uint8", ElemType::kUChar},
+      {"u8", ElemType::kUChar},
+  };
+  for (const Row& r : rows)
+    if (name == r.name) {
+      *out = r.type;
+      return true;
+    }
   return false;
 }
-inline const char* elem_type_name(ElemType t) { return t == ElemType::kFloat ? "float" : "int"; }
+inline const char* elem_type_name(ElemType t) {
+  switch (t) {
+    case ElemType::kFloat: return "float";
+    case ElemType::kInt: return "int";
+    case ElemType::kUInt: return "uint";
+    case ElemType::kDouble: return "double";
+    case ElemType::kLong: return "long";
+    case ElemType::kULong: return "ulong";
+    case ElemType::kShort: return "short";
+    case ElemType::kUShort: return "ushort";
+    case ElemType::kUChar: return "uchar";
+  }
+  return "?";
+}
 
 }  // namespace hpcp

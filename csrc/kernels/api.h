@@ -282,7 +282,18 @@ void launch_wait_flags(const uint32_t* flags, int count, uint32_t epoch, uint64_
                        cudaStream_t stream);
 
 // ------------------------------------------------------ allreduce miniapp ----
-enum class ElemType : int { kFloat = 0, kInt = 1 };
+// Element types of the miniapp's arrays (↔ mpi::get_datatype<T>(), mpi_datatype.hpp:28-51: every one of them is usable
+// with MPI_SUM upstream).  Kernels are instantiated per ADDITION CLASS: signed and unsigned integers of one width share
+// the two's-complement add.
+enum class ElemType : int {
+  kFloat = 0, kInt = 1, kUInt = 2, kDouble = 3, kLong = 4, kULong = 5, kShort = 6, kUShort = 7, kUChar = 8
+};
+constexpr size_t elem_size(ElemType t) {
+  return t == ElemType::kDouble || t == ElemType::kLong || t == ElemType::kULong ? 8
+         : t == ElemType::kShort || t == ElemType::kUShort                       ? 2
+         : t == ElemType::kUChar                                                 ? 1
+                                                                                 : 4;
+}
 
 // VA = a, VB = b, VC = c (↔ Initialize, allreduce-mpi-sycl.cpp:33-41). Any pointer may be null.
 void launch_init3(void* va, void* vb, void* vc, size_t n, double a, double b, double c,
@@ -307,8 +318,8 @@ struct RingArgs {
   uint32_t* arrived_local = nullptr;  // n_chunks words, written by the left neighbour
   uint32_t* arrived_right = nullptr;  // peer-mapped: right neighbour's arrival words
   int world = 0;
-  size_t n = 0;                   // elements per rank, multiple of 4
-  size_t chunk_elems = 0;         // 0 -> 8192 (32 KiB); multiple of 4
+  size_t n = 0;                   // elements per rank; n * elem_size a multiple of 16 bytes
+  size_t chunk_elems = 0;         // 0 -> 128 KiB worth of elements; chunk bytes a multiple of 16
   uint32_t epoch_base = 0;        // arrival words count up: base + hop
   uint64_t timeout_ns = 0;
   uint32_t* status = nullptr;
@@ -326,7 +337,7 @@ struct RingArgs {
   const void* va_left = nullptr;
   const void* slots_left = nullptr;
 };
-size_t ring_num_chunks(size_t n, size_t chunk_elems);
+size_t ring_num_chunks(size_t n, size_t chunk_elems, size_t elem_bytes = 4);
 void launch_ring_allreduce(const RingArgs& args, ElemType type, int ctas, int device,
                            cudaStream_t stream);
 
@@ -341,7 +352,7 @@ struct TwoShotArgs {
   uint32_t ticket_base = 0;
   int rank = 0;
   int world = 0;
-  size_t n = 0;                              // elements, multiple of 4 * world
+  size_t n = 0;                              // elements; n * elem_size a multiple of 16 * world bytes
   uint32_t barrier_epoch = 0;
   uint64_t timeout_ns = 0;
   uint32_t* status = nullptr;

@@ -55,6 +55,67 @@ struct Vec4<int> {
     return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
   }
 };
+template <>
+struct Vec4<double> {  // two f64 lanes per 16 bytes
+  static __device__ __forceinline__ uint4 add(const uint4& a, const uint4& b) {
+    const double lo = __hiloint2double(static_cast<int>(a.y), static_cast<int>(a.x)) +
+                      __hiloint2double(static_cast<int>(b.y), static_cast<int>(b.x));
+    const double hi = __hiloint2double(static_cast<int>(a.w), static_cast<int>(a.z)) +
+                      __hiloint2double(static_cast<int>(b.w), static_cast<int>(b.z));
+    return make_uint4(static_cast<uint32_t>(__double2loint(lo)), static_cast<uint32_t>(__double2hiint(lo)),
+                      static_cast<uint32_t>(__double2loint(hi)), static_cast<uint32_t>(__double2hiint(hi)));
+  }
+};
+template <>
+struct Vec4<long long> {  // two 64-bit lanes (signed and unsigned share the add)
+  static __device__ __forceinline__ uint4 add(const uint4& a, const uint4& b) {
+    const unsigned long long lo = ((static_cast<unsigned long long>(a.y) << 32) | a.x) +
+                                  ((static_cast<unsigned long long>(b.y) << 32) | b.x);
+    const unsigned long long hi = ((static_cast<unsigned long long>(a.w) << 32) | a.z) +
+                                  ((static_cast<unsigned long long>(b.w) << 32) | b.z);
+    return make_uint4(static_cast<uint32_t>(lo), static_cast<uint32_t>(lo >> 32), static_cast<uint32_t>(hi),
+                      static_cast<uint32_t>(hi >> 32));
+  }
+};
+template <>
+struct Vec4<short> {  // eight 16-bit lanes: per-halfword SIMD add (wraps like the scalar add)
+  static __device__ __forceinline__ uint4 add(const uint4& a, const uint4& b) {
+    return make_uint4(__vadd2(a.x, b.x), __vadd2(a.y, b.y), __vadd2(a.z, b.z), __vadd2(a.w, b.w));
+  }
+};
+template <>
+struct Vec4<unsigned char> {  // sixteen 8-bit lanes
+  static __device__ __forceinline__ uint4 add(const uint4& a, const uint4& b) {
+    return make_uint4(__vadd4(a.x, b.x), __vadd4(a.y, b.y), __vadd4(a.z, b.z), __vadd4(a.w, b.w));
+  }
+};
+
+// C++ element type -> the addition class its kernels are instantiated for.
+template <typename T> struct AddClass { using type = T; };
+template <> struct AddClass<unsigned int> { using type = int; };
+template <> struct AddClass<unsigned long long> { using type = long long; };
+template <> struct AddClass<unsigned short> { using type = short; };
+
+// Run f(T{}) with the C++ type of `t`.
+template <typename F>
+void dispatch_elem(ElemType t, F&& f) {
+  switch (t) {
+    case ElemType::kFloat: f(float{}); break;
+    case ElemType::kInt: f(int{}); break;
+    case ElemType::kUInt: f(static_cast<unsigned int>(0)); break;
+    case ElemType::kDouble: f(double{}); break;
+    case ElemType::kLong: f(static_cast<long long>(0)); break;
+    case ElemType::kULong: f(static_cast<unsigned long long>(0)); break;
+    case ElemType::kShort: f(static_cast<short>(0)); break;
+    case ElemType::kUShort: f(static_cast<unsigned short>(0)); break;
+    case ElemType::kUChar: f(static_cast<unsigned char>(0)); break;
+  }
+}
+// Run f(C{}) with the addition class of `t` (six kernel instantiations instead of nine).
+template <typename F>
+void dispatch_add_class(ElemType t, F&& f) {
+  dispatch_elem(t, [&](auto tag) { f(typename AddClass<decltype(tag)>::type{}); });
+}
 
 // ------------------------------------------------------------ small kernels ----
 template <typename T>
@@ -72,8 +133,8 @@ __global__ void accumulate_kernel(const uint4* __restrict__ va, uint4* __restric
                                   const T* va_tail, T* vc_tail, size_t tail) {
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride)
-    vc[i] = Vec4<T>::add(vc[i], ptx::ld_weak_v4(va + i));
-  if (blockIdx.x == 0 && threadIdx.x < tail) vc_tail[threadIdx.x] += va_tail[threadIdx.x];
+    vc[i] = Vec4<typename AddClass<T>::type>::add(vc[i], ptx::ld_weak_v4(va + i));
+  if (blockIdx.x == 0 && threadIdx.x < tail) vc_tail[threadIdx.x] = static_cast<T>(vc_tail[threadIdx.x] + va_tail[threadIdx.x]);
 }
 
 template <typename T>
@@ -387,56 +448,51 @@ int grid_for(size_t items, int threads, int cap) {
 void launch_init3(void* va, void* vb, void* vc, size_t n, double a, double b, double c,
                   ElemType type, cudaStream_t stream) {
   const int ctas = grid_for(n, 256, 148 * 8);
-  if (type == ElemType::kFloat)
-    init3_kernel<float><<<ctas, 256, 0, stream>>>(static_cast<float*>(va), static_cast<float*>(vb),
-                                                  static_cast<float*>(vc), n, static_cast<float>(a),
-                                                  static_cast<float>(b), static_cast<float>(c));
-  else
-    init3_kernel<int><<<ctas, 256, 0, stream>>>(static_cast<int*>(va), static_cast<int*>(vb),
-                                                static_cast<int*>(vc), n, static_cast<int>(a),
-                                                static_cast<int>(b), static_cast<int>(c));
+  dispatch_elem(type, [&](auto tag) {
+    using T = decltype(tag);
+    init3_kernel<T><<<ctas, 256, 0, stream>>>(static_cast<T*>(va), static_cast<T*>(vb), static_cast<T*>(vc), n,
+                                              static_cast<T>(a), static_cast<T>(b), static_cast<T>(c));
+  });
   HPCP_CUDA(cudaGetLastError());
 }
 
 void launch_accumulate(const void* va, void* vc, size_t n, ElemType type, cudaStream_t stream) {
-  const size_t nvec = n / 4, tail = n % 4;
+  const size_t lanes = 16 / elem_size(type);
+  const size_t nvec = n / lanes, tail = n % lanes;
   const int ctas = grid_for(std::max<size_t>(nvec, 1), 512, 148 * 4);
-  if (type == ElemType::kFloat)
-    accumulate_kernel<float><<<ctas, 512, 0, stream>>>(
-        static_cast<const uint4*>(va), static_cast<uint4*>(vc), nvec,
-        static_cast<const float*>(va) + nvec * 4, static_cast<float*>(vc) + nvec * 4, tail);
-  else
-    accumulate_kernel<int><<<ctas, 512, 0, stream>>>(
-        static_cast<const uint4*>(va), static_cast<uint4*>(vc), nvec,
-        static_cast<const int*>(va) + nvec * 4, static_cast<int*>(vc) + nvec * 4, tail);
+  dispatch_elem(type, [&](auto tag) {
+    using T = decltype(tag);
+    accumulate_kernel<T><<<ctas, 512, 0, stream>>>(static_cast<const uint4*>(va), static_cast<uint4*>(vc), nvec,
+                                                   static_cast<const T*>(va) + nvec * lanes,
+                                                   static_cast<T*>(vc) + nvec * lanes, tail);
+  });
   HPCP_CUDA(cudaGetLastError());
 }
 
 void launch_count_mismatch(const void* v, size_t n, double expected, ElemType type,
                            unsigned long long* count, cudaStream_t stream) {
   const int ctas = grid_for(n, 256, 148 * 8);
-  if (type == ElemType::kFloat)
-    count_mismatch_kernel<float><<<ctas, 256, 0, stream>>>(static_cast<const float*>(v), n, expected,
-                                                           count);
-  else
-    count_mismatch_kernel<int><<<ctas, 256, 0, stream>>>(static_cast<const int*>(v), n, expected,
-                                                         count);
+  dispatch_elem(type, [&](auto tag) {
+    using T = decltype(tag);
+    count_mismatch_kernel<T><<<ctas, 256, 0, stream>>>(static_cast<const T*>(v), n, expected, count);
+  });
   HPCP_CUDA(cudaGetLastError());
 }
 
-constexpr size_t kRingDefaultChunk = 32768;  // 128 KiB of 4-byte elements per arrival word
+constexpr size_t kRingDefaultChunkBytes = 128 * 1024;  // payload per arrival word
 
-size_t ring_num_chunks(size_t n, size_t chunk_elems) {
-  const size_t ce = chunk_elems == 0 ? kRingDefaultChunk : chunk_elems;
+size_t ring_num_chunks(size_t n, size_t chunk_elems, size_t elem_bytes) {
+  const size_t ce = chunk_elems == 0 ? kRingDefaultChunkBytes / elem_bytes : chunk_elems;
   return (n + ce - 1) / ce;
 }
 
 void launch_ring_allreduce(const RingArgs& args, ElemType type, int ctas, int device,
                            cudaStream_t stream) {
   HPCP_REQUIRE(args.world >= 1 && args.world <= kApiMaxRanks, "ring: world out of range");
-  HPCP_REQUIRE(args.n % 4 == 0, "ring: n must be a multiple of 4 elements");
-  const size_t ce = args.chunk_elems == 0 ? kRingDefaultChunk : args.chunk_elems;
-  HPCP_REQUIRE(ce % 4 == 0, "ring: chunk_elems must be a multiple of 4");
+  const size_t esz = elem_size(type), lanes = 16 / esz;
+  HPCP_REQUIRE(args.n % lanes == 0, "ring: the block must be a multiple of 16 bytes");
+  const size_t ce = args.chunk_elems == 0 ? kRingDefaultChunkBytes / esz : args.chunk_elems;
+  HPCP_REQUIRE(ce % lanes == 0, "ring: a chunk must be a multiple of 16 bytes");
   RingDev d{};
   d.va = static_cast<const uint4*>(args.va);
   d.vc = static_cast<uint4*>(args.vc);
@@ -445,9 +501,9 @@ void launch_ring_allreduce(const RingArgs& args, ElemType type, int ctas, int de
   d.arrived_local = args.arrived_local;
   d.arrived_right = args.arrived_right;
   d.world = args.world;
-  d.nvec = args.n / 4;
-  d.chunk_vec = ce / 4;
-  d.n_chunks = ring_num_chunks(args.n, ce);
+  d.nvec = args.n / lanes;
+  d.chunk_vec = ce / lanes;
+  d.n_chunks = ring_num_chunks(args.n, ce, esz);
   d.epoch_base = args.epoch_base;
   d.timeout_ns = args.timeout_ns;
   d.status = args.status;
@@ -468,16 +524,15 @@ void launch_ring_allreduce(const RingArgs& args, ElemType type, int ctas, int de
   // Ranks that share a GPU divide the clamp among themselves on the caller's side (`ctas`).
   const bool two_slots_k = args.n_slots == 2;
   const void* kernel = nullptr;
-  if (args.pull)
-    kernel = two_slots_k ? (type == ElemType::kFloat ? reinterpret_cast<const void*>(ring_pull_kernel<float, true>)
-                                                      : reinterpret_cast<const void*>(ring_pull_kernel<int, true>))
-                         : (type == ElemType::kFloat ? reinterpret_cast<const void*>(ring_pull_kernel<float, false>)
-                                                      : reinterpret_cast<const void*>(ring_pull_kernel<int, false>));
-  else
-    kernel = two_slots_k ? (type == ElemType::kFloat ? reinterpret_cast<const void*>(ring_allreduce_kernel<float, true>)
-                                                      : reinterpret_cast<const void*>(ring_allreduce_kernel<int, true>))
-                         : (type == ElemType::kFloat ? reinterpret_cast<const void*>(ring_allreduce_kernel<float>)
-                                                      : reinterpret_cast<const void*>(ring_allreduce_kernel<int>));
+  dispatch_add_class(type, [&](auto tag) {
+    using C = decltype(tag);
+    if (args.pull)
+      kernel = two_slots_k ? reinterpret_cast<const void*>(ring_pull_kernel<C, true>)
+                           : reinterpret_cast<const void*>(ring_pull_kernel<C, false>);
+    else
+      kernel = two_slots_k ? reinterpret_cast<const void*>(ring_allreduce_kernel<C, true>)
+                           : reinterpret_cast<const void*>(ring_allreduce_kernel<C, false>);
+  });
   int per_sm = 0;
   HPCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 512, 0));
   HPCP_REQUIRE(per_sm >= 1, "ring: the kernel does not fit on an SM");
@@ -521,37 +576,32 @@ void launch_ring_allreduce(const RingArgs& args, ElemType type, int ctas, int de
     p.epoch_base = d.epoch_base;
     p.timeout_ns = d.timeout_ns;
     p.status = d.status;
-    if (two_slots) {
-      if (type == ElemType::kFloat)
-        ring_pull_kernel<float, true><<<grid, 512, 0, stream>>>(p);
+    dispatch_add_class(type, [&](auto tag) {
+      using C = decltype(tag);
+      if (two_slots)
+        ring_pull_kernel<C, true><<<grid, 512, 0, stream>>>(p);
       else
-        ring_pull_kernel<int, true><<<grid, 512, 0, stream>>>(p);
-    } else if (type == ElemType::kFloat) {
-      ring_pull_kernel<float, false><<<grid, 512, 0, stream>>>(p);
-    } else {
-      ring_pull_kernel<int, false><<<grid, 512, 0, stream>>>(p);
-    }
+        ring_pull_kernel<C, false><<<grid, 512, 0, stream>>>(p);
+    });
     HPCP_CUDA(cudaGetLastError());
     return;
   }
-  if (two_slots) {
-    if (type == ElemType::kFloat)
-      ring_allreduce_kernel<float, true><<<grid, 512, 0, stream>>>(d);
+  dispatch_add_class(type, [&](auto tag) {
+    using C = decltype(tag);
+    if (two_slots)
+      ring_allreduce_kernel<C, true><<<grid, 512, 0, stream>>>(d);
     else
-      ring_allreduce_kernel<int, true><<<grid, 512, 0, stream>>>(d);
-  } else if (type == ElemType::kFloat) {
-    ring_allreduce_kernel<float><<<grid, 512, 0, stream>>>(d);
-  } else {
-    ring_allreduce_kernel<int><<<grid, 512, 0, stream>>>(d);
-  }
+      ring_allreduce_kernel<C, false><<<grid, 512, 0, stream>>>(d);
+  });
   HPCP_CUDA(cudaGetLastError());
 }
 
 int launch_allreduce_two_shot(const TwoShotArgs& args, ElemType type, int ctas, int device,
                               cudaStream_t stream) {
   HPCP_REQUIRE(args.world >= 1 && args.world <= kApiMaxRanks, "two-shot: world out of range");
-  HPCP_REQUIRE(args.n % (4 * static_cast<size_t>(args.world)) == 0,
-               "two-shot: n must be a multiple of 4*world elements");
+  const size_t lanes = 16 / elem_size(type);
+  HPCP_REQUIRE(args.n % (lanes * static_cast<size_t>(args.world)) == 0,
+               "two-shot: every rank's slice must be a multiple of 16 bytes");
   TwoShotDev d{};
   for (int p = 0; p < args.world; ++p) {
     d.va[p] = static_cast<const uint4*>(args.va[p]);
@@ -561,7 +611,7 @@ int launch_allreduce_two_shot(const TwoShotArgs& args, ElemType type, int ctas, 
   d.ticket = args.ticket;
   d.rank = args.rank;
   d.world = args.world;
-  d.slice_vec = args.n / 4 / args.world;
+  d.slice_vec = args.n / lanes / args.world;
   d.barrier_epoch = args.barrier_epoch;
   d.timeout_ns = args.timeout_ns;
   d.status = args.status;
@@ -570,10 +620,9 @@ int launch_allreduce_two_shot(const TwoShotArgs& args, ElemType type, int ctas, 
   d.ticket_target = args.ticket_base + static_cast<uint32_t>(grid);
 #define HPCP_TWO_SHOT(W, U)                                          \
   do {                                                               \
-    if (type == ElemType::kFloat)                                    \
-      two_shot_kernel<float, W, U><<<grid, 512, 0, stream>>>(d);     \
-    else                                                             \
-      two_shot_kernel<int, W, U><<<grid, 512, 0, stream>>>(d);       \
+    dispatch_add_class(type, [&](auto tag) {                         \
+      two_shot_kernel<decltype(tag), W, U><<<grid, 512, 0, stream>>>(d); \
+    });                                                              \
   } while (0)
   if (args.world <= 2)
     HPCP_TWO_SHOT(2, 4);
@@ -591,6 +640,8 @@ int launch_allreduce_two_shot(const TwoShotArgs& args, ElemType type, int ctas, 
 int launch_allreduce_nvls(const NvlsArgs& args, ElemType type, int ctas, int device,
                           cudaStream_t stream) {
   HPCP_REQUIRE(args.world >= 1 && args.world <= kApiMaxRanks, "nvls: world out of range");
+  HPCP_REQUIRE(type == ElemType::kFloat || type == ElemType::kInt || type == ElemType::kUInt,
+               "nvls: multimem reductions are wired for float and 32-bit integers (use two-shot for the other types)");
   HPCP_REQUIRE(args.n % (4 * static_cast<size_t>(args.world)) == 0,
                "nvls: n must be a multiple of 4*world elements");
   NvlsDev d{};

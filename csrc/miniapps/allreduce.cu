@@ -62,6 +62,12 @@ struct Config {
   int slots = 0;     // --slots 2: the reference's VA/VB double buffer with per-chunk acks (default: P-1 slots)
   bool pull = false; // --pull: the fused ring moves its bytes as peer LOADS (receiver-driven) instead of peer stores
   bool cpu = false;  // --cpu: host-only plumbing run (threads as ranks, memcpy as send/recv)
+  // -R: the reference's `map` variant (allreduce-map-mpi-omp-offload.cpp:113-115,159,168-170): the arrays are host
+  // malloc'ed; `target enter data map(alloc)` gives each a DEVICE-RESIDENT copy the kernels and the exchange work on
+  // (use_device_ptr, :38); `target update from(VC)` brings the result back and the HOST verifies it.  Here: malloc +
+  // cudaMalloc pair, explicit cudaMemcpy D2H as the update.  --map-alias keeps round 1's zero-copy variant instead
+  // (cudaHostRegister + device alias: every access crosses PCIe).
+  bool map_alias = false;
 };
 
 void print_help() {
@@ -72,11 +78,12 @@ void print_help() {
                " -H          pinned host memory   (cudaHostAlloc)\n"
                " -D          device memory        (cudaMalloc, default)\n"
                " -S          managed memory       (cudaMallocManaged)\n"
-               " -R          host malloc mapped to the device (cudaHostRegister + device alias:\n"
-               "             the `map` variant of the reference)\n"
+               " -R          the `map` variant of the reference: host malloc'ed arrays with a device-resident mapped copy\n"
+               "             (kernels and the exchange use the device copy; VC is updated back and verified on the host)\n"
+               " --map-alias with -R: map by cudaHostRegister + device alias instead (zero-copy over PCIe)\n"
                " -n N        ranks (one host thread + one GPU each; default: all GPUs;\n"
                "             more ranks than GPUs are placed round-robin)\n"
-               " --type float|int      element type (default float, or binary-name suffix)\n"
+               " --type T   element type: float int uint double long ulong short ushort uchar (default float, or binary-name suffix)\n"
                " --algo ring|ring-unfused   fused persistent ring kernel (default) or\n"
                "                            separate put + accumulate kernels per step\n"
                " --coll auto|nvls|twoshot   collective used with -a\n"
@@ -98,10 +105,51 @@ struct Shared {
   size_t pad_extra = 0;  // words after the fixed pad: arrival words (+ ack words with --slots 2)
   SymmetricBuffer va, vb, vc, slots, pads;
   MulticastBuffer mc_va, mc_vc;
+  std::vector<void*> host_va, host_vc;  // -R: the host arrays whose mapped copies are va / vc
   bool nvls = false;
   double best_ms = 0;
   unsigned long long total_bad = 0;
 };
+
+double first_element_as_double(const void* p, ElemType t) {
+  switch (t) {
+    case ElemType::kFloat: return *static_cast<const float*>(p);
+    case ElemType::kInt: return *static_cast<const int*>(p);
+    case ElemType::kUInt: return *static_cast<const unsigned int*>(p);
+    case ElemType::kDouble: return *static_cast<const double*>(p);
+    case ElemType::kLong: return static_cast<double>(*static_cast<const long long*>(p));
+    case ElemType::kULong: return static_cast<double>(*static_cast<const unsigned long long*>(p));
+    case ElemType::kShort: return *static_cast<const short*>(p);
+    case ElemType::kUShort: return *static_cast<const unsigned short*>(p);
+    case ElemType::kUChar: return *static_cast<const unsigned char*>(p);
+  }
+  return 0;
+}
+
+template <typename T>
+unsigned long long count_mismatch_typed(const void* p, size_t n, double expected) {
+  const T* v = static_cast<const T*>(p);
+  unsigned long long bad = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const double d = static_cast<double>(v[i]) - expected;
+    bad += !(d < 1e-6 && d > -1e-6);
+  }
+  return bad;
+}
+unsigned long long count_mismatch_on_host(const void* p, size_t n, double expected, ElemType t) {
+  switch (t) {
+    case ElemType::kFloat: return count_mismatch_typed<float>(p, n, expected);
+    case ElemType::kInt: return count_mismatch_typed<int>(p, n, expected);
+    case ElemType::kUInt: return count_mismatch_typed<unsigned int>(p, n, expected);
+    case ElemType::kDouble: return count_mismatch_typed<double>(p, n, expected);
+    case ElemType::kLong: return count_mismatch_typed<long long>(p, n, expected);
+    case ElemType::kULong: return count_mismatch_typed<unsigned long long>(p, n, expected);
+    case ElemType::kShort: return count_mismatch_typed<short>(p, n, expected);
+    case ElemType::kUShort: return count_mismatch_typed<unsigned short>(p, n, expected);
+    case ElemType::kUChar: return count_mismatch_typed<unsigned char>(p, n, expected);
+  }
+  return n;
+}
 
 uint32_t* pad_of(const Shared& sh, int r) { return static_cast<uint32_t*>(sh.pads.ptr[r]); }
 
@@ -113,7 +161,7 @@ void rank_main(RankCtx& ctx, Shared& sh) {
   cudaStream_t stream;
   HPCP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   const int right = (me + 1) % P, left = (me - 1 + P) % P;
-  const size_t esz = 4;
+  const size_t esz = elem_size(cfg.type);
   uint32_t* my_pad = pad_of(sh, me);
   uint32_t* status = my_pad + kPadWords + sh.pad_extra;
   std::vector<uint32_t*> pad_list;
@@ -239,27 +287,32 @@ void rank_main(RankCtx& ctx, Shared& sh) {
   }
 
   // Verify: every element of VC equals P(P-1)/2.
-  unsigned long long* count = nullptr;
-  HPCP_CUDA(cudaMalloc(&count, sizeof *count));
-  HPCP_CUDA(cudaMemsetAsync(count, 0, sizeof *count, stream));
-  launch_count_mismatch(vc, sh.n, 0.5 * P * (P - 1), cfg.type, count, stream);
   unsigned long long bad = 0;
-  HPCP_CUDA(cudaMemcpyAsync(&bad, count, sizeof bad, cudaMemcpyDeviceToHost, stream));
-  HPCP_CUDA(cudaStreamSynchronize(stream));
-  (void)cudaFree(count);
+  const bool mapped_copy = !sh.host_vc.empty();
+  if (mapped_copy) {
+    // `#pragma omp target update from(VC[:n])` (allreduce-map-mpi-omp-offload.cpp:159), then the host checks its
+    // own array (:163-164) and prints "<rank> <VC[0]>" (:161).
+    HPCP_CUDA(cudaMemcpyAsync(sh.host_vc[me], vc, sh.n * esz, cudaMemcpyDeviceToHost, stream));
+    HPCP_CUDA(cudaStreamSynchronize(stream));
+    bad = count_mismatch_on_host(sh.host_vc[me], sh.n, 0.5 * P * (P - 1), cfg.type);
+  } else {
+    unsigned long long* count = nullptr;
+    HPCP_CUDA(cudaMalloc(&count, sizeof *count));
+    HPCP_CUDA(cudaMemsetAsync(count, 0, sizeof *count, stream));
+    launch_count_mismatch(vc, sh.n, 0.5 * P * (P - 1), cfg.type, count, stream);
+    HPCP_CUDA(cudaMemcpyAsync(&bad, count, sizeof bad, cudaMemcpyDeviceToHost, stream));
+    HPCP_CUDA(cudaStreamSynchronize(stream));
+    (void)cudaFree(count);
+  }
   const double total_bad = ctx.sum(static_cast<double>(bad));
   if (bad == 0)
     std::cout << "Passed " << me << std::endl;
   else
     std::cout << "FAILED " << me << ": " << bad << " wrong elements" << std::endl;
-  // The map-clause variant of the reference also prints "<rank> <VC[0]>" (allreduce-map-mpi-omp-offload.cpp:161);
-  // with -R the buffer IS host memory (registered + mapped), so the host reads it in place.
-  if (cfg.kind == AllocKind::kMapped && !sh.nvls) {
-    if (cfg.type == ElemType::kInt)
-      std::cout << me << " " << static_cast<const int*>(vc)[0] << std::endl;
-    else
-      std::cout << me << " " << static_cast<const float*>(vc)[0] << std::endl;
-  }
+  if (mapped_copy)
+    std::cout << me << " " << first_element_as_double(sh.host_vc[me], cfg.type) << std::endl;
+  else if (cfg.kind == AllocKind::kMapped && !sh.nvls)  // --map-alias: the buffer IS host memory, read in place
+    std::cout << me << " " << first_element_as_double(vc, cfg.type) << std::endl;
   if (me == 0) {
     sh.best_ms = best_ms;
     sh.total_bad = static_cast<unsigned long long>(total_bad);
@@ -338,7 +391,18 @@ int run_on_host_typed(const Config& cfg) {
 }
 
 int run_on_host(const Config& cfg) {
-  return cfg.type == ElemType::kFloat ? run_on_host_typed<float>(cfg) : run_on_host_typed<int>(cfg);
+  switch (cfg.type) {
+    case ElemType::kFloat: return run_on_host_typed<float>(cfg);
+    case ElemType::kInt: return run_on_host_typed<int>(cfg);
+    case ElemType::kUInt: return run_on_host_typed<unsigned int>(cfg);
+    case ElemType::kDouble: return run_on_host_typed<double>(cfg);
+    case ElemType::kLong: return run_on_host_typed<long long>(cfg);
+    case ElemType::kULong: return run_on_host_typed<unsigned long long>(cfg);
+    case ElemType::kShort: return run_on_host_typed<short>(cfg);
+    case ElemType::kUShort: return run_on_host_typed<unsigned short>(cfg);
+    case ElemType::kUChar: return run_on_host_typed<unsigned char>(cfg);
+  }
+  return 1;
 }
 }  // namespace
 
@@ -371,6 +435,7 @@ int main(int argc, char** argv) {
                                        {"cpu", no_argument, nullptr, 9},
                                        {"slots", required_argument, nullptr, 10},
                                        {"pull", no_argument, nullptr, 11},
+                                       {"map-alias", no_argument, nullptr, 12},
                                        {"help", no_argument, nullptr, 'h'},
                                        {nullptr, 0, nullptr, 0}};
     int opt;
@@ -395,6 +460,7 @@ int main(int argc, char** argv) {
         case 7: cfg.chunk_elems = static_cast<size_t>(std::atoll(optarg)); break;
         case 8: cfg.json_path = optarg; break;
         case 9: cfg.cpu = true; break;
+        case 12: cfg.map_alias = true; break;
         case 10: cfg.slots = std::atoi(optarg); break;
         case 11: cfg.pull = true; break;
         default: print_help(); return 1;
@@ -426,10 +492,13 @@ int main(int argc, char** argv) {
     NodeMemory mem(devices);
     sh.mem = &mem;
     sh.n = size_t{1} << cfg.log2_elems;
-    if (cfg.use_collective && sh.n % (4 * static_cast<size_t>(P)) != 0)
-      sh.n = (sh.n / (4 * P) + 1) * (4 * P);  // pad so that every rank owns an aligned slice
-    const size_t bytes = sh.n * 4;
-    sh.n_chunks = ring_num_chunks(sh.n, cfg.chunk_elems);
+    const size_t esz = elem_size(cfg.type), lanes = 16 / esz;
+    if (cfg.use_collective && sh.n % (lanes * static_cast<size_t>(P)) != 0)
+      sh.n = (sh.n / (lanes * P) + 1) * (lanes * P);  // pad so that every rank owns a 16-byte aligned slice
+    else if (sh.n % lanes != 0)
+      sh.n = (sh.n / lanes + 1) * lanes;
+    const size_t bytes = sh.n * esz;
+    sh.n_chunks = ring_num_chunks(sh.n, cfg.chunk_elems, elem_size(cfg.type));
     sh.pad_extra = sh.n_chunks * (cfg.slots == 2 ? 2 : 1);
     sh.pads = mem.alloc_pads(sh.pad_extra);
 
@@ -452,18 +521,32 @@ int main(int argc, char** argv) {
         }
       }
     }
+    // `map` variant: the kernels' arrays are the device-resident mapped copies; the host arrays live next to them.
+    const bool mapped_copy = cfg.kind == AllocKind::kMapped && !cfg.map_alias;
+    const AllocKind array_kind = mapped_copy ? AllocKind::kDevice : cfg.kind;
+    if (mapped_copy) {
+      sh.host_va.resize(P);
+      sh.host_vc.resize(P);
+      for (int r = 0; r < P; ++r) {
+        sh.host_va[r] = std::malloc(bytes);   // never read on the host: map(alloc) copies nothing
+        sh.host_vc[r] = std::malloc(bytes);
+        HPCP_REQUIRE(sh.host_va[r] != nullptr && sh.host_vc[r] != nullptr, "host allocation failed");
+      }
+    }
     if (!sh.nvls) {
-      sh.va = mem.alloc(bytes, cfg.kind);
-      sh.vc = mem.alloc(bytes, cfg.kind);
+      sh.va = mem.alloc(bytes, array_kind);
+      sh.vc = mem.alloc(bytes, array_kind);
     }
     if (!cfg.use_collective) {
       if (cfg.algo == "ring")
-        sh.slots = mem.alloc(bytes * static_cast<size_t>(cfg.slots == 2 ? 2 : P - 1), cfg.kind, /*zero=*/false);
+        sh.slots = mem.alloc(bytes * static_cast<size_t>(cfg.slots == 2 ? 2 : P - 1), array_kind, /*zero=*/false);
       else
-        sh.vb = mem.alloc(bytes, cfg.kind);
+        sh.vb = mem.alloc(bytes, array_kind);
     }
 
     run_ranks(P, [&](RankCtx& ctx) { rank_main(ctx, sh); });
+    for (void* h : sh.host_va) std::free(h);   // `target exit data map(delete)` + free (:168-170)
+    for (void* h : sh.host_vc) std::free(h);
 
     // Reporting: the number the reference computes and drops.
     const std::string algo_name =

@@ -78,11 +78,18 @@ void test_devices_and_dtypes() {
   CHECK(primary_device(0, 1, 0) == -1);
   CHECK(std::string(get_dtype<float>().name) == "float" && get_dtype<float>().reducible);
   CHECK(std::string(get_dtype<int>().name) == "int" && get_dtype<int>().elem == ElemType::kInt);
-  CHECK(!get_dtype<double>().reducible && get_dtype<double>().size == 8);
+  // every type the reference's trait maps to an MPI_SUM datatype (mpi_datatype.hpp:28-51) reduces here too
+  CHECK(get_dtype<double>().reducible && get_dtype<double>().size == 8 && get_dtype<double>().elem == ElemType::kDouble);
+  CHECK(get_dtype<long>().reducible && get_dtype<long>().elem == ElemType::kLong && elem_size(ElemType::kLong) == 8);
+  CHECK(get_dtype<unsigned short>().elem == ElemType::kUShort && elem_size(ElemType::kUShort) == 2);
+  CHECK(get_dtype<unsigned char>().reducible && elem_size(ElemType::kUChar) == 1);
+  CHECK(!get_dtype<long double>().reducible);                      // no device representation: bytes
   struct Opaque { char x[24]; };
   CHECK(std::string(get_dtype<Opaque>().name) == "bytes" && get_dtype<Opaque>().size == 24);  // MPI_BYTE analogue
   ElemType t;
   CHECK(elem_type_from_name("int32", &t) && t == ElemType::kInt);
+  CHECK(elem_type_from_name("unsigned long", &t) && t == ElemType::kULong && std::string(elem_type_name(t)) == "ulong");
+  CHECK(elem_type_from_name("float64", &t) && t == ElemType::kDouble);
   CHECK(!elem_type_from_name("complex", &t));
 }
 

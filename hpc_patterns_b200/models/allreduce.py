@@ -29,7 +29,11 @@ from ..parallel.comm import Comm
 from ..parallel.symmetric import SignalPads, SymmetricBuffer
 
 ALGOS = ("ring", "ring-unfused", "twoshot", "nvls", "nccl", "ring-nccl")
-_TORCH_DTYPE = {"float": torch.float32, "int": torch.int32}
+# element types of the reference's datatype trait (mpi_datatype.hpp:28-51) -> the torch dtype whose add is bit-identical
+# (unsigned integers share the two's-complement add of the signed type of the same width; NCCL rows only)
+_TORCH_DTYPE = {"float": torch.float32, "int": torch.int32, "uint": torch.int32, "double": torch.float64,
+                "long": torch.int64, "ulong": torch.int64, "short": torch.int16, "ushort": torch.int16,
+                "uchar": torch.uint8}
 
 
 def expected_value(world: int) -> float:
@@ -51,9 +55,10 @@ class AllreduceResult:
     elements: int
     ms: float
     mismatches: int
+    elem_bytes: int = 4
 
     def row(self) -> dict:
-        nbytes = self.elements * 4
+        nbytes = self.elements * self.elem_bytes
         sent = bytes_sent_per_rank(self.algo, nbytes, self.world)
         gbps = sent / (self.ms * 1e-3) / 1e9 if self.ms > 0 else 0.0
         return {"pattern": "allreduce", "algo": self.algo, "type": self.dtype, "ranks": self.world,
@@ -71,22 +76,24 @@ class AllreduceMiniapp:
         if algo not in ALGOS:
             raise ValueError(f"algo must be one of {ALGOS}")
         if dtype not in _TORCH_DTYPE:
-            raise ValueError("dtype must be 'float' or 'int'")
+            raise ValueError(f"dtype must be one of {sorted(_TORCH_DTYPE)}")
         self.C = native()
         self.comm, self.device = comm, device
         self.rank, self.world = comm.rank, comm.world
         self.algo, self.dtype, self.ctas, self.chunk_elems = algo, dtype, ctas, chunk_elems
+        self.esz = self.C.elem_size(dtype)
+        lanes = 16 // self.esz
         n = 1 << log2_elems
-        if n % (4 * self.world):
-            n = (n // (4 * self.world) + 1) * 4 * self.world
-        self.n, self.nbytes = n, n * 4
+        if n % (lanes * self.world):
+            n = (n // (lanes * self.world) + 1) * lanes * self.world
+        self.n, self.nbytes = n, n * self.esz
         self.right, self.left = (self.rank + 1) % self.world, (self.rank - 1) % self.world
         torch.cuda.set_device(device)
         if slots not in (0, 2):
             raise ValueError("slots must be 0 (world-1 slots) or 2")
         self.slots_policy = slots if algo == "ring" else 0
         self.pull = bool(pull) and algo == "ring"
-        self.n_chunks = self.C.ring_num_chunks(n, chunk_elems)
+        self.n_chunks = self.C.ring_num_chunks(n, chunk_elems, self.esz)
         # arrival words, then (two-slot ring) ack words
         self.pads = SignalPads(comm, device, extra_words=self.n_chunks * (2 if self.slots_policy == 2 else 1),
                                timeout_s=timeout_s)
@@ -251,7 +258,7 @@ class AllreduceMiniapp:
         bad = self.mismatches()
         total_bad = int(self.comm.sum(bad))
         print(f"Passed {self.rank}" if bad == 0 else f"FAILED {self.rank}: {bad} wrong elements", flush=True)
-        return AllreduceResult(self.algo, self.dtype, self.world, self.n, best, total_bad)
+        return AllreduceResult(self.algo, self.dtype, self.world, self.n, best, total_bad, self.esz)
 
     def close(self) -> None:
         torch.cuda.synchronize(self.device)

@@ -234,7 +234,29 @@ def test_fused_bench_pinned_host_copy(native, dev):
     assert torch.equal(d.cpu(), h) and torch.equal(back, h)
 
 
-@pytest.mark.parametrize("dtype,td", [("float", torch.float32), ("int", torch.int32)])
+@pytest.mark.parametrize("dtype,td", [("double", torch.float64), ("long", torch.int64), ("ulong", torch.int64),
+                                      ("short", torch.int16), ("ushort", torch.int16), ("uchar", torch.uint8),
+                                      ("uint", torch.int32), ("float", torch.float32), ("int", torch.int32)])
+def test_accumulate_every_reference_datatype_matches_torch(native, dev, dtype, td):
+    """VC += VA for every type the reference's datatype trait maps to an MPI_SUM type (mpi_datatype.hpp:28-51), random
+    data incl. wrap-around for the integers, against the PyTorch add of the bit-identical dtype; odd tail included."""
+    n = (1 << 16) + 3
+    g = torch.Generator(device=dev).manual_seed(7)
+    if td.is_floating_point:
+        va = torch.randn(n, dtype=td, device=dev, generator=g)
+        vc = torch.randn(n, dtype=td, device=dev, generator=g)
+    else:
+        info = torch.iinfo(td)
+        va = torch.randint(info.min, info.max, (n,), dtype=torch.int64, device=dev, generator=g).to(td)
+        vc = torch.randint(info.min, info.max, (n,), dtype=torch.int64, device=dev, generator=g).to(td)
+    want = vc + va                      # integer adds wrap in torch as they do in two's complement
+    native.accumulate(va.data_ptr(), vc.data_ptr(), n, dtype, _stream())
+    torch.cuda.synchronize()
+    assert torch.equal(vc, want)
+
+
+@pytest.mark.parametrize("dtype,td", [("float", torch.float32), ("int", torch.int32), ("double", torch.float64),
+                                      ("long", torch.int64), ("short", torch.int16), ("uchar", torch.uint8)])
 def test_allreduce_building_blocks(native, dev, dtype, td):
     n = (1 << 18) + 4
     va = torch.zeros(n, dtype=td, device=dev)
@@ -256,7 +278,7 @@ def test_allreduce_building_blocks(native, dev, dtype, td):
 
 
 @pytest.mark.parametrize("algo", ["ring", "ring-unfused", "twoshot", "nccl"])
-@pytest.mark.parametrize("dtype", ["float", "int"])
+@pytest.mark.parametrize("dtype", ["float", "int", "double", "short"])
 def test_allreduce_miniapp_single_rank(native, algo, dtype):
     from hpc_patterns_b200.models.allreduce import AllreduceMiniapp
     from hpc_patterns_b200.parallel.comm import Comm

@@ -162,7 +162,9 @@ def test_cli_peer2pear_virtual_ranks(bin_dir, transport):
 
 
 @pytest.mark.parametrize("args", [[], ["--algo", "ring-unfused"], ["-a", "--coll", "twoshot"], ["--type", "int"],
-                                  ["-a", "--coll", "twoshot", "--type", "int"]])
+                                  ["-a", "--coll", "twoshot", "--type", "int"], ["--type", "double"], ["--type", "long"],
+                                  ["--type", "short"], ["--type", "uchar"], ["-a", "--type", "double"],
+                                  ["-a", "--type", "ushort"], ["--type", "ulong", "--algo", "ring-unfused"]])
 @pytest.mark.parametrize("n", [2, 4])
 def test_cli_allreduce_virtual_ranks(bin_dir, args, n):
     rc, out, err = _run([os.path.join(bin_dir, "allreduce"), "-n", str(n), "-p", "18", "--iters", "2"] + args,
