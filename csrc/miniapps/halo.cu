@@ -1,0 +1,282 @@
+// halo: the miniapp loop as a time-stepping halo exchange — native CLI of the suite's flagship kernel.
+//
+// The reference's miniapp alternates a kernel with a blocking exchange of a full block with both ring
+// neighbours and a host wait after each (allreduce-mpi-sycl.cpp:167-181: Accumulate().wait();
+// SendRecvRing(VA -> right, VB <- left); swap; Accumulate().wait()).  This program runs the same
+// dependency structure as a slab stencil whose exchange lives INSIDE the kernel
+// (csrc/kernels/halo_stencil.cu): `-n` ranks (one host thread + one GPU each, more ranks than GPUs are
+// placed round-robin like devices.hpp:46-47), a periodic field of ranks x rows rows of `--bytes` each,
+// `--steps` time steps per timed iteration in ONE persistent launch per rank (or one launch per step
+// with --per-step), exact verification of every element against the closed-form field advanced on the
+// fly by an independent kernel, and the reference-style report: "Passed <rank>" per rank, then the
+// elapsed time (max over ranks, min over iterations) and the P2P bus bandwidth.
+//
+//   halo -n 8                       # 8 GPUs, pull mode, 7 rows of 188 743 680 B, 20 steps per iteration
+//   halo -n 2 --mode push --rows 1  # NVLink-bound: every computed row is exchanged
+//   halo -n 4 --stock memcpy        # the stock shape instead: kernel, wait, cudaMemcpyAsync to peers, wait
+#include <getopt.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../common/cuda_check.h"
+#include "../common/nvtx.h"
+#include "../common/peer_mem.h"
+#include "../common/rank_runtime.h"
+#include "../common/signal_layout.h"
+#include "../kernels/api.h"
+#include "devices.hpp"
+
+namespace {
+using namespace hpcp;
+
+struct Config {
+  int ranks = 0;
+  int rows = 7;
+  size_t bytes = 1179648ull * 40 * 4;   // one row = one message of p2p/peer2pear.cpp:115-116
+  int steps = 20;
+  int iters = 5;
+  int warmup = 1;
+  std::string mode = "pull";
+  std::string stock;                     // "" | "memcpy": kernel -> wait -> library copies -> wait per step
+  bool per_step = false;
+  HaloTuning tune;
+  uint64_t timeout_ns = 30ull * 1000 * 1000 * 1000;
+  std::string json_path;
+};
+
+void print_help() {
+  std::cout << "Usage: halo [options]\n"
+               " -n N          ranks (one host thread + one GPU each; default: all GPUs; more ranks than GPUs share)\n"
+               " --rows R      rows per rank (default 7: HBM time ~ NVLink time); --bytes B  bytes per row (one message)\n"
+               " --steps K     time steps per timed iteration (default 20); --iters N  --warmup N\n"
+               " --mode pull|push   neighbours' rows are LOADED from their fields / new boundary rows are STORED into\n"
+               "                    their halo buffers — both from inside the stencil kernel\n"
+               " --per-step    one launch per step instead of one persistent K-step launch\n"
+               " --stock memcpy     the reference's shape through stock calls: kernel; wait; copies; wait\n"
+               " --ctas N --tile-kb N --stages N   kernel geometry\n"
+               " --json FILE   append one JSON row\n";
+}
+
+struct Shared {
+  Config cfg;
+  NodeMemory* mem = nullptr;
+  SymmetricBuffer field, halo, flags, pads;
+  double best_ms = 0;
+  unsigned long long total_bad = 0;
+  int ctas = 0;
+};
+
+void rank_main(RankCtx& ctx, Shared& sh) {
+  const Config& cfg = sh.cfg;
+  const int me = ctx.rank, P = ctx.world;
+  const int dev = sh.mem->device(me);
+  HPCP_CUDA(cudaSetDevice(dev));
+  cudaStream_t stream;
+  HPCP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  const int left = (me - 1 + P) % P, right = (me + 1) % P;
+  const size_t row_elems = cfg.bytes / 4, slab = static_cast<size_t>(cfg.rows) * cfg.bytes;
+  auto u = [&](int r, int parity) { return reinterpret_cast<float*>(static_cast<char*>(sh.field.ptr[r]) + parity * slab); };
+  auto halo = [&](int r, int side, int parity) {
+    return reinterpret_cast<float*>(static_cast<char*>(sh.halo.ptr[r]) + (side * 2 + parity) * cfg.bytes);
+  };
+  uint32_t* my_pad = static_cast<uint32_t*>(sh.pads.ptr[me]);
+  uint32_t* status = my_pad + kPadWords;
+  std::vector<uint32_t*> pad_list;
+  for (int r = 0; r < P; ++r) pad_list.push_back(static_cast<uint32_t*>(sh.pads.ptr[r]));
+  const HaloMode mode = !cfg.stock.empty() ? HaloMode::kNone : cfg.mode == "push" ? HaloMode::kPush : HaloMode::kPull;
+
+  HaloStencilArgs a;
+  for (int q = 0; q < 2; ++q) {
+    a.u[q] = u(me, q);
+    a.left_u[q] = u(left, q);
+    a.right_u[q] = u(right, q);
+    a.halo_lo[q] = halo(me, 0, q);
+    a.halo_hi[q] = halo(me, 1, q);
+    a.left_halo_hi[q] = halo(left, 1, q);
+    a.right_halo_lo[q] = halo(right, 0, q);
+  }
+  a.flags_local = static_cast<uint32_t*>(sh.flags.ptr[me]);
+  a.flags_left = static_cast<uint32_t*>(sh.flags.ptr[left]);
+  a.flags_right = static_cast<uint32_t*>(sh.flags.ptr[right]);
+  a.rows = cfg.rows;
+  a.row_elems = row_elems;
+  a.timeout_ns = cfg.timeout_ns;
+  a.status = status;
+
+  launch_halo_init(u(me, 0), halo(me, 0, 0), halo(me, 1, 0), cfg.rows, row_elems, me, P, stream);
+  HPCP_CUDA(cudaStreamSynchronize(stream));
+  ctx.barrier();
+
+  uint32_t g = 0, barrier_epoch = 0;
+  cudaEvent_t e0, e1;
+  HPCP_CUDA(cudaEventCreate(&e0));
+  HPCP_CUDA(cudaEventCreate(&e1));
+  double best_ms = std::numeric_limits<double>::max();
+  for (int it = 0; it < cfg.warmup + cfg.iters; ++it) {
+    NvtxRange range(it < cfg.warmup ? "halo warm-up" : "halo timed");
+    HPCP_CUDA(cudaStreamSynchronize(stream));
+    ctx.barrier();
+    launch_barrier_all(pad_list.data(), me, P, ++barrier_epoch, cfg.timeout_ns, status, stream);
+    HPCP_CUDA(cudaEventRecord(e0, stream));
+    if (!cfg.stock.empty()) {
+      for (int k = 0; k < cfg.steps; ++k, ++g) {
+        const int out = (g + 1) & 1;
+        a.step_base = g;
+        a.steps = 1;
+        launch_halo_stencil(a, HaloMode::kNone, cfg.tune, dev, stream);
+        HPCP_CUDA(cudaStreamSynchronize(stream));                                   // Accumulate(...).wait()
+        HPCP_CUDA(cudaMemcpyAsync(halo(left, 1, out), u(me, out), cfg.bytes, cudaMemcpyDefault, stream));
+        HPCP_CUDA(cudaMemcpyAsync(halo(right, 0, out), u(me, out) + static_cast<size_t>(cfg.rows - 1) * row_elems,
+                                  cfg.bytes, cudaMemcpyDefault, stream));
+        HPCP_CUDA(cudaStreamSynchronize(stream));                                   // the blocking Send/Recv pair
+        ctx.barrier();                                                              // ... of every rank
+      }
+    } else if (cfg.per_step) {
+      for (int k = 0; k < cfg.steps; ++k, ++g) {
+        a.step_base = g;
+        a.steps = 1;
+        launch_halo_stencil(a, mode, cfg.tune, dev, stream);
+      }
+    } else {
+      a.step_base = g;
+      a.steps = cfg.steps;
+      sh.ctas = launch_halo_stencil(a, mode, cfg.tune, dev, stream);
+      g += static_cast<uint32_t>(cfg.steps);
+    }
+    HPCP_CUDA(cudaEventRecord(e1, stream));
+    HPCP_CUDA(cudaStreamSynchronize(stream));
+    uint32_t st = 0;
+    HPCP_CUDA(cudaMemcpy(&st, status, sizeof st, cudaMemcpyDefault));
+    HPCP_REQUIRE(st == kStatusOk, "rank " + std::to_string(me) + ": device-side wait timed out");
+    float ms = 0;
+    HPCP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double t = ctx.max(ms);
+    if (it >= cfg.warmup) best_ms = std::min(best_ms, t);
+  }
+
+  // Verify every element of this rank's slab against the closed-form field advanced g steps.
+  unsigned long long* count = nullptr;
+  HPCP_CUDA(cudaMalloc(&count, sizeof *count));
+  HPCP_CUDA(cudaMemsetAsync(count, 0, sizeof *count, stream));
+  launch_halo_verify_from_init(u(me, g & 1), cfg.rows, row_elems, me, P, g, a.alpha, a.s, count, stream);
+  unsigned long long bad = 0;
+  HPCP_CUDA(cudaMemcpyAsync(&bad, count, sizeof bad, cudaMemcpyDeviceToHost, stream));
+  HPCP_CUDA(cudaStreamSynchronize(stream));
+  (void)cudaFree(count);
+  const double total_bad = ctx.sum(static_cast<double>(bad));
+  if (bad == 0)
+    std::cout << "Passed " << me << std::endl;
+  else
+    std::cout << "FAILED " << me << ": " << bad << " wrong elements" << std::endl;
+  if (me == 0) {
+    sh.best_ms = best_ms;
+    sh.total_bad = static_cast<unsigned long long>(total_bad);
+  }
+  (void)cudaEventDestroy(e0);
+  (void)cudaEventDestroy(e1);
+  (void)cudaStreamDestroy(stream);
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  try {
+    Config cfg;
+    static const option long_opts[] = {{"rows", required_argument, nullptr, 1},   {"bytes", required_argument, nullptr, 2},
+                                       {"steps", required_argument, nullptr, 3},  {"iters", required_argument, nullptr, 4},
+                                       {"warmup", required_argument, nullptr, 5}, {"mode", required_argument, nullptr, 6},
+                                       {"per-step", no_argument, nullptr, 7},     {"stock", required_argument, nullptr, 8},
+                                       {"ctas", required_argument, nullptr, 9},   {"tile-kb", required_argument, nullptr, 10},
+                                       {"stages", required_argument, nullptr, 11}, {"json", required_argument, nullptr, 12},
+                                       {"help", no_argument, nullptr, 'h'},       {nullptr, 0, nullptr, 0}};
+    int opt;
+    while ((opt = getopt_long(argc, argv, "hn:", long_opts, nullptr)) != -1) {
+      switch (opt) {
+        case 'h': print_help(); return 1;
+        case 'n': cfg.ranks = std::atoi(optarg); break;
+        case 1: cfg.rows = std::atoi(optarg); break;
+        case 2: cfg.bytes = static_cast<size_t>(std::atoll(optarg)); break;
+        case 3: cfg.steps = std::max(1, std::atoi(optarg)); break;
+        case 4: cfg.iters = std::max(1, std::atoi(optarg)); break;
+        case 5: cfg.warmup = std::max(0, std::atoi(optarg)); break;
+        case 6: cfg.mode = optarg; break;
+        case 7: cfg.per_step = true; break;
+        case 8: cfg.stock = optarg; break;
+        case 9: cfg.tune.ctas = std::atoi(optarg); break;
+        case 10: cfg.tune.tile_kb = std::atoi(optarg); break;
+        case 11: cfg.tune.stages = std::atoi(optarg); break;
+        case 12: cfg.json_path = optarg; break;
+        default: print_help(); return 1;
+      }
+    }
+    HPCP_REQUIRE(cfg.mode == "pull" || cfg.mode == "push", "--mode must be pull or push");
+    HPCP_REQUIRE(cfg.stock.empty() || cfg.stock == "memcpy", "--stock accepts memcpy");
+    HPCP_REQUIRE(cfg.rows >= 1 && cfg.bytes >= 16 && cfg.bytes % 16 == 0, "--rows >= 1, --bytes a multiple of 16");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+      (void)cudaGetLastError();
+      std::cerr << "Error: No devices" << std::endl;
+      return 1;
+    }
+    const int P = cfg.ranks > 0 ? cfg.ranks : ndev;
+    HPCP_REQUIRE(P >= 1 && P <= kMaxRanks, "ranks out of range");
+    HPCP_REQUIRE(P * cfg.rows <= 128, "ranks x rows must not exceed 128 (verification kernel)");
+    std::vector<int> devices;
+    for (int r = 0; r < P; ++r) devices.push_back(primary_device(r, P, ndev));
+    const int ranks_per_dev = (P + ndev - 1) / ndev;
+    const HaloMode geo_mode = cfg.mode == "push" ? HaloMode::kPush : HaloMode::kPull;
+    if (ranks_per_dev > 1) {  // co-residency of the spinning persistent kernels that share a GPU
+      HaloTuning all = cfg.tune;
+      all.ctas = 0;
+      const int full = halo_stencil_ctas(cfg.bytes / 4, all, geo_mode, devices[0]);
+      const int share = std::max(1, full / ranks_per_dev);
+      cfg.tune.ctas = cfg.tune.ctas > 0 ? std::min(cfg.tune.ctas, share) : share;
+    }
+    // the same grid on every rank and in every launch: the step words are indexed by CTA
+    cfg.tune.ctas = halo_stencil_ctas(cfg.bytes / 4, cfg.tune, geo_mode, devices[0]);
+
+    Shared sh;
+    sh.cfg = cfg;
+    NodeMemory mem(devices);
+    sh.mem = &mem;
+    sh.field = mem.alloc(2 * static_cast<size_t>(cfg.rows) * cfg.bytes, AllocKind::kDevice, /*zero=*/false);
+    sh.halo = mem.alloc(4 * cfg.bytes, AllocKind::kDevice, /*zero=*/false);
+    sh.flags = mem.alloc(kHaloFlagBytes, AllocKind::kDevice, /*zero=*/true);
+    sh.pads = mem.alloc_pads(0);
+    sh.ctas = cfg.tune.ctas;
+
+    run_ranks(P, [&](RankCtx& ctx) { rank_main(ctx, sh); });
+
+    const double ms_per_step = sh.best_ms / cfg.steps;
+    const double bus = static_cast<double>(P) * 2.0 * static_cast<double>(cfg.bytes) / (ms_per_step * 1e6);
+    const std::string what = !cfg.stock.empty() ? "stock-" + cfg.stock : cfg.mode + (cfg.per_step ? "/per-step" : "/persistent");
+    std::cout << "Elapsed (max over ranks, min of " << cfg.iters << "): " << sh.best_ms << " ms for " << cfg.steps
+              << " steps = " << ms_per_step << " ms/step | halo " << what << " P=" << P << " rows=" << cfg.rows
+              << " bytes=" << cfg.bytes << " ctas=" << sh.ctas << " | " << bus << " GB/s P2P bus (aggregate), "
+              << bus / P / 2.0 << " GB/s per GPU per direction" << std::endl;
+    if (!cfg.json_path.empty()) {
+      if (FILE* f = std::fopen(cfg.json_path.c_str(), "a")) {
+        std::fprintf(f,
+                     "{\"pattern\":\"halo\",\"variant\":\"%s\",\"ranks\":%d,\"rows\":%d,\"bytes\":%zu,\"steps\":%d,"
+                     "\"ms_per_step\":%.6f,\"bus_GBps\":%.3f,\"per_gpu_per_dir_GBps\":%.3f,\"ctas\":%d,\"mismatches\":%llu}\n",
+                     what.c_str(), P, cfg.rows, cfg.bytes, cfg.steps, ms_per_step, bus, bus / P / 2.0, sh.ctas,
+                     sh.total_bad);
+        std::fclose(f);
+      }
+    }
+    mem.free(sh.field);
+    mem.free(sh.halo);
+    mem.free(sh.flags);
+    mem.free(sh.pads);
+    return sh.total_bad == 0 ? 0 : 1;
+  } catch (const std::exception& e) {
+    std::cerr << "Error: " << e.what() << std::endl;
+    return 1;
+  }
+}

@@ -3,6 +3,7 @@
   concurency   compute-while-copy overlap benchmark (native driver in-process)
   peer2pear    P2P bandwidth, process-per-GPU (run under torchrun for >1 GPU)
   allreduce    allreduce miniapp, process-per-GPU (run under torchrun)
+  halo         the miniapp loop as a halo exchange fused into a slab stencil — the flagship (run under torchrun)
   tp           tensor-parallel linear layers with the collective fused into the GEMM, vs cuBLAS + NCCL (torchrun)
   topology     fabric planes / rank->GPU mapping (JSON)
   tile-mapping per-rank launcher: <policy> <CVD|SET> cmd...
@@ -17,7 +18,7 @@ from __future__ import annotations
 import os
 import sys
 
-_GPU_PROGRAMS = ("peer2pear", "allreduce", "tp", "interop")
+_GPU_PROGRAMS = ("peer2pear", "allreduce", "halo", "tp", "interop")
 
 
 def _no_gpu_message(prog: str):
@@ -66,6 +67,9 @@ def _dispatch(prog: str, rest: list) -> int:
         return m(rest)
     if prog == "allreduce":
         from .models.allreduce import main as m
+        return m(rest)
+    if prog == "halo":
+        from .models.halo import main as m
         return m(rest)
     if prog == "tp":
         from .models.tensor_parallel import main as m

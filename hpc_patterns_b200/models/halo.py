@@ -404,3 +404,62 @@ class VirtualRing:
     def close(self) -> None:
         for hs in self.ranks:
             hs.close()
+
+
+def main(argv: Optional[List[str]] = None) -> int:
+    """``torchrun --nproc-per-node N -m hpc_patterns_b200 halo [--rows R] [--bytes B] [--steps K] [--mode pull|push]``
+    — process-per-GPU twin of ``bin/halo``: same report lines (``Passed <rank>``, elapsed, bus GB/s)."""
+    import argparse
+    import json
+
+    from ..utils.timing import BlockTimer
+
+    ap = argparse.ArgumentParser(prog="halo")
+    ap.add_argument("--rows", type=int, default=balanced_rows())
+    ap.add_argument("--bytes", type=int, default=REFERENCE_MESSAGE_BYTES)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--mode", default="pull", choices=("pull", "push"))
+    ap.add_argument("--per-step", action="store_true", help="one launch per step instead of one persistent launch")
+    ap.add_argument("--stock", default=None, choices=("memcpy", "nccl"),
+                    help="the reference's shape through stock calls instead: kernel; wait; library transfer; wait")
+    ap.add_argument("--tile-kb", type=int, default=0)
+    ap.add_argument("--stages", type=int, default=0)
+    ap.add_argument("--ctas", type=int, default=0)
+    ap.add_argument("--json", default=None)
+    args = ap.parse_args(argv)
+    comm = Comm()
+    dev = comm.device
+    torch.cuda.set_device(dev)
+    tune = {k: v for k, v in (("tile_kb", args.tile_kb), ("stages", args.stages), ("ctas", args.ctas)) if v}
+    hs = HaloStencil(comm, dev, args.bytes, args.rows, args.mode, tune=tune)
+    if args.stock:
+        enqueue = lambda: [hs.stock_step(args.stock) for _ in range(args.steps)]      # noqa: E731
+    elif args.per_step:
+        enqueue = lambda: [hs.step(1) for _ in range(args.steps)]                      # noqa: E731
+    else:
+        enqueue = lambda: hs.step(args.steps)                                          # noqa: E731
+    m = BlockTimer(comm, hs.pads, dev).measure(enqueue, args.steps, blocks=args.iters, preheat_ms=100.0)
+    bad = hs.verify_from_init()
+    print(f"{'Passed' if bad == 0 else 'FAILED'} {comm.rank}" + ("" if bad == 0 else f": {bad} wrong elements"), flush=True)
+    total_bad = int(comm.sum(bad))
+    comm.barrier()
+    if comm.rank == 0:
+        bus = comm.world * 2 * args.bytes / (m["ms"] * 1e6)
+        what = f"stock-{args.stock}" if args.stock else args.mode + ("/per-step" if args.per_step else "/persistent")
+        print(f"Elapsed (max over ranks, min of {args.iters}): {m['ms'] * args.steps:.4f} ms for {args.steps} steps = "
+              f"{m['ms']:.5f} ms/step | halo {what} P={comm.world} rows={args.rows} bytes={args.bytes} ctas={hs.ctas} | "
+              f"{bus:.1f} GB/s P2P bus (aggregate), {bus / comm.world / 2:.1f} GB/s per GPU per direction", flush=True)
+        if args.json:
+            with open(args.json, "a") as f:
+                f.write(json.dumps({"pattern": "halo", "variant": what, "ranks": comm.world, "rows": args.rows,
+                                    "bytes": args.bytes, "steps": args.steps, "ms_per_step": m["ms"],
+                                    "bus_GBps": bus, "per_gpu_per_dir_GBps": bus / comm.world / 2, "ctas": hs.ctas,
+                                    "mismatches": total_bad}) + "\n")
+    hs.close()
+    comm.close()
+    return 0 if total_bad == 0 else 1
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

@@ -40,7 +40,7 @@ def test_topology_and_parse(native, tmp_path):
 def test_python_programs_fail_cleanly_without_gpu(gpu_count):
     if gpu_count:
         return
-    for prog in ("peer2pear", "allreduce", "tp", "interop"):
+    for prog in ("peer2pear", "allreduce", "halo", "tp", "interop"):
         p = run(prog)
         assert p.returncode == 1 and p.stderr.startswith(f"Error: {prog}: no CUDA device"), p.stderr
         assert "Traceback" not in p.stderr
@@ -50,7 +50,7 @@ def test_python_programs_fail_cleanly_without_gpu(gpu_count):
 def test_native_clis_fail_cleanly_without_gpu(bin_dir, gpu_count):
     if gpu_count:
         return
-    for exe, needle in (("peer2pear", "no CUDA device"), ("allreduce", "No devices"),
+    for exe, needle in (("peer2pear", "no CUDA device"), ("allreduce", "No devices"), ("halo", "No devices"),
                         ("interop_torchless", "no CUDA device"), ("interop_driver", "no CUDA device")):
         p = subprocess.run([os.path.join(bin_dir, exe)], capture_output=True, text=True)
         assert p.returncode == 1 and needle in (p.stderr + p.stdout), exe
@@ -58,6 +58,10 @@ def test_native_clis_fail_cleanly_without_gpu(bin_dir, gpu_count):
     assert p.returncode == 0 and "--transport" in p.stdout
     p = subprocess.run([os.path.join(bin_dir, "allreduce"), "-h"], capture_output=True, text=True)
     assert p.returncode == 1 and "2^k elements" in p.stdout
+    p = subprocess.run([os.path.join(bin_dir, "halo"), "-h"], capture_output=True, text=True)
+    assert p.returncode == 1 and "--mode pull|push" in p.stdout
+    p = subprocess.run([os.path.join(bin_dir, "halo"), "--mode", "teleport"], capture_output=True, text=True)
+    assert p.returncode == 1 and "--mode must be pull or push" in p.stderr
     p = subprocess.run([os.path.join(bin_dir, "peer2pear"), "--transport", "carrier-pigeon"], capture_output=True,
                        text=True)
     assert p.returncode == 1 and "unknown transport" in p.stderr

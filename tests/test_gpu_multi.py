@@ -171,3 +171,31 @@ def test_cli_allreduce_virtual_ranks(bin_dir, args, n):
                         env={"CUDA_VISIBLE_DEVICES": "0"}, timeout=180)
     assert rc == 0, out + err
     assert out.count("Passed") == n
+
+
+@pytest.mark.parametrize("args", [[], ["--mode", "push"], ["--per-step"], ["--stock", "memcpy"], ["--rows", "1", "--mode", "push"]])
+@pytest.mark.parametrize("n", [1, 2, 4])
+def test_cli_halo_virtual_ranks(bin_dir, args, n):
+    """The native flagship CLI with more ranks than GPUs: the persistent kernels of all ranks share one GPU and spin
+    on each other's step words (grids are sized for co-residency)."""
+    rc, out, err = _run([os.path.join(bin_dir, "halo"), "-n", str(n), "--bytes", str((4 << 20) + 4096), "--rows", "3",
+                         "--steps", "5", "--iters", "2"] + args, env={"CUDA_VISIBLE_DEVICES": "0"}, timeout=180)
+    assert rc == 0, out + err
+    assert out.count("Passed") == n and "GB/s P2P bus" in out
+
+
+@needs2
+@pytest.mark.parametrize("args", [[], ["--mode", "push"], ["--stock", "memcpy"]])
+def test_cli_halo(bin_dir, args):
+    n = min(_ngpu(), 4)
+    rc, out, err = _run([os.path.join(bin_dir, "halo"), "-n", str(n), "--bytes", str(32 << 20), "--rows", "3",
+                         "--steps", "6", "--iters", "2"] + args, timeout=180)
+    assert rc == 0, out + err
+    assert out.count("Passed") == n
+
+
+def test_python_halo_program_one_rank():
+    rc, out, err = _run([sys.executable, "-m", "hpc_patterns_b200", "halo", "--bytes", str(8 << 20), "--rows", "2",
+                         "--steps", "4", "--iters", "2"], timeout=240)
+    assert rc == 0, out + err
+    assert "Passed 0" in out and "GB/s P2P bus" in out
