@@ -72,6 +72,12 @@ struct Shared {
   int ctas = 0;
 };
 
+// HPCP_TRACE=1: one stderr line per rank per milestone (which call a stuck rank never returned from).
+void trace(int rank, const char* what, int it = -1, int k = -1) {
+  static const bool on = std::getenv("HPCP_TRACE") != nullptr;
+  if (on) std::fprintf(stderr, "[halo trace] rank %d %s it=%d step=%d\n", rank, what, it, k);
+}
+
 void rank_main(RankCtx& ctx, Shared& sh) {
   const Config& cfg = sh.cfg;
   const int me = ctx.rank, P = ctx.world;
@@ -121,9 +127,11 @@ void rank_main(RankCtx& ctx, Shared& sh) {
   for (int it = 0; it < cfg.warmup + cfg.iters; ++it) {
     NvtxRange range(it < cfg.warmup ? "halo warm-up" : "halo timed");
     HPCP_CUDA(cudaStreamSynchronize(stream));
+    trace(me, "before host barrier", it);
     ctx.barrier();
     launch_barrier_all(pad_list.data(), me, P, ++barrier_epoch, cfg.timeout_ns, status, stream);
     HPCP_CUDA(cudaEventRecord(e0, stream));
+    trace(me, "device barrier enqueued", it);
     if (!cfg.stock.empty()) {
       for (int k = 0; k < cfg.steps; ++k, ++g) {
         const int out = (g + 1) & 1;
@@ -131,10 +139,12 @@ void rank_main(RankCtx& ctx, Shared& sh) {
         a.steps = 1;
         launch_halo_stencil(a, HaloMode::kNone, cfg.tune, dev, stream);
         HPCP_CUDA(cudaStreamSynchronize(stream));                                   // Accumulate(...).wait()
+        trace(me, "kernel done", it, k);
         HPCP_CUDA(cudaMemcpyAsync(halo(left, 1, out), u(me, out), cfg.bytes, cudaMemcpyDefault, stream));
         HPCP_CUDA(cudaMemcpyAsync(halo(right, 0, out), u(me, out) + static_cast<size_t>(cfg.rows - 1) * row_elems,
                                   cfg.bytes, cudaMemcpyDefault, stream));
         HPCP_CUDA(cudaStreamSynchronize(stream));                                   // the blocking Send/Recv pair
+        trace(me, "copies done", it, k);
         ctx.barrier();                                                              // ... of every rank
       }
     } else if (cfg.per_step) {

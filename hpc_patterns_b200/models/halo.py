@@ -274,7 +274,7 @@ class HaloStencil:
         torch.cuda.synchronize(self.device)
         return bufs
 
-    def step_from_host(self, host_in: torch.Tensor, host_out: torch.Tensor, chunks: int = 8) -> None:
+    def step_from_host(self, host_in: torch.Tensor, host_out: torch.Tensor, chunks: int = 16) -> None:
         """Out-of-core time step, the public end-to-end call: the slab lives in pinned host memory; this uploads ALL of
         it (every input the step consumes), runs the fused step with the NVLink exchange, and downloads ALL of the new
         slab.  Column chunks pipeline H2D, kernel and D2H on three streams; the neighbours' halos never touch the host

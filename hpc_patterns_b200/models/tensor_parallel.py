@@ -123,9 +123,14 @@ class RowParallelLinear(_FusedLinearBase):
         self.launches += 3
         return self.y
 
-    def stock_forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """cuBLAS GEMM + NCCL reduce_scatter / all_reduce (fp32), the stock pattern."""
-        full = x.float() @ self.w.float().t() if x.device.type == "cpu" else torch.matmul(x, self.w.t()).float()
+    def stock_forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None, exact: bool = False) -> torch.Tensor:
+        """cuBLAS GEMM + NCCL reduce_scatter / all_reduce (fp32), the stock pattern.  ``exact``: fp32 GEMM (the
+        reference of ``--check``; the timed stock GEMM is bf16 in / bf16 out like a stock layer, whose output rounding
+        is NOT what the fused layer — fp32 accumulators straight into the collective — is compared against)."""
+        if x.device.type == "cpu" or exact:
+            full = x.float() @ self.w.float().t()
+        else:
+            full = torch.matmul(x, self.w.t()).float()
         if self.world == 1:
             return full
         if self.reduce == "all":
@@ -311,7 +316,7 @@ def main(argv: Optional[List[str]] = None) -> int:
     row.w.copy_(_dyadic((args.n, k_local), device, 200 + comm.rank))
     if args.check:
         y = row.forward(x).clone()
-        ref = row.stock_forward(x)
+        ref = row.stock_forward(x, exact=True)
         if P == 1:
             ref = ref[: args.m // P]
         torch.cuda.synchronize(dev)
@@ -339,7 +344,7 @@ def main(argv: Optional[List[str]] = None) -> int:
             ar.w.copy_(_dyadic((args.n, k_local), device, 200 + comm.rank))
             if args.check:
                 y = ar.forward(x).clone()
-                ref = ar.stock_forward(x)
+                ref = ar.stock_forward(x, exact=True)
                 torch.cuda.synchronize(dev)
                 ar.check()
                 out["row_parallel_allreduce_exact"] = bool(comm.min(float(torch.equal(y, ref))) == 1.0)

@@ -9,7 +9,10 @@ run bench.py --gpus $N --steps 20 --warmup 5 > $OUT/bench_n2.json 2> $OUT/bench_
 run bench.py --gpus $N --steps 200 --warmup 5 --no-extras > $OUT/bench_n2_200.json 2>> $OUT/bench_n2.err; cut -c1-500 $OUT/bench_n2_200.json
 run scripts/halo_tune.py --out $OUT/halo_tune_n2.jsonl --modes pull push --geometry 16x6 16x7 12x8 8x6 32x6 2>&1 | grep '^{' | cut -c1-260
 run scripts/halo_tune.py --out $OUT/halo_tune_n2_rows.jsonl --modes pull push --geometry 16x6 --rows 1 3 5 2>&1 | grep '^{' | cut -c1-260
-timeout 900 python -m pytest tests/test_gpu_multi.py -q --timeout 300 2>&1 | tail -15 | tee $OUT/pytest_multi.txt
+timeout 900 python -m pytest tests/test_gpu_multi.py -q --timeout 200 -k "not virtual_ranks" > $OUT/pytest_multi_full.txt 2>&1; tail -15 $OUT/pytest_multi_full.txt
+for v in "" "--mode push" "--per-step" "--stock memcpy" "--rows 1" "--rows 1 --mode push"; do
+  timeout 120 bin/halo -n $N $v --json $OUT/halo_cli_n$N.jsonl 2>&1 | tail -1 | cut -c1-250
+done
 run scripts/p2p_tune.py --out $OUT/p2p_tune.jsonl --quick 2>&1 | grep -E '^\{|skip' | cut -c1-200
 export HPCP_EXPERIMENTAL=1
 timeout 600 python -m pytest tests/test_gpu_multi.py -k "two_slots or pull_ring" -q --timeout 200 2>&1 | tail -6 | tee $OUT/pytest_ring_variants.txt
@@ -25,4 +28,10 @@ for mode in pull push; do
 done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:copy_ -s 4 -c 4 -f -o $OUT/prof_p2p_n2 \
   python scripts/ncu_p2p.py --bytes 100663296 --reps 2 > $OUT/ncu_p2p.log 2>&1; tail -2 $OUT/ncu_p2p.log
+# diagnosis of the >= 3 thread-ranks-per-GPU timeouts (GPU 0 only)
+export CUDA_VISIBLE_DEVICES=0
+HPCP_TRACE=1 timeout 100 bin/halo -n 3 --bytes 4198400 --rows 3 --steps 3 --iters 1 --stock memcpy > $OUT/diag_halo_stock_n3.txt 2>&1; tail -25 $OUT/diag_halo_stock_n3.txt
+CUDA_DEVICE_MAX_CONNECTIONS=32 timeout 100 bin/halo -n 3 --bytes 4198400 --rows 3 --steps 3 --iters 1 --stock memcpy 2>&1 | tail -3 | sed 's/^/[maxconn32] /'
+CUDA_DEVICE_MAX_CONNECTIONS=32 timeout 100 bin/allreduce -n 4 -p 18 --iters 2 2>&1 | tail -3 | sed 's/^/[maxconn32 allreduce n4] /'
+CUDA_DEVICE_MAX_CONNECTIONS=32 timeout 100 bin/peer2pear v -n 2 --transport memcpy --bytes 4194304 --iters 2 2>&1 | tail -3 | sed 's/^/[maxconn32 p2p memcpy] /'
 echo "== r2 call3 done"
