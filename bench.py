@@ -40,7 +40,9 @@ REFERENCE_UNAVAILABLE = ("argonne-lcf/HPC-Patterns is C++17 SYCL/OpenMP-offload/
                          "builds (g++ -fopenmp): see the cpu_concurency field / --config cpu_concurency")
 MESSAGE_BYTES = 1179648 * 40 * 4
 HBM_GBS_MEASURED = 6567.4     # MEASURED_PEAKS.json hbm_gbs (copy, read+write bytes)
-NVLINK_GBS_MEASURED = 770.0   # measured peer copy per direction (B200_PROFILING.md); 900 nominal
+NVLINK_GBS_MEASURED = 770.0   # measured peer copy, ONE direction busy (B200_PROFILING.md); 900 nominal
+NVLINK_BIDIR_GBS_MEASURED = 706.1   # copy engines with BOTH directions of a pair busy: 1412.2 GB/s per pair
+                                    # (profiles/r2_call3_2gpu/p2p_tune.jsonl) — what a neighbour exchange can get
 
 
 def env_int(name: str, default: int) -> int:
@@ -118,7 +120,7 @@ def main() -> int:
             uuid = None
         sampler = ClockSampler(gpu_index=device, period_ms=1.0, uuid=uuid).start(paused=True)
 
-    rows = args.rows if args.rows > 0 else balanced_rows(HBM_GBS_MEASURED, NVLINK_GBS_MEASURED)
+    rows = args.rows if args.rows > 0 else balanced_rows(HBM_GBS_MEASURED, NVLINK_BIDIR_GBS_MEASURED)
     tune = {k: v for k, v in (("ctas", args.ctas), ("tile_kb", args.tile_kb), ("stages", args.stages)) if v}
     K, W = args.steps, max(args.warmup, 3)
     hs = HaloStencil(comm, device, args.bytes, rows, args.mode, tune=tune)
@@ -145,7 +147,7 @@ def main() -> int:
     value = world * 2 * msg / (ms_per_step * 1e-3) / 1e9          # aggregate GB/s over all GPUs, both neighbours
     per_gpu_dir = msg * 2 / (ms_per_step * 1e-3) / 1e9            # per GPU per direction
     hbm_ms = hs.hbm_bytes_per_step() / HBM_GBS_MEASURED / 1e6
-    nvl_ms = (hs.nvlink_bytes_per_step() / NVLINK_GBS_MEASURED / 1e6) if world > 1 else 0.0
+    nvl_ms = (hs.nvlink_bytes_per_step() / NVLINK_BIDIR_GBS_MEASURED / 1e6) if world > 1 else 0.0
     roof_ms = max(hbm_ms, nvl_ms)
 
     extras = {}
@@ -262,8 +264,9 @@ def main() -> int:
                 "global_batch": world, "seq_len": msg // 4, "parallelism": f"ring{world}",
                 "message_bytes": msg, "messages_per_step_per_gpu": 2, "rows": rows, "mode": args.mode,
                 "ctas": hs.ctas, "steps_per_launch": K,
-                "rows_rule": "rows such that the step's HBM time ~ its NVLink time at the measured peaks "
-                             "(6567 GB/s, 770 GB/s/dir) — the balancing rule of the reference's autotuner",
+                "rows_rule": "rows such that the step's HBM time ~ its NVLink time at stock measured rates (HBM copy "
+                             "6567 GB/s; copy engines with both directions busy 706 GB/s/dir) — the balancing rule of "
+                             "the reference's autotuner",
                 "peer": "self (no NVLink at N=1)" if world == 1 else "rank-1 and rank+1 over NVLink/NVSwitch",
                 "l2": f"inputs larger than L2: {(2 * rows + 2)} x 180 MiB streamed per step, no reuse between steps",
                 "timing": "in-kernel cross-GPU barrier, then cuda events on the launching stream; max over ranks; "
@@ -283,12 +286,14 @@ def main() -> int:
             "gpu_launches": gpu_launches_per_block, "gpu_launches_all_blocks": total_fused_launches,
             "wrong_words": wrong_init + wrong_last,
             "per_gpu_per_direction_GBps": round(per_gpu_dir, 1),
+            "frac_of_nvlink_706_measured_bidirectional": round(per_gpu_dir / NVLINK_BIDIR_GBS_MEASURED, 3) if world > 1 else None,
             "frac_of_nvlink_770_measured": round(per_gpu_dir / 770.0, 3) if world > 1 else None,
             "frac_of_nvlink_900_nominal": round(per_gpu_dir / 900.0, 3) if world > 1 else None,
             "hbm_traffic_GBps": round(hs.hbm_bytes_per_step() / (ms_per_step * 1e-3) / 1e9, 1),
             "roofline": {"hbm_ms": round(hbm_ms, 4), "nvlink_ms": round(nvl_ms, 4), "bound_ms": round(roof_ms, 4),
                          "frac": round(roof_ms / ms_per_step, 3),
-                         "of": "max(HBM bytes / 6567.4 GB/s measured, NVLink bytes per direction / 770 GB/s measured)"},
+                         "of": "max(HBM bytes / 6567.4 GB/s measured copy peak, NVLink bytes per direction / 706.1 GB/s "
+                               "measured with both directions busy)"},
             **extras,
         }
         if not args.no_extras:

@@ -11,7 +11,7 @@
 // fly by an independent kernel, and the reference-style report: "Passed <rank>" per rank, then the
 // elapsed time (max over ranks, min over iterations) and the P2P bus bandwidth.
 //
-//   halo -n 8                       # 8 GPUs, pull mode, 7 rows of 188 743 680 B, 20 steps per iteration
+//   halo -n 8                       # 8 GPUs, pull mode, 8 rows of 188 743 680 B, 20 steps per iteration
 //   halo -n 2 --mode push --rows 1  # NVLink-bound: every computed row is exchanged
 //   halo -n 4 --stock memcpy        # the stock shape instead: kernel, wait, cudaMemcpyAsync to peers, wait
 #include <getopt.h>
@@ -37,7 +37,7 @@ using namespace hpcp;
 
 struct Config {
   int ranks = 0;
-  int rows = 7;
+  int rows = 8;
   size_t bytes = 1179648ull * 40 * 4;   // one row = one message of p2p/peer2pear.cpp:115-116
   int steps = 20;
   int iters = 5;
@@ -53,7 +53,7 @@ struct Config {
 void print_help() {
   std::cout << "Usage: halo [options]\n"
                " -n N          ranks (one host thread + one GPU each; default: all GPUs; more ranks than GPUs share)\n"
-               " --rows R      rows per rank (default 7: HBM time ~ NVLink time); --bytes B  bytes per row (one message)\n"
+               " --rows R      rows per rank (default 8: HBM time ~ NVLink time); --bytes B  bytes per row (one message)\n"
                " --steps K     time steps per timed iteration (default 20); --iters N  --warmup N\n"
                " --mode pull|push   neighbours' rows are LOADED from their fields / new boundary rows are STORED into\n"
                "                    their halo buffers — both from inside the stencil kernel\n"

@@ -32,17 +32,21 @@ from ..parallel.comm import Comm
 from ..parallel.symmetric import SignalPads, SymmetricBuffer, tensor_from_ptr
 
 REFERENCE_MESSAGE_BYTES = 1179648 * 40 * 4  # 188 743 680, p2p/peer2pear.cpp:115-116
-DEFAULT_ROWS = 6
+DEFAULT_ROWS = 8
 MODES = ("pull", "push", "none")
 
 
-def balanced_rows(hbm_gbs: float = 6567.4, nvlink_gbs: float = 770.0) -> int:
+def balanced_rows(hbm_gbs: float = 6567.4, nvlink_gbs: float = 706.1) -> int:
     """Rows per slab for which the step's HBM time equals its NVLink time.
 
     The reference's concurrency benchmark tunes its commands to equal duration before it
     overlaps them (concurency/main.cpp:219-258); the same rule here: a step streams
     (2*rows + 2) rows through HBM in pull mode (rows reads + rows writes + the two boundary
-    rows the neighbours read) and moves 2 rows over NVLink in each direction.
+    rows the neighbours read) and moves 2 rows over NVLink in EACH direction at once.
+    Denominators are stock measurements, not this kernel's: the driver's copy peak
+    (MEASURED_PEAKS.json hbm_gbs) and the copy engines' rate with both directions of a pair
+    busy — 1412.2 GB/s per pair = 706.1 per direction (profiles/r2_call3_2gpu/p2p_tune.jsonl;
+    one direction alone reaches 717-770).  -> 8 rows.
     """
     rows = (2.0 * hbm_gbs / nvlink_gbs - 2.0) / 2.0
     return max(1, int(rows))
@@ -155,10 +159,14 @@ class HaloStencil:
         self.comm.barrier()
 
     def _use_layout(self, chunks: int) -> None:
+        """A time series is stepped ONE way: whole-row fused steps (1), column-chunked host steps (n chunks, one word
+        set per chunk) or stock steps (0: they exchange through library calls and never touch the step words, so a
+        fused step after them would wait for words nobody advanced).  reset() starts a new series."""
         if self._flag_layout is None:
             self._flag_layout = chunks
         elif self._flag_layout != chunks:
-            raise RuntimeError("whole-row steps and chunked host steps keep different step words: reset() between them")
+            raise RuntimeError("fused steps, chunked host steps and stock steps keep different step words: "
+                               "reset() between them")
 
     # ---- the fused step ----------------------------------------------------------------
     def step(self, steps: int = 1) -> None:
@@ -198,6 +206,7 @@ class HaloStencil:
         (allreduce-mpi-sycl.cpp:176-181).  Numerically the same time series as ``step`` (the transfers fill the
         halo buffers the next kernel reads)."""
         C, pads = self.C, self.pads
+        self._use_layout(0)
         stream = torch.cuda.current_stream(self.device)
         st = stream.cuda_stream
         out = (self.g + 1) & 1

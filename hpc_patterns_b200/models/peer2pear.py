@@ -272,11 +272,15 @@ class P2PResult:
 class P2PBench:
     """Pairwise GPU<->GPU bandwidth, device-timed, max over ranks, min over iterations."""
 
-    TRANSPORTS = ("put", "get", "sendrecv", "memcpy", "nccl")
+    TRANSPORTS = ("put", "get", "hybrid", "sendrecv", "memcpy", "nccl")
 
     def __init__(self, comm: Comm, device: int, max_bytes: int = REFERENCE_MESSAGE_BYTES,
                  transport: str = "put", engine: str = "ldst", tune: Optional[dict] = None,
-                 iters: int = 10, label: str = "Tile2Tile", timeout_s: float = 30.0):
+                 iters: int = 10, label: str = "Tile2Tile", timeout_s: float = 30.0, put_fraction: float = 0.5):
+        """``hybrid``: every message is driven from BOTH ends at once — the sender puts the first ``put_fraction`` of it
+        (peer stores) while the receiver gets the rest (peer loads), two kernels on two GPUs working on one direction of
+        the link.  SM-issued stores and SM-issued loads saturate at different rates below the link's (BASELINE.md §4.1);
+        together they can fill what either leaves."""
         if transport not in self.TRANSPORTS:
             raise ValueError(f"transport must be one of {self.TRANSPORTS}")
         if comm.world < 2 or comm.world % 2:
@@ -294,6 +298,8 @@ class P2PBench:
         self.epoch = 0
         self.partner = self.rank ^ 1
         self.launches = 0
+        self.put_fraction = float(put_fraction)
+        self._side = torch.cuda.Stream(device) if transport == "hybrid" else None
 
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -314,6 +320,31 @@ class P2PBench:
                 ops.append(dist.P2POp(dist.irecv, self.recv.tensor()[:nbytes], recvs_from))
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
+            return
+        if tr == "hybrid":
+            split = int(nbytes * self.put_fraction) // 16 * 16
+            main = torch.cuda.current_stream(self.device)
+            if sends_to >= 0 and split > 0:          # my half of the outgoing message: peer stores
+                sync = pads.sync_ops(signal_rank=sends_to, signal_section=C.PAD_DONE, epoch=ep)
+                pads.advance_tickets(C.copy(self.recv.ptrs[sends_to], self.send.local_ptr, split, False, self.engine,
+                                            self.tune, sync, self.device, st))
+                self.launches += 1
+            if recvs_from >= 0 and split < nbytes:   # the other half of the incoming message: peer loads, side stream
+                self._side.wait_stream(main)
+                sync = pads.sync_ops(signal_rank=recvs_from, signal_section=C.PAD_ACK, epoch=ep)
+                sync["ticket"] = pads.word(me, C.PAD_LOCAL + 1)          # second ticket counter: concurrent kernel
+                sync["ticket_base"] = getattr(self, "_side_tickets", 0) & 0xFFFFFFFF
+                ctas = C.copy(self.recv.local_ptr + split, self.send.ptrs[recvs_from] + split, nbytes - split, True,
+                              self.engine, self.tune, sync, self.device, self._side.cuda_stream)
+                self._side_tickets = getattr(self, "_side_tickets", 0) + ctas
+                main.wait_stream(self._side)
+                self.launches += 1
+            if recvs_from >= 0 and split > 0:
+                C.wait(pads.word(me, C.PAD_DONE + recvs_from), ep, pads.timeout_ns, pads.status_ptr, st)
+                self.launches += 1
+            if sends_to >= 0 and split < nbytes:     # owner: my buffer is free once the reader is done
+                C.wait(pads.word(me, C.PAD_ACK + sends_to), ep, pads.timeout_ns, pads.status_ptr, st)
+                self.launches += 1
             return
         if tr == "sendrecv" and recvs_from >= 0:
             C.signal(pads.word(recvs_from, C.PAD_READY + me), ep, st)

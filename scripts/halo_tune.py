@@ -24,7 +24,7 @@ from hpc_patterns_b200.utils.timing import BlockTimer  # noqa: E402
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/halo_tune.jsonl")
-    ap.add_argument("--rows", type=int, nargs="+", default=[7])
+    ap.add_argument("--rows", type=int, nargs="+", default=[8])
     ap.add_argument("--modes", nargs="+", default=["pull", "push"])
     ap.add_argument("--geometry", nargs="+", default=["16x12", "16x8", "8x12", "8x24", "32x6", "8x13", "16x6", "4x24"],
                     help="tile_kb x stages")

@@ -15,7 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--world", type=int, default=1)
 ap.add_argument("--devices", type=int, nargs="*", default=None)
 ap.add_argument("--mode", default="pull")
-ap.add_argument("--rows", type=int, default=7)
+ap.add_argument("--rows", type=int, default=8)
 ap.add_argument("--bytes", type=int, default=32 << 20)
 ap.add_argument("--steps", type=int, default=3)
 args = ap.parse_args()

@@ -24,6 +24,7 @@ def main() -> int:
     ap.add_argument("--bytes", type=int, default=REFERENCE_MESSAGE_BYTES)
     ap.add_argument("--iters", type=int, default=6)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--hybrid", action="store_true", help="only the put+get-at-once transport, over the split fraction")
     args = ap.parse_args()
     comm = Comm()
     dev = comm.device
@@ -38,11 +39,19 @@ def main() -> int:
             if args.quick and not (c == 296 and thr == 512):
                 continue
             points.append((transport, "ldst", {"ctas": c, "unroll": u, "vec_bytes": vec, "threads": thr}))
+    if args.hybrid:
+        points = [("memcpy", "ldst", {})]
+        for frac in (0.3, 0.4, 0.5, 0.6, 0.7):
+            for engine in ("tma", "ldst"):
+                points.append(("hybrid", engine, {"put_fraction": frac}))
     rows = []
     for transport, engine, tune in points:
+        tune = dict(tune)
+        frac = tune.pop("put_fraction", 0.5)
         try:
             b = P2PBench(comm, dev, max_bytes=args.bytes, transport=transport, engine=engine, tune=tune,
-                         iters=args.iters)
+                         iters=args.iters, put_fraction=frac)
+            tune["put_fraction"] = frac if transport == "hybrid" else None
             r = b.run(args.bytes, verify=True)
             b.close()
         except Exception as e:

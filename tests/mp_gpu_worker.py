@@ -32,9 +32,11 @@ def main():
             hs.reset()
             for how in ("memcpy", "nccl"):
                 hs.stock_step(how)
-            hs.step(2)
             torch.cuda.synchronize()
             assert hs.verify_from_init() == 0, (mode, rows, "stock")
+            comm.barrier()
+            assert hs.verify_last_step() == 0, (mode, rows, "stock")
+            comm.barrier()
             if mode == "push":
                 hs.reset()
                 bufs = hs.make_host_buffers()

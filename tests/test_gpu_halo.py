@@ -84,9 +84,13 @@ def test_stock_arm_computes_the_same_time_series(native, how):
         for _ in range(3):
             hs.stock_step(how)
         torch.cuda.synchronize()
-        assert hs.verify_from_init() == 0
-        hs.step(2)                                      # fused steps continue from the stock steps' state
+        assert hs.verify_from_init() == 0 and hs.verify_last_step() == 0
+        with pytest.raises(RuntimeError, match="reset"):
+            hs.step(1)                                  # stock steps never advance the step words of the fused kernel
+        hs.reset()
+        hs.step(2)
         torch.cuda.synchronize()
+        hs.check()
         assert hs.verify_from_init() == 0
     finally:
         hs.close()

@@ -16,10 +16,11 @@ def test_balanced_rows_rule():
     from hpc_patterns_b200.models.halo import balanced_rows
 
     # pull mode: (2R + 2) rows through HBM vs 2 rows per direction over NVLink
-    r = balanced_rows(6567.4, 770.0)
-    assert r == 7
+    assert balanced_rows(6567.4, 770.0) == 7          # one direction busy
+    r = balanced_rows()                               # both directions busy (what a neighbour exchange gets): default
+    assert r == 8
     hbm = (2 * r + 2) / 6567.4
-    nvl = 2 / 770.0
+    nvl = 2 / 706.1
     assert abs(hbm - nvl) / nvl < 0.1
     assert balanced_rows(100.0, 1000.0) == 1            # never below one row
 
