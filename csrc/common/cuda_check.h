@@ -9,6 +9,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -50,6 +51,15 @@ inline void enable_dynamic_smem(Kernel kernel, size_t bytes, const char* file, i
                                   static_cast<int>(cudaSharedmemCarveoutMaxShared)),
              "cudaFuncSetAttribute(PreferredSharedMemoryCarveout)", file, line);
 }
+
+// Call FIRST in main(), before any CUDA call.  CUDA >= 12.2 loads kernels lazily: the first launch of a kernel loads
+// its module, and that load cannot complete while another kernel is running on the device.  This suite runs kernels
+// that spin on words a peer's kernel will write; when two ranks share a GPU (more ranks than devices) the peer's
+// FIRST launch of e.g. `signal_kernel` then waits for the spinning kernel, which waits for that signal: a deadlock
+// that only the 30 s device-side deadline breaks (found in round 2: every >= 3-ranks-per-GPU run and the
+// rendezvous / copy-engine transports of peer2pear on one GPU timed out; profiles/r2_call2_1gpu/virtual_ranks_diag.txt).
+// Eager loading makes every kernel resident at start-up.  An explicit user setting wins.
+inline void prefer_eager_module_loading() { (void)setenv("CUDA_MODULE_LOADING", "EAGER", /*overwrite=*/0); }
 
 }  // namespace hpcp
 

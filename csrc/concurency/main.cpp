@@ -17,6 +17,9 @@
 #include "driver.hpp"
 
 int main(int argc, char** argv) {
+  // CUDA backend: load every kernel at start-up — a first launch next to a running kernel would wait for it
+  // (lazy module loading; see csrc/common/cuda_check.h::prefer_eager_module_loading).  Harmless for the CPU backend.
+  (void)setenv("CUDA_MODULE_LOADING", "EAGER", /*overwrite=*/0);
   using namespace hpcp::con;
   std::vector<std::string> args(argv + 1, argv + argc);
 

@@ -22,6 +22,7 @@ __global__ void write_value(int* p, int n, int value) {
 }
 
 int main() {
+  hpcp::prefer_eager_module_loading();  // spin-waiting kernels + lazy module loading can deadlock (cuda_check.h)
   using namespace hpcp;
   try {
     int ndev = 0;

@@ -56,6 +56,7 @@ struct Runtime {
 }  // namespace foreign
 
 int main() {
+  hpcp::prefer_eager_module_loading();  // spin-waiting kernels + lazy module loading can deadlock (cuda_check.h)
   try {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {

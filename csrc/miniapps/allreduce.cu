@@ -407,6 +407,7 @@ int run_on_host(const Config& cfg) {
 }  // namespace
 
 int main(int argc, char** argv) {
+  hpcp::prefer_eager_module_loading();  // spin-waiting kernels + lazy module loading can deadlock (cuda_check.h)
   try {
     Shared sh;
     Config& cfg = sh.cfg;

@@ -196,6 +196,7 @@ void rank_main(RankCtx& ctx, Shared& sh) {
 }  // namespace
 
 int main(int argc, char** argv) {
+  hpcp::prefer_eager_module_loading();  // spin-waiting kernels + lazy module loading can deadlock (cuda_check.h)
   try {
     Config cfg;
     static const option long_opts[] = {{"rows", required_argument, nullptr, 1},   {"bytes", required_argument, nullptr, 2},

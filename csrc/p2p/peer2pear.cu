@@ -428,6 +428,7 @@ int run_on_host(const Config& cfg) {
 }  // namespace
 
 int main(int argc, char** argv) {
+  hpcp::prefer_eager_module_loading();  // spin-waiting kernels + lazy module loading can deadlock (cuda_check.h)
   try {
     Config cfg = parse(argc, argv);
     if (cfg.cpu) return run_on_host(cfg);
@@ -456,6 +457,15 @@ int main(int argc, char** argv) {
     std::vector<int> devices;
     for (int r = 0; r < cfg.ranks; ++r)
       devices.push_back(topo::device_for_rank(cfg.mapping, r, ndev, planes) % ndev);
+
+    // Ranks that share a GPU (more ranks than devices) must leave each other room: a copy kernel that waits in its
+    // prologue for the peer's "receive posted" word holds its SM slots while the peer's signal kernel needs one on the
+    // SAME GPU.  Half a wave of CTAs per sharing rank keeps registers and thread slots free.
+    int ranks_per_dev = 1;
+    for (int d = 0; d < ndev; ++d)
+      ranks_per_dev = std::max<int>(ranks_per_dev, static_cast<int>(std::count(devices.begin(), devices.end(), d)));
+    if (ranks_per_dev > 1 && cfg.tune.ctas == 0)
+      cfg.tune.ctas = std::max(1, device_sm_count(devices[0]) / ranks_per_dev);
 
     NodeMemory mem(devices);
     Shared sh;

@@ -16,6 +16,14 @@ Layout
 """
 from __future__ import annotations
 
+import os as _os
+
+# Kernels of this suite spin on words a peer's kernel will write.  CUDA's lazy module loading cannot finish loading a
+# kernel while another kernel runs on the device, so the FIRST launch of a kernel next to a spinning one deadlocks until
+# the device-side deadline (csrc/common/cuda_check.h::prefer_eager_module_loading).  Must be set before the CUDA
+# context exists; an explicit user setting wins.
+_os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 __version__ = "0.1.0"
 
 _ext = None

@@ -58,11 +58,11 @@ def main():
                "gemm_tflops": flops / t_ours / 1e9, "gemm_tflops_no_cluster": flops / t_single / 1e9,
                "cublas_ms": t_cublas, "cublas_tflops": flops / t_cublas / 1e9,
                "max_abs_diff_vs_cublas": float((c.float() - c_ref.float()).abs().max())}
-        if os.environ.get("HPCP_EXPERIMENTAL"):  # TMA-store epilogue (UTMASTG), opt-in until validated
+        if True:  # TMA-store epilogue (UTMASTG)
             t_tma = timed(lambda: gemm_put(a, b, c, 0, out_dtype=torch.bfloat16, epilogue="tma"), comm, dev)
             row["gemm_tflops_tma_epilogue"] = flops / t_tma / 1e9
             row["max_abs_diff_tma_epilogue_vs_cublas"] = float((c.float() - c_ref.float()).abs().max())
-        if os.environ.get("HPCP_EXPERIMENTAL"):  # 2-SM UMMA variant (cta_group::2), opt-in until validated
+        if True:  # 2-SM UMMA variant (cta_group::2)
             t_2sm = timed(lambda: gemm_put(a, b, c, 0, out_dtype=torch.bfloat16, cluster=3), comm, dev)
             row["gemm_tflops_2sm"] = flops / t_2sm / 1e9
             t_2sm_tma = timed(lambda: gemm_put(a, b, c, 0, out_dtype=torch.bfloat16, cluster=3, epilogue="tma"), comm, dev)

@@ -1,11 +1,10 @@
 """GPU tests of the two GEMM kernels that carry their collective (csrc/kernels/gemm_collective.cu).
 
-Written on a machine without a GPU and NOT RUN YET: opt-in (``HPCP_EXPERIMENTAL=1``) so that an unvalidated kernel
-cannot stop the regular suite; run them under ``timeout``.  One-GPU tests emulate P ranks with P launches on the
+First run on a B200 in round 2 (profiles/r2_call2_1gpu/pytest_gemm_collective.txt: 60 passed), part of the regular
+GPU suite since.  One-GPU tests emulate P ranks with P launches on the
 same device ("virtual ranks": every rank's shard / row block is a separate buffer, peer pointers are plain local
 pointers), which exercises the whole tile order, ownership, gather and signalling logic without NVLink.
-``cluster=3`` cases run the same policies on the 2-SM UMMA tile loop (``tcgen05.mma.cta_group::2``), itself not yet
-validated: run ``-k "not 3]"``-style selections first if it fails (scripts/gpu_next_round.sh does).
+``cluster=3`` cases run the same policies on the 2-SM UMMA tile loop (``tcgen05.mma.cta_group::2``).
 """
 import os
 import subprocess
@@ -14,8 +13,7 @@ import sys
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("HPCP_EXPERIMENTAL"), reason="experimental path, opt-in")]
+pytestmark = [pytest.mark.gpu]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 

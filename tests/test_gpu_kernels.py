@@ -417,7 +417,6 @@ def test_gemm_put_signal_and_few_ctas(native, dev):
     assert torch.equal(c_peer, gemm_reference(a, b))
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("HPCP_EXPERIMENTAL"), reason="experimental path, opt-in")
 @pytest.mark.parametrize("m,n,k", [(256, 256, 64), (256, 512, 256), (1024, 1024, 512), (2048, 2048, 1024),
                                    (512, 768, 4096), (8192, 8192, 512)])
 def test_gemm_put_2sm_umma(native, dev, m, n, k):
@@ -442,7 +441,6 @@ def test_gemm_put_2sm_umma(native, dev, m, n, k):
     assert torch.equal(c_bf, ref.to(torch.bfloat16))
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("HPCP_EXPERIMENTAL"), reason="experimental path, opt-in")
 @pytest.mark.parametrize("ratio", [1, 3])
 def test_triad_put_tma_l2_hint(native, dev, ratio):
     """EXPERIMENTAL (not yet run): L2 evict_first cache-policy operands on the TMA engine's streamed copies."""
@@ -459,7 +457,6 @@ def test_triad_put_tma_l2_hint(native, dev, ratio):
     assert torch.equal(peer[:n_put], a[:n_put]) and bool((peer[n_put:] == -7.0).all())
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("HPCP_EXPERIMENTAL"), reason="experimental path, opt-in")
 @pytest.mark.parametrize("halo_ctas", [8, 48, 147])
 def test_triad_put_halo_split_scheduling(native, dev, halo_ctas):
     """EXPERIMENTAL: dedicated halo CTAs instead of interleaved halo/interior tiles (TMA engine)."""

@@ -86,10 +86,7 @@ def test_cli_allreduce_oversubscribed(bin_dir):
 
 
 def _ring_rank_counts():
-    """Rank counts for the ring-variant tests: never more than two thread-ranks per GPU (three and more time out in the
-    host-synchronised parts of the CLIs on a shared GPU — profiles/r2_call2_1gpu/virtual_ranks_diag.txt)."""
-    g = _ngpu()
-    return [n for n in (2, 4, 6) if n <= 2 * g]
+    return [2, 4, 6]
 
 
 @needs2
@@ -157,11 +154,10 @@ def test_bench_one_gpu():
 # ---- the same native programs with MORE RANKS THAN GPUS (oversubscription, as the reference's devices.hpp:46-47 deals
 # ranks round-robin): on a 1-GPU box every "peer" is the GPU itself, so epochs, tickets, acks and timeouts of the
 # cross-GPU protocols are exercised without NVLink.  These run on ANY GPU count.
-# Known limit (profiles/r2_call2_1gpu/virtual_ranks_diag.txt): on ONE GPU the rendezvous / copy-engine transports of
-# peer2pear and every program with three or more thread-ranks per GPU time out in their host-synchronised sections
-# (a full-GPU kernel waiting in its prologue leaves no SM slot for the peer's signal kernel; cause of the >= 3-rank case
-# not found).  The cases below are the ones that work and run on any box; the others run with >= 2 GPUs above.
-@pytest.mark.parametrize("transport", ["put", "get"])
+# (Round 2, first attempt: sendrecv / memcpy and every run with >= 3 ranks per GPU timed out — the FIRST launch of a
+# kernel next to a spinning one waited for CUDA's lazy module load, which waits for the device to drain.  The programs
+# now ask for eager loading; csrc/common/cuda_check.h::prefer_eager_module_loading.)
+@pytest.mark.parametrize("transport", ["put", "get", "sendrecv", "memcpy"])
 def test_cli_peer2pear_virtual_ranks(bin_dir, transport):
     rc, out, err = _run([os.path.join(bin_dir, "peer2pear"), "v", "-n", "2", "--transport", transport,
                          "--bytes", str(4 << 20), "--bytes", "1024", "--iters", "3"],
@@ -174,7 +170,7 @@ def test_cli_peer2pear_virtual_ranks(bin_dir, transport):
                                   ["-a", "--coll", "twoshot", "--type", "int"], ["--type", "double"], ["--type", "long"],
                                   ["--type", "short"], ["--type", "uchar"], ["-a", "--type", "double"],
                                   ["-a", "--type", "ushort"], ["--type", "ulong", "--algo", "ring-unfused"]])
-@pytest.mark.parametrize("n", [2])
+@pytest.mark.parametrize("n", [2, 4])
 def test_cli_allreduce_virtual_ranks(bin_dir, args, n):
     rc, out, err = _run([os.path.join(bin_dir, "allreduce"), "-n", str(n), "-p", "18", "--iters", "2"] + args,
                         env={"CUDA_VISIBLE_DEVICES": "0"}, timeout=180)
@@ -187,8 +183,6 @@ def test_cli_allreduce_virtual_ranks(bin_dir, args, n):
 def test_cli_halo_virtual_ranks(bin_dir, args, n):
     """The native flagship CLI with more ranks than GPUs: the persistent kernels of all ranks share one GPU and spin
     on each other's step words (grids are sized for co-residency)."""
-    if n > 2 and "--stock" in args:
-        pytest.skip("host-synchronised steps with > 2 thread-ranks on one GPU: known limit, see above")
     rc, out, err = _run([os.path.join(bin_dir, "halo"), "-n", str(n), "--bytes", str((4 << 20) + 4096), "--rows", "3",
                          "--steps", "5", "--iters", "2"] + args, env={"CUDA_VISIBLE_DEVICES": "0"}, timeout=180)
     assert rc == 0, out + err
