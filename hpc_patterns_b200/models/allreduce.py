@@ -292,7 +292,7 @@ def main(argv: Optional[List[str]] = None) -> int:
     ap = argparse.ArgumentParser(prog="allreduce", add_help=True)
     ap.add_argument("-a", action="store_true", help="use the one-launch collective (nvls, else twoshot)")
     ap.add_argument("-p", type=int, default=25, help="2^p elements (default 25)")
-    ap.add_argument("--type", default="float", choices=("float", "int"))
+    ap.add_argument("--type", default="float", choices=sorted(_TORCH_DTYPE))
     ap.add_argument("--algo", default="ring", choices=ALGOS)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=1)
