@@ -655,13 +655,16 @@ int launch_allreduce_nvls(const NvlsArgs& args, ElemType type, int ctas, int dev
   d.barrier_epoch = args.barrier_epoch;
   d.timeout_ns = args.timeout_ns;
   d.status = args.status;
-  // Tuning knobs for sweeps (defaults = the measured configuration: 4 in flight, 512 threads, one CTA per SM):
+  // Tuning knobs for sweeps (defaults = the measured configuration: 4 in flight, 512 threads, 32 CTAs):
   //   HPCP_NVLS_UNROLL=1|2|4|8   HPCP_NVLS_THREADS=256|512|1024   HPCP_NVLS_CTAS_PER_SM=k   (or --ctas / ctas>0)
   static const int unroll = env_choice("HPCP_NVLS_UNROLL", {1, 2, 4, 8}, 4);
   static const int threads = env_choice("HPCP_NVLS_THREADS", {256, 512, 1024}, 512);
-  static const int per_sm = env_choice("HPCP_NVLS_CTAS_PER_SM", {1, 2, 3, 4}, 1);
+  static const int per_sm = env_choice("HPCP_NVLS_CTAS_PER_SM", {0, 1, 2, 3, 4}, 0);
   const int sms = device_sm_count(device);
-  const int grid = grid_for(std::max<size_t>(d.slice_vec, 1), threads, ctas > 0 ? ctas : sms * per_sm);
+  // Default grid: 32 CTAs.  The in-switch reduction saturates at modest request parallelism and more requesters only
+  // queue in the switch: 8xB200, 2^25 floats 0.297 ms @32 CTAs vs 0.325 @148 vs 0.349 @296; 2^28 floats 2.23 ms @32 vs
+  // 3.41 @148 (NCCL: 0.431 / 2.907 ms) — profiles/r2_call4_8gpu/nvls_tune.txt.  HPCP_NVLS_CTAS_PER_SM / --ctas override.
+  const int grid = grid_for(std::max<size_t>(d.slice_vec, 1), threads, ctas > 0 ? ctas : per_sm > 0 ? sms * per_sm : 32);
   d.ticket_target = args.ticket_base + static_cast<uint32_t>(grid);
 #define HPCP_NVLS(U, B)                                             \
   do {                                                              \

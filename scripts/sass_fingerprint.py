@@ -24,11 +24,15 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MANIFEST = os.path.join(ROOT, "docs", "sass", "VALIDATED.sha256")
-# demangled-name patterns of kernels written after the last GPU call (opt-in paths, GPU tests behind HPCP_EXPERIMENTAL)
+# demangled-name patterns of instantiations that have NOT run on a GPU (everything else ran in round 2:
+# profiles/r2_call2_1gpu .. r2_call5_1gpu; the experimental gates of round 1 are gone)
 UNVALIDATED = (
-    r"gemm_put_2sm", r"gemm_put_tma_kernel", r"gemm_put_policy_kernel", r"gemm_reduce_scatter", r"gemm_allreduce", r"gemm_all_to_all",
-    r"allgather_gemm", r"wait_flags_kernel", r"ring_allreduce_kernel<\w+, true>", r"ring_pull_kernel", r"triad_put_tma_kernel<\w+, true>",
-    r"nvls_kernel<\w+, (1|2|8), \d+>", r"nvls_kernel<\w+, \d+, 1024>",
+    r"gemm_put_policy_kernel",                                            # only behind HPCP_GEMM_PUT_TEMPLATE=1
+    r"ring_pull_kernel<(double|long long|short|unsigned char)",           # pull / two-slot rings ran for float and int
+    r"ring_allreduce_kernel<(double|long long|short|unsigned char), true>",
+    r"two_shot_kernel<[\w ]+, 16, 1>",                                    # more than 8 ranks
+    r"two_shot_kernel<(long long|unsigned char), ", r"two_shot_kernel<short, 8, ",
+    r"nvls_kernel<\w+, (1|2), \d+>", r"nvls_kernel<\w+, \d+, 1024>", r"nvls_kernel<int, ",
 )
 
 

@@ -15,6 +15,7 @@ from hpc_patterns_b200.ops import gemm as real_ops
 class FakeComm:
     def __init__(self, rank, world):
         self.rank, self.world, self.local_rank = rank, world, rank
+        self.device = 0          # Comm.device: the ordinal the rank->device mapping chose
 
 
 class FakeSymmetricBuffer:
