@@ -141,6 +141,25 @@ def test_bench_two_gpus():
     assert d["e2e"]["wrong_words"] == 0 and d["stock"]["wrong_words"] == 0
 
 
+def _bench_ms(n, steps, port):
+    args = [os.path.join(ROOT, "bench.py"), "--gpus", str(n), "--steps", str(steps), "--warmup", "5", "--no-extras",
+            "--e2e-steps", "1", "--blocks", "3"]
+    rc, out, err = _torchrun(n, args, timeout=300, port=port) if n > 1 else _run([sys.executable] + args, timeout=300)
+    assert rc == 0, out[-2000:] + err[-2000:]
+    d = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+    assert d["wrong_words"] == 0 and d["steps"] == steps
+    return d["ms_per_step"]
+
+
+def test_short_blocks_measure_what_long_runs_measure():
+    """The driver times 20 steps; a number that only holds for 200-step runs is not a number (round 1: 26 % apart).
+    With the device-side barrier in front of the start event and the pre-heat, 20-step blocks and a 200-step run
+    must agree within 10 % — on every GPU count this box has, up to 2."""
+    n = 2 if _ngpu() >= 2 else 1
+    short, long = _bench_ms(n, 20, 29621), _bench_ms(n, 200, 29622)
+    assert abs(short - long) / long < 0.10, (short, long)
+
+
 def test_bench_one_gpu():
     rc, out, err = _run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "5", "--warmup", "3",
                          "--e2e-steps", "2", "--preheat-ms", "50"])
