@@ -139,7 +139,8 @@ def main() -> int:
                           warmup=lambda: hs.step(W))
     if sampler is not None:
         sampler.pause()
-    gpu_launches_per_block = 2          # the stencil launch + the in-kernel barrier in front of the start event
+    gpu_launches_per_block = 1          # ONE persistent K-halo launch runs all K steps of a timed block (the in-kernel
+                                        # barrier is enqueued before the start event, i.e. outside the region)
     total_fused_launches = hs.launches - launches0
     wrong_last = int(comm.sum(hs.verify_last_step()))
     ms_per_step = fused["ms"]
@@ -287,6 +288,8 @@ def main() -> int:
                             "NVLink exchange, and the WHOLE new slab is downloaded, every step",
                     "api": "hpc_patterns_b200.models.halo.HaloStencil.step_from_host"},
             "gpu_launches": gpu_launches_per_block, "gpu_launches_all_blocks": total_fused_launches,
+            "gpu_launches_note": "halo_stencil_kernel<pull|push>: K steps per launch (config.steps_per_launch); "
+                                 "one_launch_per_step_ms is the same kernel launched K times",
             "wrong_words": wrong_init + wrong_last,
             "per_gpu_per_direction_GBps": round(per_gpu_dir, 1),
             "frac_of_nvlink_706_measured_bidirectional": round(per_gpu_dir / NVLINK_BIDIR_GBS_MEASURED, 3) if world > 1 else None,

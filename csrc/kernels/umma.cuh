@@ -143,7 +143,9 @@ __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity
                                                   int index) {
   for (unsigned long long spins = 0;; ++spins) {
     uint32_t ok;
-    if (cluster_scope)  // arrivals may come from the other CTA of the pair
+    if (cluster_scope)  // cluster-scope acquire: costs an L1 invalidate (CCTL.IVALL) per successful wait — not used by
+                        // the tile loops (a cta-scope wait observes remote arrivals too; what they order is TMA / TMEM
+                        // traffic, fenced by tcgen05.fence / the async proxy, not generic-proxy data in L1)
       asm volatile(
           "{\n\t.reg .pred p;\n\t"
           "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
@@ -615,7 +617,12 @@ __device__ __forceinline__ void gemm_persistent_2sm(const CUtensorMap& map_a, co
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     for (int s = 0; s < kStages2; ++s) {
-      ptx::mbar_init(&full_bar[s], 2);
+      // ONE arrival per phase: the leader's arrive.expect_tx for the bytes of BOTH CTAs.  The partner's TMA loads signal
+      // this barrier directly (cta_group::2 complete_tx); a per-stage remote arrive from the partner costs a
+      // cluster-scope release (MEMBAR.ALL.GPU) per k-block and paced the whole loop at 30 % tensor activity
+      // (profiles/r2_call6_1gpu/prof_gemm_2sm).  Early complete_tx bytes only drive the tx-count negative until the
+      // leader's expect_tx arrives; the phase cannot complete before that arrival.
+      ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -654,7 +661,6 @@ __device__ __forceinline__ void gemm_persistent_2sm(const CUtensorMap& map_a, co
           if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes2);
           tma_load_2d_2sm(sa, &map_a, kb * kBK, m0, &full_bar[stage]);
           tma_load_2d_2sm(sa + kABytes, &map_b, kb * kBK, n0, &full_bar[stage]);
-          if (!leader) mbar_arrive_cluster(&full_bar[stage], 0);
         }
         __syncwarp();
         if (++stage == kStages2) {
@@ -672,11 +678,11 @@ __device__ __forceinline__ void gemm_persistent_2sm(const CUtensorMap& map_a, co
     for (int item = first_item; item < num_items; item += item_stride, ++local_tile) {
       const int acc = local_tile & 1;
       const uint32_t acc_phase = static_cast<uint32_t>(local_tile >> 1) & 1;
-      mbar_wait_or_trap(&tmem_empty_bar[acc], acc_phase ^ 1, true, kWaitTmemEmpty, acc);  // both epilogues drained it
+      mbar_wait_or_trap(&tmem_empty_bar[acc], acc_phase ^ 1, false, kWaitTmemEmpty, acc);  // both epilogues drained it
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kBN);
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait_or_trap(&full_bar[stage], phase, true, kWaitFull, stage);  // both CTAs' TMA bytes landed
+        mbar_wait_or_trap(&full_bar[stage], phase, false, kWaitFull, stage);  // both CTAs' TMA bytes landed
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = ptx::smem_u32(smem + static_cast<size_t>(stage) * kStageBytes2);

@@ -161,3 +161,19 @@ def test_pull_mode_refuses_host_steps(native):
             hs.step_from_host(b[0], b[1])
     finally:
         hs.close()
+
+
+@pytest.mark.parametrize("rows,row_elems,tune", [(1, 1024, SMALL), (3, 5 * 1024 + 4, SMALL), (8, 1 << 20, None),
+                                                 (2, (3 << 20) + 12, {"tile_kb": 32, "stages": 6})])
+def test_stencil_step_op_matches_torch_fp32(native, rows, row_elems, tune):
+    """The compute half alone, as an op on tensors, against the plain PyTorch fp32 expression (bit-exact)."""
+    from hpc_patterns_b200.ops.halo import stencil_step, stencil_step_reference
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    u = torch.randn(rows, row_elems, device="cuda", generator=g)
+    lo = torch.randn(row_elems, device="cuda", generator=g)
+    hi = torch.randn(row_elems, device="cuda", generator=g)
+    for alpha, s in ((0.5, 0.25), (0.3, 0.7)):          # the second pair rounds in every operation
+        got = stencil_step(u, lo, hi, alpha=alpha, s=s, tune=tune)
+        torch.cuda.synchronize()
+        assert torch.equal(got, stencil_step_reference(u, lo, hi, alpha, s))
