@@ -48,7 +48,7 @@ struct Config {
   std::string label = "Tile2Tile";
   int ranks = 0;  // 0 -> all GPUs (rounded down to even)
   std::string transport = "put";
-  std::string engine = "ldst";
+  std::string engine = "tma";   // measured best for both put (683 vs 675 GB/s) and get (731 vs 726), BASELINE.md 5.2
   std::string mapping = "compact";
   std::vector<size_t> sizes;
   bool sweep = false;
@@ -73,7 +73,7 @@ void usage() {
          "        get      one-sided: kernel loads from the peer\n"
          "        sendrecv two-sided rendezvous: receiver posts, sender waits+puts (Isend/Irecv)\n"
          "        memcpy   cudaMemcpyPeerAsync copy-engine baseline\n"
-         "  --engine ldst|tma        128-bit ld/st from all threads, or TMA bulk copies\n"
+         "  --engine tma|ldst        TMA bulk copies through an smem ring (default), or 128-bit ld/st from all threads\n"
          "  --bytes B                message size (default 188743680, the reference size)\n"
          "  --sweep                  1 KiB .. 1 GiB in powers of two plus the reference size\n"
          "  --iters N                timed iterations, minimum reported (default 10)\n"

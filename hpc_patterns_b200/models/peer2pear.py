@@ -275,7 +275,7 @@ class P2PBench:
     TRANSPORTS = ("put", "get", "hybrid", "sendrecv", "memcpy", "nccl")
 
     def __init__(self, comm: Comm, device: int, max_bytes: int = REFERENCE_MESSAGE_BYTES,
-                 transport: str = "put", engine: str = "ldst", tune: Optional[dict] = None,
+                 transport: str = "put", engine: str = "tma", tune: Optional[dict] = None,
                  iters: int = 10, label: str = "Tile2Tile", timeout_s: float = 30.0, put_fraction: float = 0.5):
         """``hybrid``: every message is driven from BOTH ends at once — the sender puts the first ``put_fraction`` of it
         (peer stores) while the receiver gets the rest (peer loads), two kernels on two GPUs working on one direction of
@@ -435,7 +435,7 @@ def main(argv: Optional[List[str]] = None) -> int:
     ap = argparse.ArgumentParser(prog="peer2pear")
     ap.add_argument("label", nargs="?", default="Tile2Tile")
     ap.add_argument("--transport", default="put", choices=P2PBench.TRANSPORTS)
-    ap.add_argument("--engine", default="ldst", choices=("ldst", "tma"))
+    ap.add_argument("--engine", default="tma", choices=("ldst", "tma"))
     ap.add_argument("--bytes", type=int, action="append")
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--iters", type=int, default=10)
