@@ -1,4 +1,5 @@
-// K-fused-triad-put: the suite's flagship fused compute + communication kernel.
+// K-fused-triad-put: fused compute + one-directional ring put (round 1's flagship; K-halo in halo_stencil.cu, where
+// every step consumes what the neighbours produced, is the flagship since round 2).
 //
 // The reference never overlaps compute with communication: its miniapp runs
 // "kernel; wait; MPI_Send/Recv; wait" (allreduce-mpi-sycl.cpp:176-181, whose

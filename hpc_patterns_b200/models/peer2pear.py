@@ -1,4 +1,5 @@
-"""peer2pear for one-process-per-GPU runs (torchrun), and the flagship fused exchange.
+"""peer2pear for one-process-per-GPU runs (torchrun), and round 1's flagship fused exchange (the flagship since
+round 2 is the halo exchange of models/halo.py).
 
 Two public classes:
 
@@ -8,7 +9,7 @@ Two public classes:
                         ``put`` (↔ MPI_Put+fence), ``get``, ``sendrecv`` (↔ Isend/Irecv),
                         plus the stock baselines ``memcpy`` (cudaMemcpyPeerAsync) and
                         ``nccl`` (torch.distributed send/recv).
-``FusedTriadExchange``  the headline op of this suite: every rank computes the stream
+``FusedTriadExchange``  round 1's headline op: every rank computes the stream
                         triad ``a = b + s*c`` and puts ``a`` into its ring neighbour
                         in ONE kernel (csrc/kernels/fused_triad_put.cu); bench.py
                         measures it, the halo-exchange style loops use it.
