@@ -40,6 +40,8 @@
 #include "api.h"
 
 #include <algorithm>
+#include <mutex>
+#include <vector>
 
 #include "../common/cuda_check.h"
 #include "../common/signal.cuh"
@@ -343,9 +345,27 @@ struct HaloGeometry {
 
 template <int kMode>
 int occupancy_of(size_t smem) {
-  HPCP_ENABLE_SMEM(halo_stencil_kernel<kMode>, smem);
+  // One attribute + occupancy query per (mode, smem, device), not per launch (per-step launches come here K times).
+  // The dynamic shared-memory limit of the function is only ever RAISED: instances with different stage counts coexist.
+  struct Entry {
+    size_t smem;
+    int device, per_sm;
+  };
+  static std::mutex mu;
+  static std::vector<Entry> cache;
+  static size_t limit_set[64] = {0};
+  int device = 0;
+  HPCP_CUDA(cudaGetDevice(&device));
+  std::lock_guard<std::mutex> lk(mu);
+  if (device >= 0 && device < 64 && smem > limit_set[device]) {
+    HPCP_ENABLE_SMEM(halo_stencil_kernel<kMode>, smem);
+    limit_set[device] = smem;
+  }
+  for (const Entry& e : cache)
+    if (e.smem == smem && e.device == device) return e.per_sm;
   int per_sm = 0;
   HPCP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, halo_stencil_kernel<kMode>, kHaloThreads, smem));
+  cache.push_back({smem, device, per_sm});
   return per_sm;
 }
 
@@ -366,7 +386,7 @@ HaloGeometry halo_geometry(size_t row_bytes, const HaloTuning& tune, HaloMode mo
   }
   HPCP_REQUIRE(per_sm >= 1, "halo_stencil: kernel does not fit on an SM");
   const size_t tiles = (row_bytes + g.tile_bytes - 1) / g.tile_bytes;
-  const int resident = sms * per_sm;
+  const int resident = std::min(sms * per_sm, kHaloMaxCtas);  // one step word per CTA and side
   const int want = tune.ctas > 0 ? std::min(tune.ctas, resident) : resident;
   g.ctas = static_cast<int>(std::max<size_t>(1, std::min<size_t>(tiles, static_cast<size_t>(want))));
   HPCP_REQUIRE(g.ctas <= kHaloMaxCtas, "halo_stencil: more CTAs than flag words");
@@ -429,8 +449,7 @@ int launch_halo_stencil(const HaloStencilArgs& a, HaloMode mode, const HaloTunin
   // Flag words: one 32-byte sector per (flag set, side, CTA); the kernel adds blockIdx.x * kHaloFlagWords.
   const size_t set_words = static_cast<size_t>(a.flag_set) * 2 * kHaloMaxCtas * kHaloFlagWords;
   const size_t side_words = static_cast<size_t>(kHaloMaxCtas) * kHaloFlagWords;
-  auto launch = [&](auto kernel) {
-    HPCP_ENABLE_SMEM(kernel, g.smem);
+  auto launch = [&](auto kernel) {  // the shared-memory attribute was set when the geometry was computed
     kernel<<<ctas, kHaloThreads, g.smem, stream>>>(p);
   };
   if (mode != HaloMode::kNone) {
