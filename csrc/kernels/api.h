@@ -119,6 +119,7 @@ struct HaloTuning {
   int ctas = 0;     // 0 -> every resident CTA slot (SMs x occupancy); always clamped to it
   int tile_kb = 0;  // bytes of a row per shared-memory stage in KiB; 0 -> 16
   int stages = 0;   // shared-memory stages (>= 6); 0 -> 6 (two CTAs per SM with 16 KiB tiles)
+  int l2_hint = 0;  // 1: L2 evict_first policy on the streaming loads / stores of the slab's own rows
 };
 struct HaloStencilArgs {
   float* u[2] = {nullptr, nullptr};                 // local field, ping-pong: step g reads u[g&1], writes u[(g+1)&1]

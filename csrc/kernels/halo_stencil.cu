@@ -69,6 +69,7 @@ struct HaloParams {
   size_t tile_begin, tile_end;      // column tiles [begin, end) of a row handled by this launch
   uint32_t tile_bytes;
   int stages;
+  int l2_hint;                      // 1: L2 evict_first policy on the local streaming loads and stores (used once)
   float alpha, s;
   uint32_t step_base;
   int steps;
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(kHaloThreads) halo_stencil_kernel(const HaloPa
   if (warp == 0) {
     if (threadIdx.x != 0) return;
     // ------------------------------------------------------------------ DMA thread ----
+    const uint64_t policy = p.l2_hint ? ptx::l2_policy_evict_first() : 0;
     Ring ld{0, 0};    // next tile to load
     Ring st{0, 0};    // tile the next finished row overwrote (= the next one to store)
     Ring done{0, 0};  // next `computed` barrier to consume
@@ -177,7 +179,10 @@ __global__ void __launch_bounds__(kHaloThreads) halo_stencil_kernel(const HaloPa
                                    : m_l == R + 1 ? dn_src + off
                                                   : uin + static_cast<size_t>(m_l - 1) * p.row_bytes + off;
         ptx::mbar_arrive_expect_tx(&full[ld.slot], len);
-        ptx::bulk_g2s(smem + static_cast<size_t>(ld.slot) * T, src, len, &full[ld.slot]);
+        if (p.l2_hint && m_l != 0 && m_l != R + 1)  // own rows: streamed once, never re-read through L2
+          ptx::bulk_g2s_hint(smem + static_cast<size_t>(ld.slot) * T, src, len, &full[ld.slot], policy);
+        else
+          ptx::bulk_g2s(smem + static_cast<size_t>(ld.slot) * T, src, len, &full[ld.slot]);
         ld.advance(1, S);
         ++issued;
         if (++m_l == R + 2) {
@@ -195,7 +200,12 @@ __global__ void __launch_bounds__(kHaloThreads) halo_stencil_kernel(const HaloPa
         const size_t off = col_off(jj_c);
         const uint32_t len = col_len(off);
         const unsigned char* sa = smem + static_cast<size_t>(st.slot) * T;
-        ptx::bulk_s2g(uout + static_cast<size_t>(r) * p.row_bytes + off, sa, len);
+        // interior rows are not read again before the next step has streamed the whole slab through L2; the boundary
+        // rows are what the neighbours pull, leave them to the default policy
+        if (p.l2_hint && r != 0 && r != R - 1)
+          ptx::bulk_s2g_hint(uout + static_cast<size_t>(r) * p.row_bytes + off, sa, len, policy);
+        else
+          ptx::bulk_s2g(uout + static_cast<size_t>(r) * p.row_bytes + off, sa, len);
         if (kMode == 2) {
           if (r == 0) ptx::bulk_s2g(p.put_first[out] + off, sa, len);
           if (r == R - 1) ptx::bulk_s2g(p.put_last[out] + off, sa, len);
@@ -440,6 +450,7 @@ int launch_halo_stencil(const HaloStencilArgs& a, HaloMode mode, const HaloTunin
   HPCP_REQUIRE(p.tile_begin < p.tile_end && p.tile_end <= tiles_per_row, "halo_stencil: bad column-tile range");
   p.tile_bytes = g.tile_bytes;
   p.stages = g.stages;
+  p.l2_hint = tune.l2_hint;
   p.alpha = a.alpha;
   p.s = a.s;
   p.step_base = a.step_base;

@@ -19,6 +19,7 @@
 //                 rendezvous put kernel, then Accumulate kernel, per step (VA/VB swap)
 //   (with -a)     nvls when NVSwitch multicast is available, else two-shot P2P;
 //                 force with --coll nvls|twoshot
+#include <cuda_profiler_api.h>
 #include <getopt.h>
 
 #include <algorithm>
@@ -54,6 +55,7 @@ struct Config {
   std::string algo = "ring";
   std::string coll = "auto";
   int iters = 5;
+  bool profile_relaunch = false;  // rank 0 repeats its last launch between cudaProfilerStart/Stop
   int warmup = 1;
   int ctas = 0;
   size_t chunk_elems = 0;
@@ -81,6 +83,8 @@ void print_help() {
                " -R          the `map` variant of the reference: host malloc'ed arrays with a device-resident mapped copy\n"
                "             (kernels and the exchange use the device copy; VC is updated back and verified on the host)\n"
                " --map-alias with -R: map by cudaHostRegister + device alias instead (zero-copy over PCIe)\n"
+               " --profile-relaunch    after the run rank 0 repeats its last launch (same epochs, peers idle) between\n"
+               "                       cudaProfilerStart/Stop: use with `ncu --profile-from-start off`\n"
                " -n N        ranks (one host thread + one GPU each; default: all GPUs;\n"
                "             more ranks than GPUs are placed round-robin)\n"
                " --type T   element type: float int uint double long ulong short ushort uchar (default float, or binary-name suffix)\n"
@@ -176,18 +180,12 @@ void rank_main(RankCtx& ctx, Shared& sh) {
   HPCP_CUDA(cudaEventCreate(&e1));
   double best_ms = std::numeric_limits<double>::max();
 
-  for (int it = 0; it < cfg.warmup + cfg.iters; ++it) {
-    NvtxRange iter_range(it < cfg.warmup ? "allreduce warm-up" : "allreduce timed");
-    // (Re-)initialise outside the timed region: VA = VB = rank, VC = 0.
-    launch_init3(va, cfg.algo == "ring-unfused" && !cfg.use_collective ? sh.vb.ptr[me] : nullptr, vc,
-                 sh.n, me, me, 0, cfg.type, stream);
-    HPCP_CUDA(cudaStreamSynchronize(stream));
-    ctx.barrier();
-    launch_barrier_all(pad_list.data(), me, P, ++barrier_epoch, cfg.timeout_ns, status, stream);
-    HPCP_CUDA(cudaEventRecord(e0, stream));
-
+  // One allreduce on `stream`.  replay = enqueue the PREVIOUS launch again with the same epochs: every word it would
+  // wait for is already there, so it moves the same bytes over the same links without needing a running peer —
+  // the shape a kernel-replay profiler can capture (--profile-relaunch).
+  auto launch_once = [&](bool replay) {
     if (cfg.use_collective) {
-      ++barrier_epoch;
+      if (!replay) ++barrier_epoch;
       if (sh.nvls) {
         NvlsArgs a;
         a.va_mc = sh.mc_va.mc;
@@ -230,7 +228,7 @@ void rank_main(RankCtx& ctx, Shared& sh) {
       a.world = P;
       a.n = sh.n;
       a.chunk_elems = cfg.chunk_elems;
-      a.epoch_base = ring_epoch;
+      a.epoch_base = replay ? ring_epoch - static_cast<uint32_t>(P) : ring_epoch;
       a.timeout_ns = cfg.timeout_ns;
       a.status = status;
       a.n_slots = cfg.slots;
@@ -243,9 +241,10 @@ void rank_main(RankCtx& ctx, Shared& sh) {
         a.ack_local = my_pad + kPadWords + sh.n_chunks;
         a.ack_left = pad_of(sh, left) + kPadWords + sh.n_chunks;
       }
-      ring_epoch += static_cast<uint32_t>(P);
+      if (!replay) ring_epoch += static_cast<uint32_t>(P);
       launch_ring_allreduce(a, cfg.type, cfg.ctas, dev, stream);
     } else {  // ring-unfused: the reference's step structure with separate kernels
+      HPCP_REQUIRE(!replay, "--profile-relaunch supports the one-launch algorithms only");
       void* cur = va;
       void* other = sh.vb.ptr[me];
       void* right_cur = sh.va.ptr[right];     // what the right neighbour currently calls VA
@@ -274,6 +273,20 @@ void rank_main(RankCtx& ctx, Shared& sh) {
         launch_accumulate(cur, vc, sh.n, cfg.type, stream);
       }
     }
+
+  };
+
+  for (int it = 0; it < cfg.warmup + cfg.iters; ++it) {
+    NvtxRange iter_range(it < cfg.warmup ? "allreduce warm-up" : "allreduce timed");
+    // (Re-)initialise outside the timed region: VA = VB = rank, VC = 0.
+    launch_init3(va, cfg.algo == "ring-unfused" && !cfg.use_collective ? sh.vb.ptr[me] : nullptr, vc,
+                 sh.n, me, me, 0, cfg.type, stream);
+    HPCP_CUDA(cudaStreamSynchronize(stream));
+    ctx.barrier();
+    launch_barrier_all(pad_list.data(), me, P, ++barrier_epoch, cfg.timeout_ns, status, stream);
+    HPCP_CUDA(cudaEventRecord(e0, stream));
+
+    launch_once(false);
 
     HPCP_CUDA(cudaEventRecord(e1, stream));
     HPCP_CUDA(cudaStreamSynchronize(stream));
@@ -313,6 +326,23 @@ void rank_main(RankCtx& ctx, Shared& sh) {
     std::cout << me << " " << first_element_as_double(sh.host_vc[me], cfg.type) << std::endl;
   else if (cfg.kind == AllocKind::kMapped && !sh.nvls)  // --map-alias: the buffer IS host memory, read in place
     std::cout << me << " " << first_element_as_double(vc, cfg.type) << std::endl;
+  if (cfg.profile_relaunch) {
+    // Profilers that replay one kernel many times serialise the process's kernels, and a replayed pass would wait for
+    // peers that are long done.  Rank 0 therefore re-enqueues its last launch with the SAME epochs between
+    // cudaProfilerStart/Stop while every other rank is idle: `ncu --profile-from-start off` captures exactly that one.
+    ctx.barrier();
+    if (me == 0) {
+      HPCP_CUDA(cudaProfilerStart());
+      launch_once(true);
+      HPCP_CUDA(cudaStreamSynchronize(stream));
+      HPCP_CUDA(cudaProfilerStop());
+      uint32_t st = 0;
+      HPCP_CUDA(cudaMemcpy(&st, status, sizeof st, cudaMemcpyDeviceToHost));
+      HPCP_REQUIRE(st == 0, "profile relaunch: device-side wait timed out");
+      std::cout << "# profile relaunch of rank 0 done (same epochs, peers idle)" << std::endl;
+    }
+    ctx.barrier();
+  }
   if (me == 0) {
     sh.best_ms = best_ms;
     sh.total_bad = static_cast<unsigned long long>(total_bad);
@@ -437,6 +467,7 @@ int main(int argc, char** argv) {
                                        {"slots", required_argument, nullptr, 10},
                                        {"pull", no_argument, nullptr, 11},
                                        {"map-alias", no_argument, nullptr, 12},
+                                       {"profile-relaunch", no_argument, nullptr, 13},
                                        {"help", no_argument, nullptr, 'h'},
                                        {nullptr, 0, nullptr, 0}};
     int opt;
@@ -462,6 +493,7 @@ int main(int argc, char** argv) {
         case 8: cfg.json_path = optarg; break;
         case 9: cfg.cpu = true; break;
         case 12: cfg.map_alias = true; break;
+        case 13: cfg.profile_relaunch = true; break;
         case 10: cfg.slots = std::atoi(optarg); break;
         case 11: cfg.pull = true; break;
         default: print_help(); return 1;

@@ -435,12 +435,14 @@ def main(argv: Optional[List[str]] = None) -> int:
     ap.add_argument("--tile-kb", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=0)
+    ap.add_argument("--l2-hint", action="store_true", help="evict_first L2 policy on the slab's own streaming traffic")
     ap.add_argument("--json", default=None)
     args = ap.parse_args(argv)
     comm = Comm()
     dev = comm.device
     torch.cuda.set_device(dev)
-    tune = {k: v for k, v in (("tile_kb", args.tile_kb), ("stages", args.stages), ("ctas", args.ctas)) if v}
+    tune = {k: v for k, v in (("tile_kb", args.tile_kb), ("stages", args.stages), ("ctas", args.ctas),
+                              ("l2_hint", int(args.l2_hint))) if v}
     hs = HaloStencil(comm, dev, args.bytes, args.rows, args.mode, tune=tune)
     if args.stock:
         enqueue = lambda: [hs.stock_step(args.stock) for _ in range(args.steps)]      # noqa: E731

@@ -29,6 +29,7 @@ def main() -> int:
     ap.add_argument("--geometry", nargs="+", default=["16x12", "16x8", "8x12", "8x24", "32x6", "8x13", "16x6", "4x24"],
                     help="tile_kb x stages")
     ap.add_argument("--ctas", type=int, nargs="+", default=[0])
+    ap.add_argument("--l2-hint", type=int, nargs="+", default=[0], help="0: default L2 policy, 1: evict_first streaming")
     ap.add_argument("--bytes", type=int, default=REFERENCE_MESSAGE_BYTES)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--preheat-ms", type=float, default=100.0)
@@ -37,9 +38,9 @@ def main() -> int:
     dev = comm.device
     torch.cuda.set_device(dev)
     rows_out = []
-    for rows, mode, geo, ctas in itertools.product(args.rows, args.modes, args.geometry, args.ctas):
+    for rows, mode, geo, ctas, hint in itertools.product(args.rows, args.modes, args.geometry, args.ctas, args.l2_hint):
         tile_kb, stages = (int(x) for x in geo.split("x"))
-        tune = {"tile_kb": tile_kb, "stages": stages}
+        tune = {"tile_kb": tile_kb, "stages": stages, "l2_hint": hint}
         if ctas:
             tune["ctas"] = ctas
         try:
@@ -52,7 +53,7 @@ def main() -> int:
         m = timer.measure(lambda: hs.step(args.steps), args.steps, blocks=3, preheat_ms=args.preheat_ms)
         m1 = timer.measure(lambda: [hs.step(1) for _ in range(args.steps)], args.steps, blocks=3, preheat_ms=0)
         bad = int(comm.sum(hs.verify_last_step()))
-        row = {"world": comm.world, "rows": rows, "mode": mode, "tile_kb": tile_kb, "stages": stages, "ctas": hs.ctas,
+        row = {"world": comm.world, "rows": rows, "mode": mode, "tile_kb": tile_kb, "stages": stages, "l2_hint": hint, "ctas": hs.ctas,
                "ms_per_step": round(m["ms"], 5), "blocks": m["blocks_ms"], "per_step_launch_ms": round(m1["ms"], 5),
                "hbm_GBps": round(hs.hbm_bytes_per_step() / m["ms"] / 1e6, 1),
                "nvlink_GBps_per_dir": round(hs.nvlink_bytes_per_step() / m["ms"] / 1e6, 1), "wrong_words": bad}

@@ -56,6 +56,19 @@ def test_persistent_multi_step_launch(native, mode, world, rows):
         ring.close()
 
 
+@pytest.mark.parametrize("mode", ["pull", "push"])
+def test_l2_evict_first_hint_is_exact(native, mode):
+    """tune l2_hint=1: the slab's own rows stream with an evict_first policy; the values must not change."""
+    world, rows, message_bytes = 2, 4, 9 * 4096 + 512
+    ring = _ring(world, message_bytes, rows, mode, tune={**SMALL, "l2_hint": 1})
+    try:
+        ring.step(3)
+        ring.step(4, persistent=True)
+        assert torch.equal(ring.gather(), _want(world, rows, message_bytes // 4, 7))
+    finally:
+        ring.close()
+
+
 def test_default_tiles_large_rows(native):
     """Default 16 KiB x 12 stage geometry, rows larger than one wave of tiles, both modes, single rank."""
     from hpc_patterns_b200.models.halo import HaloStencil
