@@ -197,6 +197,16 @@ def test_cli_allreduce_virtual_ranks(bin_dir, args, n):
     assert out.count("Passed") == n
 
 
+@pytest.mark.parametrize("args", [[], ["--slots", "2"], ["--pull"], ["-a", "--coll", "twoshot"]])
+def test_cli_allreduce_profile_relaunch(bin_dir, args):
+    """--profile-relaunch: rank 0 repeats its last launch with the same epochs while the peers idle (what ncu's
+    kernel replay needs); the repeat must run through without a running peer and without a device-side timeout."""
+    rc, out, err = _run([os.path.join(bin_dir, "allreduce"), "-n", "2", "-p", "18", "--iters", "2",
+                         "--profile-relaunch"] + args, env={"CUDA_VISIBLE_DEVICES": "0"}, timeout=180)
+    assert rc == 0, out + err
+    assert out.count("Passed") == 2 and "profile relaunch of rank 0 done" in out
+
+
 @pytest.mark.parametrize("args", [[], ["--mode", "push"], ["--per-step"], ["--stock", "memcpy"], ["--rows", "1", "--mode", "push"]])
 @pytest.mark.parametrize("n", [1, 2, 4])
 def test_cli_halo_virtual_ranks(bin_dir, args, n):
