@@ -17,6 +17,7 @@
 #include <getopt.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
@@ -48,6 +49,8 @@ struct Config {
   HaloTuning tune;
   uint64_t timeout_ns = 30ull * 1000 * 1000 * 1000;
   std::string json_path;
+  bool cpu = false;                      // host-only plumbing run: ranks are threads, rows live in host vectors
+  std::string dump_path;                 // --cpu only: the final field, rank after rank, raw fp32
 };
 
 void print_help() {
@@ -61,7 +64,11 @@ void print_help() {
                " --stock memcpy     the reference's shape through stock calls: kernel; wait; copies; wait\n"
                " --ctas N --tile-kb N --stages N   kernel geometry\n"
                " --l2-hint             evict_first L2 policy on the slab's own streaming loads / stores\n"
-               " --json FILE   append one JSON row\n";
+               " --json FILE   append one JSON row\n"
+               " --cpu         no GPU: ranks are host threads, the exchange is a memcpy into (push) or a read out of (pull)\n"
+               "               the neighbours' arrays, one barrier per step — options, ring order, verification and output\n"
+               "               of the program on a machine without a device (default 4 ranks); --dump FILE writes the final\n"
+               "               field (rank after rank, raw fp32) for comparison with an independent implementation\n";
 }
 
 struct Shared {
@@ -194,6 +201,131 @@ void rank_main(RankCtx& ctx, Shared& sh) {
   (void)cudaStreamDestroy(stream);
 }
 
+// ---------------------------------------------------------------- host-only path ----
+// The same program without a device, like `allreduce --cpu` / `peer2pear --cpu`: ranks are threads of the rank
+// runtime, a slab is a host vector, "pull" reads the neighbours' boundary rows in place, "push" copies the new boundary
+// rows into the neighbours' halo arrays, and one barrier per step stands in for the step words.  Exists to test the
+// program logic (options, slab decomposition, ring order, parity double-buffering, verification, output) on a machine
+// without a GPU; the verification advances the closed-form initial field of the WHOLE ring column by column, exactly as
+// halo_verify_init_kernel does.
+__attribute__((noinline)) float host_stencil1(float prev, float cur, float next, float alpha, float s) {
+  const float sum = prev + next;
+  const float side = s * sum;
+  const float mid = alpha * cur;
+  return mid + side;
+}
+
+float host_u0(uint32_t grow, uint64_t j) {  // halo_u0 of kernels/halo_stencil.cu
+  const uint32_t jl = static_cast<uint32_t>(j);
+  const uint32_t h = (grow * 2654435761u) ^ (jl * 40503u + (jl >> 11));
+  return static_cast<float>(static_cast<int>(h & 0xFFFFu) - 32768) * (1.0f / 1024.0f);
+}
+
+int run_on_host(const Config& cfg) {
+  const int P = cfg.ranks > 0 ? cfg.ranks : 4;
+  HPCP_REQUIRE(P >= 1 && P <= kMaxRanks, "ranks out of range");
+  const int R = cfg.rows;
+  const size_t n = cfg.bytes / 4;
+  const bool push = cfg.mode == "push" || !cfg.stock.empty();  // the stock shape is a push with host waits
+  const float alpha = HaloStencilArgs{}.alpha, sc = HaloStencilArgs{}.s;
+  std::vector<std::vector<float>> u[2], lo[2], hi[2];
+  for (int q = 0; q < 2; ++q) {
+    u[q].resize(P);
+    lo[q].resize(P);
+    hi[q].resize(P);
+  }
+  double best_ms = 0;
+  unsigned long long total_bad = 0;
+  int final_parity = 0;
+  run_ranks(P, [&](RankCtx& ctx) {
+    const int me = ctx.rank, left = (me - 1 + P) % P, right = (me + 1) % P;
+    const uint32_t G = static_cast<uint32_t>(P) * R, first = static_cast<uint32_t>(me) * R;
+    for (int q = 0; q < 2; ++q) {
+      u[q][me].assign(static_cast<size_t>(R) * n, 0.f);
+      lo[q][me].assign(n, 0.f);
+      hi[q][me].assign(n, 0.f);
+    }
+    for (size_t j = 0; j < n; ++j) {
+      for (int r = 0; r < R; ++r) u[0][me][static_cast<size_t>(r) * n + j] = host_u0(first + r, j);
+      lo[0][me][j] = host_u0((first + G - 1) % G, j);
+      hi[0][me][j] = host_u0((first + R) % G, j);
+    }
+    uint32_t g = 0;
+    double best = std::numeric_limits<double>::max();
+    for (int it = 0; it < cfg.warmup + cfg.iters; ++it) {
+      ctx.barrier();
+      const auto t0 = std::chrono::steady_clock::now();
+      for (int k = 0; k < cfg.steps; ++k, ++g) {
+        const int in = g & 1, out = in ^ 1;
+        ctx.barrier();  // every rank finished step g-1: its rows (pull) / my halo arrays (push) hold step g's inputs
+        const float* below = push ? lo[in][me].data() : u[in][left].data() + static_cast<size_t>(R - 1) * n;
+        const float* above = push ? hi[in][me].data() : u[in][right].data();
+        const float* src = u[in][me].data();
+        float* dst = u[out][me].data();
+        for (int r = 0; r < R; ++r) {
+          const float* dn = r == 0 ? below : src + static_cast<size_t>(r - 1) * n;
+          const float* up = r == R - 1 ? above : src + static_cast<size_t>(r + 1) * n;
+          const float* ce = src + static_cast<size_t>(r) * n;
+          for (size_t j = 0; j < n; ++j) dst[static_cast<size_t>(r) * n + j] = host_stencil1(dn[j], ce[j], up[j], alpha, sc);
+        }
+        if (push) {  // my new first row is the left neighbour's upper halo, my new last row the right one's lower halo
+          std::copy(dst, dst + n, hi[out][left].begin());
+          std::copy(dst + static_cast<size_t>(R - 1) * n, dst + static_cast<size_t>(R) * n, lo[out][right].begin());
+        }
+      }
+      ctx.barrier();
+      const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      const double t = ctx.max(ms);
+      if (it >= cfg.warmup) best = std::min(best, t);
+    }
+    // every column of the whole ring from the closed form, advanced g steps; compare this rank's rows exactly
+    unsigned long long bad = 0;
+    std::vector<float> v(G), w(G);
+    const float* mine = u[g & 1][me].data();
+    for (size_t j = 0; j < n; ++j) {
+      for (uint32_t q = 0; q < G; ++q) v[q] = host_u0(q, j);
+      for (uint32_t k = 0; k < g; ++k) {
+        for (uint32_t q = 0; q < G; ++q) w[q] = host_stencil1(v[(q + G - 1) % G], v[q], v[(q + 1) % G], alpha, sc);
+        v.swap(w);
+      }
+      for (int r = 0; r < R; ++r) bad += mine[static_cast<size_t>(r) * n + j] != v[first + r];
+    }
+    const double all_bad = ctx.sum(static_cast<double>(bad));
+    if (bad == 0)
+      std::cout << "Passed " << me << std::endl;
+    else
+      std::cout << "FAILED " << me << ": " << bad << " wrong elements" << std::endl;
+    if (me == 0) {
+      best_ms = best;
+      total_bad = static_cast<unsigned long long>(all_bad);
+      final_parity = static_cast<int>(g & 1);
+    }
+  });
+  if (!cfg.dump_path.empty()) {
+    FILE* f = std::fopen(cfg.dump_path.c_str(), "wb");
+    HPCP_REQUIRE(f != nullptr, "cannot open --dump file");
+    for (int r = 0; r < P; ++r) std::fwrite(u[final_parity][r].data(), sizeof(float), u[final_parity][r].size(), f);
+    std::fclose(f);
+  }
+  const double ms_per_step = best_ms / cfg.steps;
+  const double bus = static_cast<double>(P) * 2.0 * static_cast<double>(cfg.bytes) / (ms_per_step * 1e6);
+  const std::string what = std::string(!cfg.stock.empty() ? "stock-" + cfg.stock : cfg.mode) + "/host-threads";
+  std::cout << "Elapsed (max over ranks, min of " << cfg.iters << "): " << best_ms << " ms for " << cfg.steps
+            << " steps = " << ms_per_step << " ms/step | halo " << what << " P=" << P << " rows=" << R
+            << " bytes=" << cfg.bytes << " ctas=0 | " << bus << " GB/s P2P bus (aggregate), " << bus / P / 2.0
+            << " GB/s per GPU per direction" << std::endl;
+  if (!cfg.json_path.empty()) {
+    if (FILE* f = std::fopen(cfg.json_path.c_str(), "a")) {
+      std::fprintf(f,
+                   "{\"pattern\":\"halo\",\"variant\":\"%s\",\"ranks\":%d,\"rows\":%d,\"bytes\":%zu,\"steps\":%d,"
+                   "\"ms_per_step\":%.6f,\"bus_GBps\":%.3f,\"per_gpu_per_dir_GBps\":%.3f,\"ctas\":0,\"mismatches\":%llu}\n",
+                   what.c_str(), P, R, cfg.bytes, cfg.steps, ms_per_step, bus, bus / P / 2.0, total_bad);
+      std::fclose(f);
+    }
+  }
+  return total_bad == 0 ? 0 : 1;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -206,7 +338,8 @@ int main(int argc, char** argv) {
                                        {"per-step", no_argument, nullptr, 7},     {"stock", required_argument, nullptr, 8},
                                        {"ctas", required_argument, nullptr, 9},   {"tile-kb", required_argument, nullptr, 10},
                                        {"stages", required_argument, nullptr, 11}, {"json", required_argument, nullptr, 12},
-                                       {"l2-hint", no_argument, nullptr, 13},
+                                       {"l2-hint", no_argument, nullptr, 13},      {"cpu", no_argument, nullptr, 14},
+                                       {"dump", required_argument, nullptr, 15},
                                        {"help", no_argument, nullptr, 'h'},       {nullptr, 0, nullptr, 0}};
     int opt;
     while ((opt = getopt_long(argc, argv, "hn:", long_opts, nullptr)) != -1) {
@@ -226,12 +359,16 @@ int main(int argc, char** argv) {
         case 11: cfg.tune.stages = std::atoi(optarg); break;
         case 12: cfg.json_path = optarg; break;
         case 13: cfg.tune.l2_hint = 1; break;
+        case 14: cfg.cpu = true; break;
+        case 15: cfg.dump_path = optarg; break;
         default: print_help(); return 1;
       }
     }
     HPCP_REQUIRE(cfg.mode == "pull" || cfg.mode == "push", "--mode must be pull or push");
     HPCP_REQUIRE(cfg.stock.empty() || cfg.stock == "memcpy", "--stock accepts memcpy");
     HPCP_REQUIRE(cfg.rows >= 1 && cfg.bytes >= 16 && cfg.bytes % 16 == 0, "--rows >= 1, --bytes a multiple of 16");
+    HPCP_REQUIRE(cfg.dump_path.empty() || cfg.cpu, "--dump belongs to --cpu");
+    if (cfg.cpu) return run_on_host(cfg);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
       (void)cudaGetLastError();

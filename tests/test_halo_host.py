@@ -169,3 +169,25 @@ def test_block_timer_preheat_count_is_rank_independent():
     with mock.patch.object(timing.torch.cuda, "synchronize", lambda *_: None):
         info = t.preheat(lambda: calls.append(1), min_ms=10.0)
     assert info["blocks"] == len(calls) == 1 + 8          # (10 - 2) / 2 -> max(4, 7) -> 7 + 1
+
+
+@pytest.mark.parametrize("mode", ["pull", "push"])
+@pytest.mark.parametrize("ranks,rows,row_bytes,steps", [(1, 1, 64, 3), (3, 2, 4096, 5), (4, 5, 1040, 4)])
+def test_native_halo_host_path_matches_torch(bin_dir, tmp_path, mode, ranks, rows, row_bytes, steps):
+    """`halo --cpu`: the native program's slab decomposition, ring order and parity double-buffering without a GPU.
+    Its final field (--dump) must equal a plain PyTorch fp32 run of the undecomposed periodic stencil bit for bit —
+    which also pins the C++ closed-form initial field to models/halo.py::initial_field."""
+    import numpy as np
+    import torch
+    from hpc_patterns_b200.models.halo import initial_field, reference_steps
+
+    dump = tmp_path / "field.f32"
+    iters, warmup = 2, 1
+    p = subprocess.run([os.path.join(bin_dir, "halo"), "--cpu", "-n", str(ranks), "--rows", str(rows), "--bytes",
+                        str(row_bytes), "--steps", str(steps), "--iters", str(iters), "--warmup", str(warmup),
+                        "--mode", mode, "--dump", str(dump)], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert p.stdout.count("Passed") == ranks and f"halo {mode}/host-threads P={ranks} rows={rows}" in p.stdout
+    got = torch.from_numpy(np.fromfile(dump, dtype=np.float32)).reshape(ranks * rows, row_bytes // 4)
+    want = reference_steps(initial_field(ranks, rows, row_bytes // 4), steps * (iters + warmup))
+    assert torch.equal(got, want), float((got - want).abs().max())
