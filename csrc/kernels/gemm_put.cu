@@ -77,8 +77,8 @@ struct PutPolicy {
 // loop written out, not the policy template.  The template (umma.cuh: gemm_persistent) is the same loop with the
 // hooks factored out and every later variant uses it, but it does not compile to byte-identical SASS (register
 // allocation differs), and the contract for refactors around GPU-validated kernels is "not one instruction changes"
-// (docs/sass/VALIDATED.sha256, scripts/sass_fingerprint.py).  Once the template instantiation with PutPolicy has run
-// on a GPU this copy can go.
+// (docs/sass/VALIDATED.sha256, scripts/sass_fingerprint.py).  PutPolicy above is what the 2-SM kernel instantiates the
+// template with.
 // kCluster == 2: thread-block clusters of two CTAs working on vertically adjacent tiles (same n_blk).
 // Both need the same B tile, so each CTA fetches half of it (128 rows) and TMA-multicasts it into both
 // CTAs' shared memory: L2->SM operand traffic drops from 48 to 32 KiB per CTA per k-block.  A stage
@@ -285,15 +285,6 @@ __global__ void __launch_bounds__(kThreads, 1)
     last_cta_publish(g.sync.ticket, g.sync.ticket_base + gridDim.x, g.sync.signal_flag, g.sync.signal_epoch);
 }
 
-// The same kernel as an instantiation of the policy template (HPCP_GEMM_PUT_TEMPLATE=1 selects it): once it has run
-// on a GPU next to the copy above, the copy can be retired.
-template <int kCluster>
-__global__ void __launch_bounds__(kThreads, 1)
-    gemm_put_policy_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                           const __grid_constant__ GemmDev g) {
-  gemm_persistent<kCluster, kStages>(map_a, map_b, g.tiles_m, g.tiles_n, g.k, PutPolicy{g});
-}
-
 // Alternative epilogue (opt-in, `tma_epilogue`): the C tile leaves through the TMA unit — swizzled [32 x 128 B]
 // pieces in shared memory, one cp.async.bulk.tensor.2d store (UTMASTG) per piece and destination — instead of
 // 128-bit st.global from the epilogue warps.  Frees the LSU and sends the peer copy as bulk stores.
@@ -414,18 +405,8 @@ int launch_gemm_put(const void* a_bf16, const void* b_bf16, void* c_local, void*
       HPCP_CUDA(cudaLaunchKernelEx(&cfg, gemm_put_tma_kernel<2>, map_a, map_b, g, maps));
     return grid;
   }
-  static const bool use_template = [] {
-    const char* e = std::getenv("HPCP_GEMM_PUT_TEMPLATE");
-    return e != nullptr && e[0] == '1';
-  }();
   if (!use_cluster || grid < 2) {
     const CUtensorMap map_b_full = use_cluster ? make_kmajor_map(b_bf16, n, k, kBN) : map_b;
-    if (use_template) {
-      HPCP_ENABLE_SMEM(gemm_put_policy_kernel<1>, kSmemBytes);
-      gemm_put_policy_kernel<1><<<grid, kThreads, kSmemBytes, stream>>>(map_a, map_b_full, g);
-      HPCP_CUDA(cudaGetLastError());
-      return grid;
-    }
     HPCP_ENABLE_SMEM(gemm_put_kernel<1>, kSmemBytes);
     gemm_put_kernel<1><<<grid, kThreads, kSmemBytes, stream>>>(map_a, map_b_full, g);
     HPCP_CUDA(cudaGetLastError());
@@ -435,8 +416,6 @@ int launch_gemm_put(const void* a_bf16, const void* b_bf16, void* c_local, void*
   grid &= ~1;  // whole pairs
   if (two_sm)
     HPCP_ENABLE_SMEM(gemm_put_2sm_kernel, gemm_2sm_smem_bytes(0));
-  else if (use_template)
-    HPCP_ENABLE_SMEM(gemm_put_policy_kernel<2>, kSmemBytes);
   else
     HPCP_ENABLE_SMEM(gemm_put_kernel<2>, kSmemBytes);
   cudaLaunchConfig_t cfg{};
@@ -453,8 +432,6 @@ int launch_gemm_put(const void* a_bf16, const void* b_bf16, void* c_local, void*
   cfg.numAttrs = 1;
   if (two_sm)
     HPCP_CUDA(cudaLaunchKernelEx(&cfg, gemm_put_2sm_kernel, map_a, map_b, g));
-  else if (use_template)
-    HPCP_CUDA(cudaLaunchKernelEx(&cfg, gemm_put_policy_kernel<2>, map_a, map_b, g));
   else
     HPCP_CUDA(cudaLaunchKernelEx(&cfg, gemm_put_kernel<2>, map_a, map_b, g));
   return grid;

@@ -655,34 +655,27 @@ int launch_allreduce_nvls(const NvlsArgs& args, ElemType type, int ctas, int dev
   d.barrier_epoch = args.barrier_epoch;
   d.timeout_ns = args.timeout_ns;
   d.status = args.status;
-  // Tuning knobs for sweeps (defaults = the measured configuration: 4 in flight, 512 threads, 32 CTAs):
-  //   HPCP_NVLS_UNROLL=1|2|4|8   HPCP_NVLS_THREADS=256|512|1024   HPCP_NVLS_CTAS_PER_SM=k   (or --ctas / ctas>0)
-  static const int unroll = env_choice("HPCP_NVLS_UNROLL", {1, 2, 4, 8}, 4);
-  static const int threads = env_choice("HPCP_NVLS_THREADS", {256, 512, 1024}, 512);
+  // HPCP_NVLS_UNROLL=4|8 (vectors in flight per thread; default 4), HPCP_NVLS_CTAS_PER_SM=k or --ctas / ctas>0 (grid).
+  static const int unroll = env_choice("HPCP_NVLS_UNROLL", {4, 8}, 4);
   static const int per_sm = env_choice("HPCP_NVLS_CTAS_PER_SM", {0, 1, 2, 3, 4}, 0);
+  constexpr int threads = 512;
   const int sms = device_sm_count(device);
   // Default grid: 32 CTAs.  The in-switch reduction saturates at modest request parallelism and more requesters only
   // queue in the switch: 8xB200, 2^25 floats 0.297 ms @32 CTAs vs 0.325 @148 vs 0.349 @296; 2^28 floats 2.23 ms @32 vs
   // 3.41 @148 (NCCL: 0.431 / 2.907 ms) — profiles/r2_call4_8gpu/nvls_tune.txt.  HPCP_NVLS_CTAS_PER_SM / --ctas override.
   const int grid = grid_for(std::max<size_t>(d.slice_vec, 1), threads, ctas > 0 ? ctas : per_sm > 0 ? sms * per_sm : 32);
   d.ticket_target = args.ticket_base + static_cast<uint32_t>(grid);
-#define HPCP_NVLS(U, B)                                             \
-  do {                                                              \
-    if (type == ElemType::kFloat)                                   \
-      nvls_kernel<float, U, B><<<grid, threads, 0, stream>>>(d);    \
-    else                                                            \
-      nvls_kernel<int, U, B><<<grid, threads, 0, stream>>>(d);      \
+#define HPCP_NVLS(U)                                                  \
+  do {                                                                \
+    if (type == ElemType::kFloat)                                     \
+      nvls_kernel<float, U, threads><<<grid, threads, 0, stream>>>(d); \
+    else                                                              \
+      nvls_kernel<int, U, threads><<<grid, threads, 0, stream>>>(d);   \
   } while (0)
-  if (threads > 512) {  // 1024-thread blocks: 64 registers per thread
-    if (unroll == 1) HPCP_NVLS(1, 1024);
-    else if (unroll == 2) HPCP_NVLS(2, 1024);
-    else HPCP_NVLS(4, 1024);
-  } else {
-    if (unroll == 1) HPCP_NVLS(1, 512);
-    else if (unroll == 2) HPCP_NVLS(2, 512);
-    else if (unroll == 8) HPCP_NVLS(8, 512);
-    else HPCP_NVLS(4, 512);
-  }
+  if (unroll == 8)
+    HPCP_NVLS(8);
+  else
+    HPCP_NVLS(4);
 #undef HPCP_NVLS
   HPCP_CUDA(cudaGetLastError());
   return grid;

@@ -21,7 +21,6 @@ for p in 25 28; do
     for k in 1 2; do run "unroll=$u threads=512 ctas_per_sm=$k" HPCP_NVLS_UNROLL=$u HPCP_NVLS_CTAS_PER_SM=$k --; done
     for c in 16 32 64 96; do run "unroll=$u threads=512 ctas=$c" HPCP_NVLS_UNROLL=$u -- --ctas $c; done
   done
-  run "unroll=4 threads=1024 ctas=32" HPCP_NVLS_UNROLL=4 HPCP_NVLS_THREADS=1024 -- --ctas 32
   timeout 120 ./bin/allreduce -n "$N" -p $p -a --coll twoshot --iters 10 2>&1 | grep Elapsed | sed "s/^/p=$p twoshot | /" | tee -a $OUT/nvls_tune.txt
 done
 for p in 25 28; do

@@ -25,14 +25,14 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MANIFEST = os.path.join(ROOT, "docs", "sass", "VALIDATED.sha256")
 # demangled-name patterns of instantiations that have NOT run on a GPU (everything else ran in round 2:
-# profiles/r2_call2_1gpu .. r2_call5_1gpu; the experimental gates of round 1 are gone)
+# profiles/r2_call2_1gpu .. r2_call14_2gpu; the experimental gates of round 1 are gone)
 UNVALIDATED = (
-    r"gemm_put_policy_kernel",                                            # only behind HPCP_GEMM_PUT_TEMPLATE=1
-    r"ring_pull_kernel<(double|long long|short|unsigned char)",           # pull / two-slot rings ran for float and int
-    r"ring_allreduce_kernel<(double|long long|short|unsigned char), true>",
-    r"two_shot_kernel<[\w ]+, 16, 1>",                                    # more than 8 ranks
-    r"two_shot_kernel<(long long|unsigned char), ", r"two_shot_kernel<short, 8, ",
-    r"nvls_kernel<\w+, (1|2), \d+>", r"nvls_kernel<\w+, \d+, 1024>", r"nvls_kernel<int, ",
+    # more than 8 ranks: needs > 8 GPUs; 12 / 16 thread-ranks on ONE GPU time out in the device barrier (ranks sharing
+    # a hardware queue serialise their spinning kernels) — profiles/r2_call14_2gpu
+    r"two_shot_kernel<[\w ]+, 16, 1>",
+    # (add class, world bucket) pairs of two-shot that no GPU call reached before the budget ran out; their siblings
+    # (same template, other type or other bucket) all ran — tests/test_gpu_multi.py::test_cli_two_shot_remaining_type_classes
+    r"two_shot_kernel<long long, 4, ", r"two_shot_kernel<unsigned char, (2|8), ",
 )
 
 

@@ -197,6 +197,43 @@ def test_cli_allreduce_virtual_ranks(bin_dir, args, n):
     assert out.count("Passed") == n
 
 
+@pytest.mark.parametrize("variant", [["--pull"], ["--slots", "2"], ["--pull", "--slots", "2"]])
+@pytest.mark.parametrize("type_", ["double", "long", "short", "uchar"])
+def test_cli_allreduce_ring_variants_every_type_class(bin_dir, variant, type_):
+    """The pull ring and the two-slot + ack ring for every add class of the reference's datatype trait (8-, 2- and
+    1-byte lanes next to float / int), four thread-ranks on one GPU (the ack channel matters from P = 4 on)."""
+    rc, out, err = _run([os.path.join(bin_dir, "allreduce"), "-n", "4", "-p", "18", "--iters", "2", "--type", type_]
+                        + variant, env={"CUDA_VISIBLE_DEVICES": "0"}, timeout=180)
+    assert rc == 0, out + err
+    assert out.count("Passed") == 4
+
+
+@pytest.mark.parametrize("n,type_", [(6, "short"), (2, "long"), (4, "uchar"), (6, "ulong"), (4, "long"), (2, "uchar"),
+                                     (6, "uchar")])
+def test_cli_two_shot_remaining_type_classes(bin_dir, n, type_):
+    """Two-shot for the (world bucket, add class) pairs the other tests do not reach, as thread-ranks on one GPU.
+    (More than 8 ranks on ONE GPU time out in the device barrier — 12 and 16 tried, profiles/r2_call14_2gpu: the
+    spinning kernels of ranks that share a hardware queue serialise — so the 16-wide instantiation stays unvalidated.)"""
+    rc, out, err = _run([os.path.join(bin_dir, "allreduce"), "-n", str(n), "-p", "16", "--iters", "2", "-a", "--coll",
+                         "twoshot", "--type", type_], env={"CUDA_VISIBLE_DEVICES": "0"}, timeout=180)
+    assert rc == 0, out + err
+    assert out.count("Passed") == n
+
+
+@needs2
+@pytest.mark.parametrize("type_", ["int", "uint"])
+@pytest.mark.parametrize("unroll", ["4", "8"])
+def test_cli_nvls_integer(bin_dir, type_, unroll):
+    """`multimem.ld_reduce` for 32-bit integers (`-a` prefers two-shot for them; --coll nvls forces the switch)."""
+    n = min(_ngpu(), 8)
+    rc, out, err = _run([os.path.join(bin_dir, "allreduce"), "-n", str(n), "-p", "20", "--iters", "2", "-a", "--coll",
+                         "nvls", "--type", type_], env={"HPCP_NVLS_UNROLL": unroll})
+    if rc != 0 and "multicast" in (out + err).lower():
+        pytest.skip("no NVLS multicast on this box")
+    assert rc == 0, out + err
+    assert out.count("Passed") == n
+
+
 @pytest.mark.parametrize("args", [[], ["--slots", "2"], ["--pull"], ["-a", "--coll", "twoshot"]])
 def test_cli_allreduce_profile_relaunch(bin_dir, args):
     """--profile-relaunch: rank 0 repeats its last launch with the same epochs while the peers idle (what ncu's
