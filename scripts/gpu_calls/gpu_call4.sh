@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # 1-GPU call: tcgen05 payload checks + ncu, fused-concurrency diagnosis, sanitizer pass.
 set -u
-cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/../..}"
 OUT=gpurun_out; mkdir -p $OUT
 t() { local secs=$1; shift; timeout "$secs" "$@"; }
 t 300 python -m pytest tests/test_gpu_kernels.py -q --timeout 200 -k "tcgen05 or tensor_command or smoke" -s 2>&1 | tail -15 | tee $OUT/call4_tests.txt

@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # 1-GPU call: concurrency tables (reduced env matrix) + fused-mode rechecks after the carveout fix.
-cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/../..}"
 OUT=gpurun_out; mkdir -p $OUT; rm -f $OUT/cuda.log $OUT/cuda.jsonl
 LC=(--commands C C --commands C M2D --commands C D2M --commands M2D D2M --commands H2D D2H)
 for envs in "HPCP_DEVICE=0" "HPCP_DEVICE=0 CUDA_DEVICE_MAX_CONNECTIONS=1"; do

@@ -2,7 +2,7 @@
 # One gpurun call = everything we want to learn from the box (run with --gpus 2 or 8).
 # Every step is individually bounded by `timeout`; outputs go to gpurun_out/.
 set -u
-cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/../..}"
 OUT=gpurun_out; mkdir -p $OUT
 NGPU=$(nvidia-smi -L | wc -l)
 echo "== $NGPU GPUs" | tee $OUT/summary.txt

@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # Final validation on 2 GPUs: whole GPU test-suite, bench at N=1/2, fused GEMM->put over NVLink, peer-letter groups.
-cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/../..}"
 OUT=gpurun_out; mkdir -p $OUT
 timeout 900 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -12 | tee $OUT/final_pytest.txt
 timeout 200 python bench.py --gpus 1 | tee $OUT/final_bench_n1.json | cut -c1-300

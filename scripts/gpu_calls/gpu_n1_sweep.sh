@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # N=1 (loop-back, HBM-bound) sweep of the flagship kernel's tiling.
-cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/../..}"
 mkdir -p gpurun_out
 run() { local tag=$1; shift; timeout 100 python bench.py --gpus 1 --no-extras --e2e-steps 1 "$@" 2>/dev/null | grep '^{' | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print('$tag', d['ms_per_step'], d['value'])"; }
 run "tma default(16k x6)" --engine tma

@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # 8-GPU confirmation run: topology, scaling of the flagship, peer2pear on 4 pairs, allreduce at P=8.
 set -u
-cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/../..}"
 OUT=gpurun_out; mkdir -p $OUT
 NGPU=$(nvidia-smi -L | wc -l)
 t() { local secs=$1; shift; timeout "$secs" "$@"; }

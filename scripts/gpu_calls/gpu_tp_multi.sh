@@ -2,7 +2,7 @@
 # Multi-GPU call for the fused tensor-parallel layers (run with gpurun --gpus 2, then --gpus 8; ~5 min of box time
 # each, i.e. ~10 and ~40 GPU-minutes):
 # exactness against cuBLAS + NCCL, then fused vs stock timings for a small and a Llama-70B-like shape.
-cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/../..}"
 OUT=gpurun_out; mkdir -p $OUT
 N=${1:-$(nvidia-smi -L | wc -l)}
 export HPCP_EXPERIMENTAL=1

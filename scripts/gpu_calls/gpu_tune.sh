@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # Kernel tuning sweep on 2 GPUs + ncu captures on 1 GPU.  Outputs -> gpurun_out/.
 set -u
-cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/../..}"
 OUT=gpurun_out; mkdir -p $OUT
 B=188743680
 t() { local secs=$1; shift; timeout "$secs" "$@"; }

@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # Round 2, first GPU call (1 GPU): the new flagship (K-halo) — exactness, driver-protocol bench, geometry sweep, ncu.
-cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/../..}"
 OUT=gpurun_out/r2c1; mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1
 timeout 400 python -m pytest tests/test_gpu_halo.py -x -q --timeout 120 2>&1 | tail -15 | tee $OUT/pytest_halo.txt

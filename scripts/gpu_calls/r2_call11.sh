@@ -2,7 +2,7 @@
 # Round 2, call 11 (2 GPUs): ncu captures of the kernels that spin on a peer (fused ring, pull ring, two-shot, NVLS).
 # A replayed pass cannot wait for a peer, so rank 0 repeats its LAST launch with the same epochs (every word already
 # satisfied, peers idle) between cudaProfilerStart/Stop: bin/allreduce --profile-relaunch.
-cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/../..}"
 OUT=gpurun_out/r2c11; mkdir -p $OUT
 timeout 60 bin/allreduce -n 2 -p 25 --iters 2 --profile-relaunch 2>&1 | tail -3
 cap() {  # name, allreduce args...

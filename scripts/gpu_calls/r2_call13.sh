@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # Round 2, last 2-GPU call: the tree as committed — driver-protocol bench at N=2 and the multi-GPU tests a 1-GPU box skips.
-cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/../..}"
 OUT=gpurun_out/r2c13; mkdir -p $OUT
 export PYTHONPATH=$PWD
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29677 \

@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # Round 2, second GPU call (1 GPU): whole GPU suite, the never-run kernels (2-SM UMMA GEMM, GEMM+collective fusions on
 # virtual ranks), driver-protocol bench with all extras, a finer K-halo geometry sweep, fused-mode concurrency verdicts.
-cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/../..}"
 OUT=gpurun_out/r2c2; mkdir -p $OUT
 timeout 900 python -m pytest tests -m gpu -q --timeout 300 2>&1 | tail -25 | tee $OUT/pytest_gpu.txt
 export HPCP_EXPERIMENTAL=1

@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/../..}"
 OUT=gpurun_out/r2c2b; mkdir -p $OUT
 export CUDA_VISIBLE_DEVICES=0
 for t in get sendrecv memcpy; do

@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # Round 2, 2-GPU call: the flagship over NVLink (driver-protocol bench, geometry sweep, ncu with NVLink counters),
 # K-p2p geometry sweep at 180 MiB, the never-run ring variants, the multi-GPU suite.
-cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/../..}"
 OUT=gpurun_out/r2c3; mkdir -p $OUT
 N=2
 run() { timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29655 "$@"; }

@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # 2-GPU follow-up: hybrid put+get transport, rows=8 bench at N=2 and N=1, the tests that failed in call 3.
-cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/../..}"
 OUT=gpurun_out/r2c3b; mkdir -p $OUT
 N=2
 run() { timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29655 "$@"; }

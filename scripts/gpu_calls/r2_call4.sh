@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # Round 2, the ONE 8-GPU call (charged 8x): flagship at N=8 under the driver's protocol, native halo CLI, NVLS / two-shot
 # sweep against NCCL at 128 MiB and 1 GiB, ring variants, peer2pear on 4 pairs, typed reductions, fused TP check.
-cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/../..}"
 OUT=gpurun_out/r2c4; mkdir -p $OUT
 N=8
 run() { timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29655 "$@"; }

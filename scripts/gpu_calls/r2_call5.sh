@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # Round 2, 1-GPU call after the eager-module-loading fix: the whole suite (virtual-rank tests at full width), ncu of the
 # two GEMM tile loops (1-SM CTA-pair multicast vs 2-SM UMMA) and of the fused concurrency kernel.
-cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/../..}"
 OUT=gpurun_out/r2c5; mkdir -p $OUT
 timeout 1200 python -m pytest tests -m gpu -q --timeout 300 > $OUT/pytest_gpu_full.txt 2>&1; tail -12 $OUT/pytest_gpu_full.txt
 cat > /tmp/gemm_one.py <<'PY'

@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # Round 2, last 1-GPU call: the final tree — whole GPU suite, smoke(), driver-protocol bench, ncu of the two GEMM loops.
-cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/../..}"
 OUT=gpurun_out/r2c6; mkdir -p $OUT
 export PYTHONPATH=$PWD
 timeout 900 python -m pytest tests -m gpu -q --timeout 300 > $OUT/pytest_gpu_full.txt 2>&1; tail -6 $OUT/pytest_gpu_full.txt

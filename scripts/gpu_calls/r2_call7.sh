@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # 1-GPU call: the 2-SM UMMA loop after the barrier fix (one arrival per full barrier, cta-scope waits) — exactness, then
 # throughput next to the 1-SM kernel and cuBLAS; the new stencil_step op test.
-cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/../..}"
 OUT=gpurun_out/r2c7; mkdir -p $OUT
 export PYTHONPATH=$PWD
 timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_gemm_collective.py tests/test_gpu_halo.py -q --timeout 120 -k "gemm or 2sm or stencil_step or allgather" > $OUT/pytest_gemm.txt 2>&1; tail -5 $OUT/pytest_gemm.txt

@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # 1-GPU: ncu of the flagship kernel at the benchmark's real shape and final geometry (rows 8 x 188 743 680 B, 2 CTAs/SM),
 # pull and push, plus the launch list of a short bench run (device time per launch, shares only).
-cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/../..}"
 OUT=gpurun_out/r2c8; mkdir -p $OUT
 export PYTHONPATH=$PWD
 for mode in pull push; do

@@ -420,8 +420,9 @@ def test_gemm_put_signal_and_few_ctas(native, dev):
 @pytest.mark.parametrize("m,n,k", [(256, 256, 64), (256, 512, 256), (1024, 1024, 512), (2048, 2048, 1024),
                                    (512, 768, 4096), (8192, 8192, 512)])
 def test_gemm_put_2sm_umma(native, dev, m, n, k):
-    """EXPERIMENTAL (written without GPU access, not yet run): tcgen05.mma.cta_group::2, one 256x256 tile per
-    CTA pair (`cluster=3`).  Run under `timeout`: a protocol error here is a hang, not a wrong number."""
+    """tcgen05.mma.cta_group::2, one 256x256 tile per CTA pair (`cluster=3`): exact against the fp32 reference (inputs
+    are multiples of 1/4, sums are exact).  Written without GPU access in round 1, first run in round 2 (6/6 exact, then
+    2x faster after the barrier fix: profiles/r2_call6_1gpu -> r2_call7_1gpu)."""
     from hpc_patterns_b200.ops.gemm import gemm_put, gemm_reference
 
     torch.manual_seed(m + n + k)
@@ -443,7 +444,7 @@ def test_gemm_put_2sm_umma(native, dev, m, n, k):
 
 @pytest.mark.parametrize("ratio", [1, 3])
 def test_triad_put_tma_l2_hint(native, dev, ratio):
-    """EXPERIMENTAL (not yet run): L2 evict_first cache-policy operands on the TMA engine's streamed copies."""
+    """L2 evict_first cache-policy operands on the TMA engine's streamed copies (round-1 flagship): same values."""
     n_put = (64 * 16384) // 4
     n = n_put * ratio
     b = torch.randn(n, device=dev)
@@ -459,7 +460,7 @@ def test_triad_put_tma_l2_hint(native, dev, ratio):
 
 @pytest.mark.parametrize("halo_ctas", [8, 48, 147])
 def test_triad_put_halo_split_scheduling(native, dev, halo_ctas):
-    """EXPERIMENTAL: dedicated halo CTAs instead of interleaved halo/interior tiles (TMA engine)."""
+    """Dedicated halo CTAs instead of interleaved halo/interior tiles (TMA engine, round-1 flagship): same values."""
     n_put = (64 * 16384) // 4
     n = n_put * 3
     b = torch.randn(n, device=dev)
