@@ -45,6 +45,18 @@ NVLINK_BIDIR_GBS_MEASURED = 706.1   # copy engines with BOTH directions of a pai
                                     # (profiles/r2_call3_2gpu/p2p_tune.jsonl) — what a neighbour exchange can get
 
 
+def measured_hbm_gbs() -> float:
+    """Roofline denominator: the driver-written copy bandwidth of THIS box generation (MEASURED_PEAKS.json), the
+    committed value when the file is missing or unreadable.  `rows` keeps using the committed constant so that the
+    benchmark's configuration does not move with a re-measurement."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            v = float(json.load(f)["hbm_gbs"])
+        return v if v > 0 else HBM_GBS_MEASURED
+    except Exception:
+        return HBM_GBS_MEASURED
+
+
 def env_int(name: str, default: int) -> int:
     return int(os.environ.get(name, str(default)))
 
@@ -147,7 +159,8 @@ def main() -> int:
     msg = args.bytes
     value = world * 2 * msg / (ms_per_step * 1e-3) / 1e9          # aggregate GB/s over all GPUs, both neighbours
     per_gpu_dir = msg * 2 / (ms_per_step * 1e-3) / 1e9            # per GPU per direction
-    hbm_ms = hs.hbm_bytes_per_step() / HBM_GBS_MEASURED / 1e6
+    hbm_peak = measured_hbm_gbs()
+    hbm_ms = hs.hbm_bytes_per_step() / hbm_peak / 1e6
     nvl_ms = (hs.nvlink_bytes_per_step() / NVLINK_BIDIR_GBS_MEASURED / 1e6) if world > 1 else 0.0
     roof_ms = max(hbm_ms, nvl_ms)
 
@@ -298,8 +311,9 @@ def main() -> int:
             "hbm_traffic_GBps": round(hs.hbm_bytes_per_step() / (ms_per_step * 1e-3) / 1e9, 1),
             "roofline": {"hbm_ms": round(hbm_ms, 4), "nvlink_ms": round(nvl_ms, 4), "bound_ms": round(roof_ms, 4),
                          "frac": round(roof_ms / ms_per_step, 3),
-                         "of": "max(HBM bytes / 6567.4 GB/s measured copy peak, NVLink bytes per direction / 706.1 GB/s "
-                               "measured with both directions busy)"},
+                         "hbm_gbs": hbm_peak, "nvlink_gbs_per_dir": NVLINK_BIDIR_GBS_MEASURED,
+                         "of": "max(HBM bytes / MEASURED_PEAKS.json hbm_gbs (copy peak), NVLink bytes per direction / "
+                               "706.1 GB/s measured with both directions busy)"},
             **extras,
         }
         if not args.no_extras:
