@@ -26,19 +26,21 @@ export ASAN_OPTIONS=detect_leaks=1:abort_on_error=0 UBSAN_OPTIONS=print_stacktra
 if grep -E "ERROR: AddressSanitizer|runtime error:|LeakSanitizer" "$out/run.log"; then
   echo "sanitize_host: FAILED (see $out/run.log)"; exit 1
 fi
-# Optional (SANITIZE_CLI=1, needs nvcc + build/libhpcp.a, ~2 min): the --cpu plumbing paths of the two GPU CLIs under
+# Optional (SANITIZE_CLI=1, needs nvcc + build/libhpcp.a, ~2 min): the --cpu plumbing paths of the three GPU CLIs under
 # ThreadSanitizer (ranks are host threads there) and ASan/UBSan.
 if [ "${SANITIZE_CLI:-0}" = 1 ]; then
   make -s build/libhpcp.a >/dev/null
   for san in thread "address,-fsanitize=undefined"; do
     tag=${san%%,*}
-    for prog in miniapps/allreduce p2p/peer2pear; do
+    for prog in miniapps/allreduce miniapps/halo p2p/peer2pear; do
       nvcc -ccbin $CXX -gencode arch=compute_100a,code=sm_100a -O1 -g -std=c++17 -Xcompiler -fopenmp,-fsanitize=$san \
            -Icsrc csrc/$prog.cu build/libhpcp.a -o "$out/$(basename $prog)_$tag" -lgomp
     done
     ASAN_OPTIONS=protect_shadow_gap=0 "$out/allreduce_$tag" --cpu -n 6 -p 14 >> "$out/cli.log" 2>&1
     ASAN_OPTIONS=protect_shadow_gap=0 "$out/allreduce_$tag" --cpu -a --type int -p 12 >> "$out/cli.log" 2>&1
     ASAN_OPTIONS=protect_shadow_gap=0 "$out/peer2pear_$tag" label --cpu -n 4 --bytes 1048576 >> "$out/cli.log" 2>&1
+    ASAN_OPTIONS=protect_shadow_gap=0 "$out/halo_$tag" --cpu -n 5 --rows 3 --bytes 8192 --steps 6 --iters 2 >> "$out/cli.log" 2>&1
+    ASAN_OPTIONS=protect_shadow_gap=0 "$out/halo_$tag" --cpu -n 3 --rows 1 --bytes 4096 --steps 5 --iters 2 --mode push >> "$out/cli.log" 2>&1
   done
   if grep -E "WARNING: ThreadSanitizer|ERROR: AddressSanitizer|runtime error:" "$out/cli.log"; then
     echo "sanitize_host: FAILED (see $out/cli.log)"; exit 1
