@@ -56,7 +56,8 @@ struct Config {
 void print_help() {
   std::cout << "Usage: halo [options]\n"
                " -n N          ranks (one host thread + one GPU each; default: all GPUs; more ranks than GPUs share)\n"
-               " --rows R      rows per rank (default 8: HBM time ~ NVLink time); --bytes B  bytes per row (one message)\n"
+               " --rows R      rows per rank (default 8: HBM time ~ NVLink time)\n"
+               " --bytes B     bytes per row (one row = one message)\n"
                " --steps K     time steps per timed iteration (default 20); --iters N  --warmup N\n"
                " --mode pull|push   neighbours' rows are LOADED from their fields / new boundary rows are STORED into\n"
                "                    their halo buffers — both from inside the stencil kernel\n"
@@ -65,10 +66,11 @@ void print_help() {
                " --ctas N --tile-kb N --stages N   kernel geometry\n"
                " --l2-hint             evict_first L2 policy on the slab's own streaming loads / stores\n"
                " --json FILE   append one JSON row\n"
-               " --cpu         no GPU: ranks are host threads, the exchange is a memcpy into (push) or a read out of (pull)\n"
-               "               the neighbours' arrays, one barrier per step — options, ring order, verification and output\n"
-               "               of the program on a machine without a device (default 4 ranks); --dump FILE writes the final\n"
-               "               field (rank after rank, raw fp32) for comparison with an independent implementation\n";
+               " --cpu         no GPU: ranks are host threads, the exchange is a memcpy into (push) or a read out of\n"
+               "               (pull) the neighbours' arrays, one barrier per step: options, ring order, verification\n"
+               "               and output of the program on a machine without a device (default 4 ranks)\n"
+               " --dump FILE   with --cpu: the final field (rank after rank, raw fp32), for comparison with an\n"
+               "               independent implementation\n";
 }
 
 struct Shared {
@@ -95,7 +97,9 @@ void rank_main(RankCtx& ctx, Shared& sh) {
   HPCP_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   const int left = (me - 1 + P) % P, right = (me + 1) % P;
   const size_t row_elems = cfg.bytes / 4, slab = static_cast<size_t>(cfg.rows) * cfg.bytes;
-  auto u = [&](int r, int parity) { return reinterpret_cast<float*>(static_cast<char*>(sh.field.ptr[r]) + parity * slab); };
+  auto u = [&](int r, int parity) {
+    return reinterpret_cast<float*>(static_cast<char*>(sh.field.ptr[r]) + parity * slab);
+  };
   auto halo = [&](int r, int side, int parity) {
     return reinterpret_cast<float*>(static_cast<char*>(sh.halo.ptr[r]) + (side * 2 + parity) * cfg.bytes);
   };
@@ -266,7 +270,8 @@ int run_on_host(const Config& cfg) {
           const float* dn = r == 0 ? below : src + static_cast<size_t>(r - 1) * n;
           const float* up = r == R - 1 ? above : src + static_cast<size_t>(r + 1) * n;
           const float* ce = src + static_cast<size_t>(r) * n;
-          for (size_t j = 0; j < n; ++j) dst[static_cast<size_t>(r) * n + j] = host_stencil1(dn[j], ce[j], up[j], alpha, sc);
+          float* o = dst + static_cast<size_t>(r) * n;
+          for (size_t j = 0; j < n; ++j) o[j] = host_stencil1(dn[j], ce[j], up[j], alpha, sc);
         }
         if (push) {  // my new first row is the left neighbour's upper halo, my new last row the right one's lower halo
           std::copy(dst, dst + n, hi[out][left].begin());
@@ -318,7 +323,8 @@ int run_on_host(const Config& cfg) {
     if (FILE* f = std::fopen(cfg.json_path.c_str(), "a")) {
       std::fprintf(f,
                    "{\"pattern\":\"halo\",\"variant\":\"%s\",\"ranks\":%d,\"rows\":%d,\"bytes\":%zu,\"steps\":%d,"
-                   "\"ms_per_step\":%.6f,\"bus_GBps\":%.3f,\"per_gpu_per_dir_GBps\":%.3f,\"ctas\":0,\"mismatches\":%llu}\n",
+                   "\"ms_per_step\":%.6f,\"bus_GBps\":%.3f,\"per_gpu_per_dir_GBps\":%.3f,\"ctas\":0,"
+                   "\"mismatches\":%llu}\n",
                    what.c_str(), P, R, cfg.bytes, cfg.steps, ms_per_step, bus, bus / P / 2.0, total_bad);
       std::fclose(f);
     }
@@ -332,15 +338,15 @@ int main(int argc, char** argv) {
   hpcp::prefer_eager_module_loading();  // spin-waiting kernels + lazy module loading can deadlock (cuda_check.h)
   try {
     Config cfg;
-    static const option long_opts[] = {{"rows", required_argument, nullptr, 1},   {"bytes", required_argument, nullptr, 2},
-                                       {"steps", required_argument, nullptr, 3},  {"iters", required_argument, nullptr, 4},
-                                       {"warmup", required_argument, nullptr, 5}, {"mode", required_argument, nullptr, 6},
-                                       {"per-step", no_argument, nullptr, 7},     {"stock", required_argument, nullptr, 8},
-                                       {"ctas", required_argument, nullptr, 9},   {"tile-kb", required_argument, nullptr, 10},
-                                       {"stages", required_argument, nullptr, 11}, {"json", required_argument, nullptr, 12},
-                                       {"l2-hint", no_argument, nullptr, 13},      {"cpu", no_argument, nullptr, 14},
-                                       {"dump", required_argument, nullptr, 15},
-                                       {"help", no_argument, nullptr, 'h'},       {nullptr, 0, nullptr, 0}};
+    static const option long_opts[] = {
+        {"rows", required_argument, nullptr, 1}, {"bytes", required_argument, nullptr, 2},
+        {"steps", required_argument, nullptr, 3}, {"iters", required_argument, nullptr, 4},
+        {"warmup", required_argument, nullptr, 5}, {"mode", required_argument, nullptr, 6},
+        {"per-step", no_argument, nullptr, 7}, {"stock", required_argument, nullptr, 8},
+        {"ctas", required_argument, nullptr, 9}, {"tile-kb", required_argument, nullptr, 10},
+        {"stages", required_argument, nullptr, 11}, {"json", required_argument, nullptr, 12},
+        {"l2-hint", no_argument, nullptr, 13}, {"cpu", no_argument, nullptr, 14},
+        {"dump", required_argument, nullptr, 15}, {"help", no_argument, nullptr, 'h'}, {nullptr, 0, nullptr, 0}};
     int opt;
     while ((opt = getopt_long(argc, argv, "hn:", long_opts, nullptr)) != -1) {
       switch (opt) {
@@ -406,7 +412,8 @@ int main(int argc, char** argv) {
 
     const double ms_per_step = sh.best_ms / cfg.steps;
     const double bus = static_cast<double>(P) * 2.0 * static_cast<double>(cfg.bytes) / (ms_per_step * 1e6);
-    const std::string what = !cfg.stock.empty() ? "stock-" + cfg.stock : cfg.mode + (cfg.per_step ? "/per-step" : "/persistent");
+    const std::string what =
+        !cfg.stock.empty() ? "stock-" + cfg.stock : cfg.mode + (cfg.per_step ? "/per-step" : "/persistent");
     std::cout << "Elapsed (max over ranks, min of " << cfg.iters << "): " << sh.best_ms << " ms for " << cfg.steps
               << " steps = " << ms_per_step << " ms/step | halo " << what << " P=" << P << " rows=" << cfg.rows
               << " bytes=" << cfg.bytes << " ctas=" << sh.ctas << " | " << bus << " GB/s P2P bus (aggregate), "
@@ -415,7 +422,8 @@ int main(int argc, char** argv) {
       if (FILE* f = std::fopen(cfg.json_path.c_str(), "a")) {
         std::fprintf(f,
                      "{\"pattern\":\"halo\",\"variant\":\"%s\",\"ranks\":%d,\"rows\":%d,\"bytes\":%zu,\"steps\":%d,"
-                     "\"ms_per_step\":%.6f,\"bus_GBps\":%.3f,\"per_gpu_per_dir_GBps\":%.3f,\"ctas\":%d,\"mismatches\":%llu}\n",
+                     "\"ms_per_step\":%.6f,\"bus_GBps\":%.3f,\"per_gpu_per_dir_GBps\":%.3f,\"ctas\":%d,"
+                     "\"mismatches\":%llu}\n",
                      what.c_str(), P, cfg.rows, cfg.bytes, cfg.steps, ms_per_step, bus, bus / P / 2.0, sh.ctas,
                      sh.total_bad);
         std::fclose(f);
