@@ -124,3 +124,56 @@ def test_report_renders_tensor_parallel_and_gemm_rows(tmp_path):
     assert cells[2:6] == ["8", "8192", "8192", "28672"] and cells[8] == "2.00"
     assert "row_parallel_allreduce" not in text                      # unavailable rows are skipped
     assert "| 8192 | 8192 | 4096 | 2 | 1486 | 1600 | 1662 |" in text
+
+
+def test_clock_sampler_nvml_thread_with_a_fake_driver(monkeypatch):
+    """The NVML polling thread against a fake pynvml: handle by UUID, samples only while resumed (the bench keeps it
+    paused outside timed regions), throttle-reason bits decoded, median over the samples taken under load."""
+    import sys
+    import time
+    import types
+
+    from hpc_patterns_b200.utils.clocks import ClockSampler
+
+    state = {"clock": 1965, "power_mw": 900_000, "mask": 0, "by_uuid": 0, "by_index": 0, "reads": 0}
+    nv = types.ModuleType("pynvml")
+    nv.NVML_CLOCK_SM = 1
+    nv.nvmlInit = lambda: None
+
+    def by_uuid(u):
+        state["by_uuid"] += 1
+        assert u == b"GPU-1234"
+        return "handle"
+
+    def by_index(i):
+        state["by_index"] += 1
+        return "handle"
+
+    def clock(h, kind):
+        state["reads"] += 1
+        return state["clock"]
+    nv.nvmlDeviceGetHandleByUUID, nv.nvmlDeviceGetHandleByIndex = by_uuid, by_index
+    nv.nvmlDeviceGetMaxClockInfo = lambda h, kind: 1965
+    nv.nvmlDeviceGetClockInfo = clock
+    nv.nvmlDeviceGetPowerUsage = lambda h: state["power_mw"]
+    nv.nvmlDeviceGetCurrentClocksEventReasons = lambda h: state["mask"]
+    monkeypatch.setitem(sys.modules, "pynvml", nv)
+
+    s = ClockSampler(gpu_index=3, period_ms=0.2, uuid="GPU-1234").start(paused=True)
+    assert state["by_uuid"] == 1 and state["by_index"] == 0
+    time.sleep(0.05)
+    assert state["reads"] == 0, "paused: no NVML call may happen next to a timed region's barrier"
+    s.resume()
+    time.sleep(0.05)
+    state.update(clock=1800, mask=0x4)          # sw_power_cap appears while under load
+    time.sleep(0.05)
+    s.pause()
+    time.sleep(0.01)
+    n = state["reads"]
+    state.update(clock=210, power_mw=140_000, mask=0x8)   # idle again, and a reason that must NOT be recorded now
+    time.sleep(0.05)
+    assert state["reads"] == n
+    out = s.stop()
+    assert out["sampler"] == "nvml-thread" and out["samples"] == n > 10
+    assert out["sm_max_mhz"] == 1965 and out["sm_mhz"] in (1800, 1882.5, 1965)
+    assert out["reasons"] == ["sw_power_cap"] and out["power_w_max"] == 900.0
