@@ -191,3 +191,56 @@ def test_native_halo_host_path_matches_torch(bin_dir, tmp_path, mode, ranks, row
     got = torch.from_numpy(np.fromfile(dump, dtype=np.float32)).reshape(ranks * rows, row_bytes // 4)
     want = reference_steps(initial_field(ranks, rows, row_bytes // 4), steps * (iters + warmup))
     assert torch.equal(got, want), float((got - want).abs().max())
+
+
+def test_block_timer_order_of_operations_and_statistics(monkeypatch):
+    """What made round 1's driver numbers wrong was host work between the cross-rank barrier and the start event.  The
+    order in which a timed block touches the world is therefore a contract: synchronize, host barrier, DEVICE barrier
+    enqueued, start event, the work, stop event, synchronize, host barrier, status check — nothing else in between;
+    a measurement is the minimum over the blocks, every block is reported."""
+    from hpc_patterns_b200.utils import timing
+
+    log = []
+    times = iter([8.0, 50.0, 44.0, 40.0, 42.0, 41.0])       # pre-heat block, then five timed blocks (ms per block)
+
+    class Event:
+        made = 0
+
+        def __init__(self, enable_timing=False):
+            self.name = "e0" if Event.made % 2 == 0 else "e1"      # block_ms creates the start event, then the stop event
+            Event.made += 1
+
+        def record(self, stream):
+            log.append(self.name)
+
+        def elapsed_time(self, other):
+            assert (self.name, other.name) == ("e0", "e1")
+            return next(times)
+
+    class Comm:
+        def barrier(self):
+            log.append("host_barrier")
+
+        def max(self, v):
+            return v
+
+    class Pads:
+        def device_barrier(self, stream):
+            log.append("device_barrier")
+
+        def check(self):
+            log.append("check")
+
+    monkeypatch.setattr(timing.torch.cuda, "Event", Event)
+    monkeypatch.setattr(timing.torch.cuda, "synchronize", lambda d=None: log.append("sync"))
+    t = timing.BlockTimer.__new__(timing.BlockTimer)
+    t.comm, t.pads, t.device = Comm(), Pads(), 0
+    t.stream = type("S", (), {"cuda_stream": 0})()
+    m = t.measure(lambda: log.append("work"), units=20, blocks=5, preheat_ms=4.0)
+    block = ["sync", "host_barrier", "device_barrier", "e0", "work", "e1", "sync", "host_barrier", "check"]
+    assert log[:len(block)] == block                                   # the pre-heat block (8 ms >= 4 ms: no repeats)
+    assert log[len(block):len(block) + 3] == ["sync", "host_barrier", "check"]   # end of the pre-heat
+    timed = log[len(block) + 3:]
+    assert timed == block * 5
+    assert m["ms"] == 2.0 and m["max_ms"] == 2.5 and m["median_ms"] == 2.1
+    assert m["blocks_ms"] == [2.5, 2.2, 2.0, 2.1, 2.05] and m["spread_pct"] == 25.0
