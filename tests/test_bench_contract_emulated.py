@@ -97,3 +97,29 @@ def test_reference_arm_line(monkeypatch, capsys):
     # ranks other than 0 of a torchrun launch print nothing and exit 0
     monkeypatch.setenv("RANK", "3")
     assert bench.main() == 0 and capsys.readouterr().out == ""
+
+
+@pytest.mark.parametrize("flags,what", [([], "pull/persistent"), (["--mode", "push"], "push/persistent"),
+                                        (["--per-step"], "pull/per-step"), (["--stock", "memcpy"], "stock-memcpy"),
+                                        (["--mode", "push", "--l2-hint", "--ctas", "2"], "push/persistent")])
+def test_python_halo_program_report_lines(emu, monkeypatch, capsys, tmp_path, flags, what):  # noqa: F811
+    """`python -m hpc_patterns_b200 halo` (process-per-GPU twin of bin/halo) on the emulated device: the reference-style
+    report — `Passed <rank>`, the elapsed line, the JSON row — for every way of stepping."""
+    from hpc_patterns_b200.models import halo as halo_mod
+
+    emu.barrier_all = lambda pads, rank, epoch, timeout_ns, status, stream: None
+    monkeypatch.setattr(torch.cuda, "Event", TickingEvent)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "HPCP_DEVICE"):
+        monkeypatch.delenv(k, raising=False)
+    row = tmp_path / "rows.jsonl"
+    rc = halo_mod.main(["--rows", "3", "--bytes", "6144", "--steps", "4", "--iters", "2", "--tile-kb", "1", "--json",
+                        str(row)] + flags)
+    out = capsys.readouterr().out
+    assert rc == 0 and "Passed 0" in out
+    assert f"Elapsed (max over ranks, min of 2): 2.0000 ms for 4 steps = 0.50000 ms/step | halo {what} P=1 rows=3" in out
+    d = json.loads(row.read_text())
+    assert d["pattern"] == "halo" and d["variant"] == what and d["mismatches"] == 0 and d["ranks"] == 1
+    assert d["bus_GBps"] == pytest.approx(2 * 6144 / (0.5 * 1e6))
+    if "--ctas" in flags:
+        assert d["ctas"] == 2
+    assert not emu.live
