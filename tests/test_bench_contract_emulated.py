@@ -11,22 +11,10 @@ import sys
 import pytest
 import torch
 
-from tests.test_halo_python_emulated import EmuNative, emu  # noqa: F401  (the fixture)
+from tests.emu_device import TickingEvent
+from tests.test_halo_python_emulated import emu  # noqa: F401  (the fixture)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-
-
-class TickingEvent:
-    """cuda.Event stand-in: every start/stop pair reports 2 ms."""
-
-    def __init__(self, enable_timing=False):
-        pass
-
-    def record(self, stream=None):
-        pass
-
-    def elapsed_time(self, other):
-        return 2.0
 
 
 def _load_bench():
@@ -38,7 +26,6 @@ def _load_bench():
 
 @pytest.mark.parametrize("extras", [False, True])
 def test_bench_line_has_the_contract_keys(emu, monkeypatch, capsys, extras):  # noqa: F811
-    emu.barrier_all = lambda pads, rank, epoch, timeout_ns, status, stream: None
     monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
     monkeypatch.setattr(torch.cuda, "Event", TickingEvent)
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "HPCP_DEVICE"):
@@ -107,7 +94,6 @@ def test_python_halo_program_report_lines(emu, monkeypatch, capsys, tmp_path, fl
     report — `Passed <rank>`, the elapsed line, the JSON row — for every way of stepping."""
     from hpc_patterns_b200.models import halo as halo_mod
 
-    emu.barrier_all = lambda pads, rank, epoch, timeout_ns, status, stream: None
     monkeypatch.setattr(torch.cuda, "Event", TickingEvent)
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "HPCP_DEVICE"):
         monkeypatch.delenv(k, raising=False)
