@@ -17,7 +17,9 @@ import numpy as np
 import torch
 
 import hpc_patterns_b200
+from hpc_patterns_b200.models import allreduce as allreduce_mod
 from hpc_patterns_b200.models import halo as halo_mod
+from hpc_patterns_b200.models import peer2pear as peer2pear_mod
 from hpc_patterns_b200.models.halo import initial_field, reference_steps
 from hpc_patterns_b200.parallel import local as local_mod
 from hpc_patterns_b200.parallel import symmetric as symmetric_mod
@@ -96,6 +98,84 @@ class EmuNative:
         ctypes.memmove(dst, src, nbytes)
         if "signal_flag" in sync:
             _u32(sync["signal_flag"]).value = sync["signal_epoch"]
+        return 2
+
+    # ---- pure host helpers of the real extension ---------------------------------------------------
+    def elem_size(self, name):
+        return self.real.elem_size(name)
+
+    def ring_num_chunks(self, n, chunk_elems, elem_bytes=4):
+        return self.real.ring_num_chunks(n, chunk_elems, elem_bytes)
+
+    def multicast_supported(self, device):
+        return False                       # no switch to reduce in: `-a` must agree on two-shot
+
+    # ---- peer2pear payload ---------------------------------------------------------------------------
+    @staticmethod
+    def _pattern(n_words, seed):
+        i = np.arange(n_words, dtype=np.uint64)
+        return (((i * np.uint64(2654435761)) ^ np.uint64(seed)) & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+
+    def fill_pattern(self, dst, n_words, seed, stream):
+        np.ctypeslib.as_array((ctypes.c_uint32 * n_words).from_address(dst))[:] = self._pattern(n_words, seed)
+
+    def verify_pattern(self, data, n_words, seed, mismatch, word_sum=0, wait_flag=0, wait_epoch=0, timeout_ns=0,
+                       status=0, stream=0):
+        if wait_flag:
+            self._await(wait_flag, wait_epoch, "verify_pattern")
+        got = np.ctypeslib.as_array((ctypes.c_uint32 * n_words).from_address(data))
+        ctypes.c_int64.from_address(mismatch).value += int((got != self._pattern(n_words, seed)).sum())
+        if word_sum:
+            ctypes.c_int64.from_address(word_sum).value += int(got.astype(np.uint64).sum())
+
+    # ---- allreduce miniapp ---------------------------------------------------------------------------
+    _NP = {"float": np.float32, "int": np.int32, "uint": np.uint32, "double": np.float64, "long": np.int64,
+           "ulong": np.uint64, "short": np.int16, "ushort": np.uint16, "uchar": np.uint8}
+
+    def _arr(self, ptr, n, dtype):
+        t = self._NP[dtype]
+        return np.ctypeslib.as_array((ctypes.c_uint8 * (n * np.dtype(t).itemsize)).from_address(ptr)).view(t)
+
+    def init3(self, va, vb, vc, n, a, b, c, dtype, stream):
+        for ptr, v in ((va, a), (vb, b), (vc, c)):
+            if ptr:
+                self._arr(ptr, n, dtype)[:] = self._NP[dtype](v)
+
+    def accumulate(self, va, vc, n, dtype, stream):
+        self._arr(vc, n, dtype)[:] += self._arr(va, n, dtype)
+
+    def count_mismatch(self, v, n, expected, dtype, count, stream):
+        ctypes.c_int64.from_address(count).value += int((self._arr(v, n, dtype) != self._NP[dtype](expected)).sum())
+
+    def ring_allreduce(self, va, vc, slots_local, slots_right, arrived_local, arrived_right, world, n, chunk_elems,
+                       epoch_base, timeout_ns, status, dtype, ctas, device, stream, slots_policy=0, ack_local=0,
+                       ack_left=0, pull=False, va_left=0, slots_left=0):
+        """The faithful ring of the reference in one launch, default buffering (P-1 receive slots, hop t lands in slot
+        t-1): accumulate my block, forward what I hold, wait per chunk for what my left neighbour forwards."""
+        assert slots_policy == 0 and not pull, "the emulation covers the default ring"
+        esz = np.dtype(self._NP[dtype]).itemsize
+        chunks = self.ring_num_chunks(n, chunk_elems, esz)
+        acc = self._arr(vc, n, dtype)
+        for t in range(world):
+            if t > 0:
+                for c in range(chunks):
+                    self._await(arrived_local + 4 * c, epoch_base + t, f"ring hop {t}, chunk {c}")
+            src = self._arr(va if t == 0 else slots_local + (t - 1) * n * esz, n, dtype)
+            acc += src
+            if t + 1 < world:
+                self._arr(slots_right + t * n * esz, n, dtype)[:] = src
+                for c in range(chunks):
+                    _u32(arrived_right + 4 * c).value = epoch_base + t + 1
+
+    def allreduce_two_shot(self, va, vc, pads, ticket, ticket_base, rank, n, barrier_epoch, timeout_ns, status, dtype,
+                           ctas, device, stream):
+        world = len(va)
+        per = n // world
+        lo, hi = rank * per, (rank + 1) * per
+        total = sum(self._arr(p, n, dtype)[lo:hi].astype(self._NP[dtype]) for p in va)
+        for p in vc:
+            self._arr(p, n, dtype)[lo:hi] = total
+        self.barrier_all(pads, rank, barrier_epoch, timeout_ns, status, stream)
         return 2
 
     # ---- K-halo ------------------------------------------------------------------------------
@@ -258,7 +338,7 @@ class SharedEmuNative(EmuNative):
 
 def install(setattr_like, emu):
     """Point the package at the emulated device: native() -> emu, torch.cuda.* -> no-ops, 'cuda' tensors -> CPU."""
-    for mod in (halo_mod, local_mod, symmetric_mod):
+    for mod in (halo_mod, local_mod, symmetric_mod, allreduce_mod, peer2pear_mod):
         setattr_like(mod, "native", lambda: emu)
     view = (lambda ptr, nbytes, device, dtype=torch.uint8:
             torch.frombuffer((ctypes.c_uint8 * nbytes).from_address(ptr), dtype=torch.uint8).view(dtype))
@@ -269,6 +349,8 @@ def install(setattr_like, emu):
                        ("device", lambda d=None: contextlib.nullcontext()),
                        ("stream", lambda s=None: contextlib.nullcontext()), ("device_count", lambda: 1)):
         setattr_like(torch.cuda, name, fake)
+    setattr_like(torch.cuda.nvtx, "range_push", lambda msg: None)
+    setattr_like(torch.cuda.nvtx, "range_pop", lambda: None)
     real_zeros = torch.zeros
     setattr_like(torch, "zeros", lambda *a, **k: real_zeros(*a, **{**k, "device": "cpu"}))
     setattr_like(torch.Tensor, "pin_memory", lambda self: self)

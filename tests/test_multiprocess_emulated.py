@@ -44,6 +44,45 @@ def _ring_job(comm, emu, mode):
             "launches": [l[:3] for l in emu.launches[:4]]}
 
 
+def _p2p_job(comm, emu, transport):
+    """The peer2pear program's Python twin: pairs (2k, 2k+1), unidirectional then bidirectional, verified payload."""
+    from hpc_patterns_b200.models.peer2pear import P2PBench
+
+    bench = P2PBench(comm, comm.device, max_bytes=1 << 16, transport=transport, engine="tma", iters=3, label="emu",
+                     timeout_s=20.0)
+    out = []
+    for nbytes in (4096, 1 << 16):
+        r = bench.run(nbytes)
+        out.append({"bytes": nbytes, "mismatches": r.mismatches, "lines": r.lines(with_size=True),
+                    "row": r.row()})
+    launches = bench.launches
+    bench.close()
+    return {"runs": out, "launches": launches, "leaked": len(emu.live) + len(emu.opened)}
+
+
+def _allreduce_job(comm, emu, algo):
+    """The allreduce miniapp's Python twin: VA = rank, VC = 0 -> every element P(P-1)/2, float and int."""
+    import contextlib
+
+    from hpc_patterns_b200.models import allreduce as ar
+
+    if algo == "main-a":                                   # the program itself: -a must agree on two-shot (no multicast)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            rc = ar.main(["-a", "-p", "10", "--iters", "2", "--type", "int"])
+        return {"rc": rc, "stdout": buf.getvalue(), "leaked": len(emu.live) + len(emu.opened)}
+    res = []
+    # the stock-library rows go through gloo here, which has no 16-bit integer reduction
+    for dtype in ("float", "int", "double") + (() if algo in ("nccl", "ring-nccl") else ("short", "uchar")):
+        app = ar.AllreduceMiniapp(comm, comm.device, 10, dtype, algo, timeout_s=20.0)
+        with contextlib.redirect_stdout(io.StringIO()) as buf:
+            r = app.run(iters=2, warmup=1)
+        app.close()
+        res.append({"dtype": dtype, "mismatches": r.mismatches, "passed": f"Passed {comm.rank}" in buf.getvalue(),
+                    "launches": app.launches})
+    return {"results": res, "leaked": len(emu.live) + len(emu.opened)}
+
+
 def _bench_job(comm_unused, emu, extras):
     import importlib.util
 
@@ -79,10 +118,11 @@ def _worker(rank, world, port, job, arg, q):
         install(setattr, emu)
         torch.cuda.Event = TickingEvent
         torch.cuda.is_available = lambda: True
-        if job == "ring":
+        if job in ("ring", "p2p", "allreduce"):
             comm = Comm()
-            res = _ring_job(comm, emu, arg)
-            comm.close()
+            res = {"ring": _ring_job, "p2p": _p2p_job, "allreduce": _allreduce_job}[job](comm, emu, arg)
+            if not (job == "allreduce" and arg == "main-a"):       # main() closes the Comm it made
+                comm.close()
         else:
             res = _bench_job(None, emu, arg)
         dist.barrier()
@@ -139,3 +179,36 @@ def test_bench_line_at_two_ranks(extras, port):
         assert d["stock"]["wrong_words"] == 0
         assert d["stock"]["nccl_sendrecv_ms"] is not None or "nccl_error" in d
         assert d["speedup_vs_stock_memcpy"] > 0 and d["rows_1"]["wrong_words"] == 0
+
+
+@pytest.mark.parametrize("world,transport,port", [(2, "put", 29761), (2, "get", 29762), (2, "sendrecv", 29763),
+                                                  (4, "memcpy", 29764), (2, "nccl", 29765), (4, "hybrid", 29766)])
+def test_peer2pear_python_twin(world, transport, port):
+    res = _run(world, port, "p2p", transport)
+    for rank, r in res.items():
+        assert r["leaked"] == 0
+        for run in r["runs"]:
+            assert run["mismatches"] == 0, (rank, run)
+            assert run["row"]["ranks"] == world and run["row"]["transport"] == transport
+    lines = res[0]["runs"][1]["lines"]
+    assert any("Unidirectional Bandwidth:" in l for l in lines) and any("Bidirectional Bandwidth:" in l for l in lines)
+    assert all(r["launches"] > 0 for r in res.values()) or transport == "nccl"
+
+
+@pytest.mark.parametrize("world,algo,port", [(2, "ring", 29771), (4, "ring", 29772), (4, "ring-unfused", 29773),
+                                             (4, "twoshot", 29774), (2, "nccl", 29775), (3, "ring-nccl", 29776)])
+def test_allreduce_python_twin(world, algo, port):
+    res = _run(world, port, "allreduce", algo)
+    for rank, r in res.items():
+        assert r["leaked"] == 0
+        for x in r["results"]:
+            assert x["mismatches"] == 0 and x["passed"], (rank, x)
+
+
+def test_allreduce_program_dash_a_agrees_on_two_shot():
+    res = _run(4, 29781, "allreduce", "main-a")
+    assert all(r["rc"] == 0 and r["leaked"] == 0 for r in res.values())
+    assert "# -a: twoshot" in res[0]["stdout"] and "# -a:" not in res[1]["stdout"]
+    for rank, r in res.items():
+        assert f"Passed {rank}" in r["stdout"]
+    assert "Elapsed (max over ranks, min of 2)" in res[0]["stdout"]
